@@ -1,0 +1,144 @@
+/*
+ * mcmcb200.h -- C ABI of the B200-native batched adaptive Metropolis-Hastings path.
+ *
+ * This is the drop-in boundary for mcmcf90's sampling hot path.  In the reference the
+ * driver dispatches on `method` to MCMC_run / MCMC_run_ram / MCMC_run_scam
+ * (mcmc_main.F90:29-37), which run ONE chain on module-global state (mcmc.F90:28-60).
+ * Here the same dispatch point hands `nchains` independent chains to CUDA kernels; the
+ * host side (namelist, initialize, file output) stays where it is and talks to the
+ * device through the plain-C calls below (ISO_C_BINDING from Fortran, ctypes from
+ * Python, direct from C/C++).  No torch / C++ types cross this boundary.
+ *
+ * Conventions: every call returns 0 on success or a negative MCMCB_E* code and never
+ * exits the process (the reference `stop`s, e.g. matutils.F90:764-789).  The caller
+ * owns all host buffers.  One host thread per handle; one handle drives one GPU
+ * (multi-GPU = one handle per rank with chain_offset set).
+ * Matrices are column-major (Fortran) unless stated.
+ */
+#ifndef MCMCB200_H
+#define MCMCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCMCB_ABI_VERSION 1
+
+/* error codes */
+#define MCMCB_OK 0
+#define MCMCB_EINVAL (-1)       /* bad argument / call order */
+#define MCMCB_ECUDA (-2)        /* CUDA runtime error, see mcmcb_last_error */
+#define MCMCB_EUNSUPPORTED (-3) /* configuration the device path does not implement */
+#define MCMCB_ENOMODEL (-4)     /* unknown user model name */
+#define MCMCB_ENOMEM (-5)
+
+/* method (namelist `method`, mcmcinit.F90:60; dispatch mcmc_main.F90:29-37) */
+#define MCMCB_DRAM 0
+#define MCMCB_RAM 1
+#define MCMCB_SCAM 2
+
+/* rng_mode */
+#define MCMCB_RNG_PHILOX 0   /* Philox4x32-10 keyed by (seed, global chain id) -- replaces random_number */
+#define MCMCB_RNG_INJECTED 1 /* consume caller-provided uniforms in the reference's draw order */
+
+/* per-chain status bits (replace the reference's `stop`s) */
+#define MCMCB_ST_CHOLFAIL 1       /* Cholesky failed in adaptation: old R kept (MCMC_adapt.F90:169-171) */
+#define MCMCB_ST_DOWNDATE_FAIL 2  /* dchdd info=-1: update skipped (matutils.F90:716-722 stops) */
+#define MCMCB_ST_RNG_EXHAUSTED 4  /* injected uniform stream ran out */
+#define MCMCB_ST_SVDFAIL 8
+#define MCMCB_ST_STORE_FULL 16    /* stored chain rows exceeded nsimu */
+
+/* Mirror of namelist &mcmc (mcmcinit.F90:74-82; defaults 184-230), kernel-relevant
+ * fields, followed by the batch fields the reference does not have. */
+typedef struct mcmcb_config {
+  int abi_version; /* MCMCB_ABI_VERSION */
+  /* --- &mcmc --- */
+  int method;
+  int nsimu; /* chain length incl. the initial point; also the row capacity of stored chains */
+  int doadapt, adaptint, adapthist, adaptend, initcmatn;
+  int doburnin, burnintime, badaptint, greedy;
+  double scalelimit, scalefactor, drscale, condmax;
+  double N0, S02;
+  int updatesigma;
+  double alphatarget, nuparam;
+  /* --- &mcmcb (new) --- */
+  long long nchains;      /* chains owned by this handle */
+  long long chain_offset; /* global id of this handle's first chain (Philox stream id) */
+  unsigned long long seed;
+  int rng_mode;
+  int device;          /* CUDA device ordinal */
+  int store_chains;    /* run-length chain/sschain/s2chain kept in HBM for the first store_chains chains (-1 = all) */
+  int lanes_per_chain; /* 0 = auto; 1,2,4,8,16,32 lanes cooperate on one chain's ssfunction */
+  int dump_stride;     /* >0: every dump_stride steps all chains' theta are streamed to pinned host buffers */
+  int kernel;          /* 0 = auto; 1 = small-npar register kernel; 2 = large-npar warp kernel */
+  char model[32];      /* user-model name: "expreg", "gauss", "banana", "hier", or a plugin's name */
+} mcmcb_config;
+
+typedef struct mcmcb_handle_s* mcmcb_handle;
+
+/* namelist defaults, mcmcinit.F90:184-230 (MCMC_init_namelist) */
+int mcmcb_default_config(mcmcb_config* cfg);
+/* sanity rules + derived flags, mcmcinit.F90:235-368 (check_mcmcinit_parameters) */
+int mcmcb_check_config(mcmcb_config* cfg, int* dodr, int* doscam, int* usesvd);
+
+/* replaces the allocation half of MCMC_init (MCMC_init.F90:81-132) */
+int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out);
+int mcmcb_destroy(mcmcb_handle h); /* MCMC_cleanup, MCMC_aux.F90:90-118 */
+const char* mcmcb_last_error(mcmcb_handle h);
+
+/* user-model data (what the plugin's ssfunction loads on first call, e.g. data.dat at
+ * testcases/mcmcrun.F90:69-86).  Opaque blob of doubles, staged into shared memory. */
+int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t ndoubles);
+/* default Gaussian prior read from priorsfile (priorfun.f90:58-100): mu[npar], sig[npar]
+ * (sig<=0 disables a component).  NULL/NULL = flat prior. */
+int mcmcb_set_priors(mcmcb_handle h, const double* mu, const double* sig, int npar);
+/* what `initialize` returns (external_inc.h:33-42, initialize.F90:21-121):
+ * par0 is npar values shared by all chains (par0_stride==0) or nchains rows of
+ * par0_stride doubles; cmat0 is npar x npar column-major; sigma2/nobs have nycol entries. */
+int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const double* par0, long long par0_stride,
+                      const double* cmat0, const double* sigma2, const int* nobs);
+/* parity hook: u holds nchains rows of per_chain uniforms in [0,1), consumed in the
+ * reference's draw order instead of Philox. */
+int mcmcb_inject_uniforms(mcmcb_handle h, const double* u, size_t per_chain);
+
+/* advance every chain by nsteps iterations of MCMC_LOOP (MCMC_run.F90:41-107,
+ * MCMC_run_ram.F90:45-80, MCMC_run_scam.F90:38-88).  The first call also evaluates the
+ * initial point (MCMC_run.F90:27-36).  Asynchronous; mcmcb_sync waits. */
+int mcmcb_run(mcmcb_handle h, int nsteps);
+int mcmcb_sync(mcmcb_handle h);
+
+/* stored chain of one chain in the reference's layout (MCMC_aux.F90:166-185):
+ * chain is (ld x (npar+1)) column-major, last column = repeat count; sschain is
+ * (ld x (nycol+1)); s2chain is (ld x nycol) indexed by step (not compressed, Q16).
+ * *nrows receives chainind.  Any output pointer may be NULL. */
+int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                      double* s2chain_out, int* nrows);
+
+/* Per-chain state arrays, chain-major on the host side: out[chain * width + k].
+ *  "par" (npar) "ss" (nycol) "sspri" (1) "sigma2" (nycol) "mean" (npar) "wsum" (1)
+ *  "cmat" "R" "R2" "iC" (npar*npar, column-major, upper triangle authoritative)
+ *  "qcovstd" (npar)
+ *  "counters" (8 x int64: stayed, bndstayed, draccepted, drtries, chainind, simuind, status, ndrawn) */
+int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes);
+
+/* streamed dumps (MCMC_dump.F90:12-30 hook): pops the oldest completed snapshot of all
+ * chains' theta (nchains x npar, chain-major) from the pinned ring; returns 1 if one was
+ * copied, 0 if none pending. *step receives simuind of the snapshot. */
+int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step);
+
+/* introspection for measurement */
+void* mcmcb_stream(mcmcb_handle h);              /* cudaStream_t the kernels run on */
+long long mcmcb_launch_count(mcmcb_handle h);    /* kernels launched so far */
+int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes_per_chain, int* kernel, int* threads_per_block,
+               int* blocks, size_t* smem_bytes);
+/* FP64 pipe microbenchmark: dependent-free DFMA chains on every SM; returns measured
+ * TFLOP/s (2 flop per DFMA) and the elapsed milliseconds. */
+int mcmcb_dfma_peak(int device, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCMCB200_H */

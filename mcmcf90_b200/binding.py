@@ -1,0 +1,233 @@
+"""ctypes binding of include/mcmcb200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DRAM, RAM, SCAM = 0, 1, 2
+RNG_PHILOX, RNG_INJECTED = 0, 1
+METHODS = {"dram": DRAM, "am": DRAM, "ram": RAM, "scam": SCAM}
+ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "EUNSUPPORTED", -4: "ENOMODEL", -5: "ENOMEM"}
+COUNTER_NAMES = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "simuind", "status", "ndrawn"]
+
+EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_destroy", "mcmcb_last_error",
+           "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
+           "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
+           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak"]
+
+
+class MCMCBError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """mcmcb_config: namelist &mcmc (mcmcinit.F90:74-82) + batch fields."""
+    _fields_ = [
+        ("abi_version", C.c_int),
+        ("method", C.c_int), ("nsimu", C.c_int),
+        ("doadapt", C.c_int), ("adaptint", C.c_int), ("adapthist", C.c_int), ("adaptend", C.c_int),
+        ("initcmatn", C.c_int),
+        ("doburnin", C.c_int), ("burnintime", C.c_int), ("badaptint", C.c_int), ("greedy", C.c_int),
+        ("scalelimit", C.c_double), ("scalefactor", C.c_double), ("drscale", C.c_double), ("condmax", C.c_double),
+        ("N0", C.c_double), ("S02", C.c_double),
+        ("updatesigma", C.c_int),
+        ("alphatarget", C.c_double), ("nuparam", C.c_double),
+        ("nchains", C.c_longlong), ("chain_offset", C.c_longlong), ("seed", C.c_ulonglong),
+        ("rng_mode", C.c_int), ("device", C.c_int), ("store_chains", C.c_int), ("lanes_per_chain", C.c_int),
+        ("dump_stride", C.c_int), ("kernel", C.c_int),
+        ("model", C.c_char * 32),
+    ]
+
+
+def library_path():
+    return os.path.join(_HERE, "libmcmcb200.so")
+
+
+def load_library():
+    """Load the CUDA library; raise (never fall back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MCMCBError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.mcmcb_default_config.argtypes = [C.POINTER(Config)]
+    L.mcmcb_check_config.argtypes = [C.POINTER(Config), ip, ip, ip]
+    L.mcmcb_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.mcmcb_destroy.argtypes = [C.c_void_p]
+    L.mcmcb_last_error.argtypes = [C.c_void_p]
+    L.mcmcb_last_error.restype = C.c_char_p
+    L.mcmcb_set_data.argtypes = [C.c_void_p, dp, C.c_size_t]
+    L.mcmcb_set_priors.argtypes = [C.c_void_p, dp, dp, C.c_int]
+    L.mcmcb_set_initial.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.c_longlong, dp, dp, ip]
+    L.mcmcb_inject_uniforms.argtypes = [C.c_void_p, dp, C.c_size_t]
+    L.mcmcb_run.argtypes = [C.c_void_p, C.c_int]
+    L.mcmcb_sync.argtypes = [C.c_void_p]
+    L.mcmcb_fetch_chain.argtypes = [C.c_void_p, C.c_longlong, C.c_int, dp, dp, dp, ip]
+    L.mcmcb_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.mcmcb_dump_pop.argtypes = [C.c_void_p, dp, C.c_size_t, ip]
+    L.mcmcb_stream.argtypes = [C.c_void_p]
+    L.mcmcb_stream.restype = C.c_void_p
+    L.mcmcb_launch_count.argtypes = [C.c_void_p]
+    L.mcmcb_launch_count.restype = C.c_longlong
+    L.mcmcb_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_size_t)]
+    L.mcmcb_dfma_peak.argtypes = [C.c_int, dp, dp]
+    _LIB = L
+    return L
+
+
+def default_config(**kw):
+    """Namelist defaults (MCMC_init_namelist, mcmcinit.F90:184-230) overridden by keywords."""
+    c = Config()
+    load_library().mcmcb_default_config(C.byref(c))
+    for k, v in kw.items():
+        if k == "method" and isinstance(v, str):
+            v = METHODS[v.lower()]
+        if k == "model" and isinstance(v, str):
+            v = v.encode()
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    return c
+
+
+def dfma_peak(device=0):
+    t, ms = C.c_double(0), C.c_double(0)
+    rc = load_library().mcmcb_dfma_peak(device, C.byref(t), C.byref(ms))
+    if rc:
+        raise MCMCBError("mcmcb_dfma_peak failed: %s" % ERRORS.get(rc, rc))
+    return t.value, ms.value
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class Sampler:
+    """One handle = nchains independent chains on one GPU (replaces the module-global
+    single chain of mcmc.F90:28-60)."""
+
+    def __init__(self, cfg):
+        self.L = load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        self._chk(self.L.mcmcb_create(C.byref(cfg), C.byref(self.h)), "mcmcb_create")
+        self.nchains = int(cfg.nchains)
+        self.npar = self.nycol = None
+        self._keep = []
+
+    def _chk(self, rc, what):
+        if rc < 0:
+            msg = self.L.mcmcb_last_error(self.h).decode() if self.h else ""
+            raise MCMCBError("%s: %s %s" % (what, ERRORS.get(rc, rc), msg))
+        return rc
+
+    def set_data(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float64)
+        self._chk(self.L.mcmcb_set_data(self.h, _dp(blob), blob.size), "mcmcb_set_data")
+
+    def set_priors(self, mu, sig):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        self._chk(self.L.mcmcb_set_priors(self.h, _dp(mu), _dp(sig), mu.size), "mcmcb_set_priors")
+
+    def set_initial(self, par0, cmat0, sigma2, nobs):
+        """par0: (npar,) shared or (nchains, npar); cmat0 (npar,npar); sigma2, nobs (nycol,)."""
+        par0 = np.ascontiguousarray(par0, dtype=np.float64)
+        cmat0 = np.asfortranarray(np.asarray(cmat0, dtype=np.float64))
+        sigma2 = np.ascontiguousarray(np.atleast_1d(sigma2), dtype=np.float64)
+        nobs = np.ascontiguousarray(np.atleast_1d(nobs), dtype=np.int32)
+        npar = par0.shape[-1]
+        stride = 0 if par0.ndim == 1 else npar
+        if par0.ndim == 2 and par0.shape[0] != self.nchains:
+            raise ValueError("par0 must have nchains rows")
+        self.npar, self.nycol = int(npar), int(sigma2.size)
+        self._chk(self.L.mcmcb_set_initial(self.h, npar, sigma2.size, _dp(par0), stride, _dp(cmat0), _dp(sigma2),
+                                           nobs.ctypes.data_as(C.POINTER(C.c_int))), "mcmcb_set_initial")
+
+    def inject_uniforms(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if u.ndim == 1:
+            u = u.reshape(1, -1)
+        if u.shape[0] != self.nchains:
+            raise ValueError("u must have nchains rows")
+        self._chk(self.L.mcmcb_inject_uniforms(self.h, _dp(u), u.shape[1]), "mcmcb_inject_uniforms")
+
+    def run(self, nsteps, sync=True):
+        self._chk(self.L.mcmcb_run(self.h, int(nsteps)), "mcmcb_run")
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._chk(self.L.mcmcb_sync(self.h), "mcmcb_sync")
+
+    def fetch(self, what):
+        d, m, N = self.npar, self.nycol, self.nchains
+        if what == "counters":
+            out = np.zeros((N, 8), dtype=np.int64)
+        else:
+            width = {"par": d, "ss": m, "sspri": 1, "sigma2": m, "mean": d, "wsum": 1, "qcovstd": d,
+                     "cmat": d * d, "R": d * d, "R2": d * d, "iC": d * d}[what]
+            out = np.zeros((N, width))
+        self._chk(self.L.mcmcb_fetch(self.h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes),
+                  "mcmcb_fetch(%s)" % what)
+        if what in ("cmat", "R", "R2", "iC"):
+            out = out.reshape(N, d, d).transpose(0, 2, 1)  # column-major -> [chain, i, j]
+        return out
+
+    def counters(self):
+        c = self.fetch("counters")
+        return {k: c[:, i] for i, k in enumerate(COUNTER_NAMES)}
+
+    def fetch_chain(self, chain):
+        """Returns dict(chain=(rows, npar+1), sschain=(rows, nycol+1), s2chain=(simuind, nycol))."""
+        ld = int(self.cfg.nsimu)
+        d, m = self.npar, self.nycol
+        ch = np.zeros((ld, d + 1), order="F")
+        ss = np.zeros((ld, m + 1), order="F")
+        s2 = np.zeros((ld, m), order="F")
+        nrows = C.c_int(0)
+        self._chk(self.L.mcmcb_fetch_chain(self.h, chain, ld, _dp(ch), _dp(ss), _dp(s2), C.byref(nrows)),
+                  "mcmcb_fetch_chain")
+        n = nrows.value
+        return dict(chain=ch[:n].copy(), sschain=ss[:n].copy(), s2chain=s2.copy(), nrows=n)
+
+    def dump_pop(self):
+        out = np.zeros((self.nchains, self.npar))
+        step = C.c_int(0)
+        rc = self._chk(self.L.mcmcb_dump_pop(self.h, _dp(out), out.nbytes, C.byref(step)), "mcmcb_dump_pop")
+        return (step.value, out) if rc == 1 else None
+
+    @property
+    def stream(self):
+        return self.L.mcmcb_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.L.mcmcb_launch_count(self.h))
+
+    def info(self):
+        v = [C.c_int(0) for _ in range(6)]
+        sm = C.c_size_t(0)
+        self.L.mcmcb_info(self.h, *[C.byref(x) for x in v], C.byref(sm))
+        k = ["npar", "nycol", "lanes_per_chain", "kernel", "threads_per_block", "blocks"]
+        r = dict(zip(k, [x.value for x in v]))
+        r["smem_bytes"] = sm.value
+        return r
+
+    def close(self):
+        if self.h:
+            self.L.mcmcb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,657 @@
+// C ABI of the batched adaptive-MH path (include/mcmcb200.h): handle, model registry,
+// kernel launchers, state fetch, streamed dumps.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "k1_small.cuh"
+#include "mcmcb200.h"
+#include "models.cuh"
+#include "registry.h"
+
+using namespace mcmcb;
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                    \
+      return MCMCB_ECUDA;                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------ registry
+namespace mcmcb {
+std::vector<ModelEntry>& registry() {
+  static std::vector<ModelEntry> r;
+  return r;
+}
+int register_model(const ModelEntry& e) {
+  for (auto& x : registry())
+    if (std::strcmp(x.name, e.name) == 0 && x.kernel == e.kernel) {
+      x = e;
+      return 0;
+    }
+  registry().push_back(e);
+  return 0;
+}
+}  // namespace mcmcb
+
+// ------------------------------------------------------------------ K1 launcher
+namespace {
+
+template <class M>
+struct K1 {
+  static constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+
+  static K1Params params(mcmcb_handle h, int nsteps) {
+    K1Params p{};
+    p.c = h->dc;
+    p.nchains = h->cfg.nchains;
+    p.pitch = h->pitch;
+    p.chain_offset = h->cfg.chain_offset;
+    p.seed = h->cfg.seed;
+    p.nsteps = nsteps;
+    p.st = h->d_st;
+    p.ist = h->d_ist;
+    p.par0 = h->d_par0;
+    p.cmat0 = h->d_cmat0;
+    p.sigma2_0 = h->d_sigma2;
+    p.nobs = h->d_nobs;
+    p.blob = h->d_blob;
+    p.blob_n = h->blob_n;
+    p.blob_bytes = (unsigned)h->blob_bytes;
+    p.prior = h->d_prior;
+    p.inj = h->d_inj;
+    p.inj_per_chain = h->inj_per_chain;
+    p.store_chains = h->store_chains;
+    p.store_rows = h->cfg.nsimu;
+    p.store_rows_p = h->d_store_rows;
+    p.store_cnt_p = h->d_store_cnt;
+    p.store_s2_p = h->d_store_s2;
+    p.tile_counter = h->d_tile;
+    return p;
+  }
+
+  static int alloc(mcmcb_handle h) {
+    constexpr K1Layout Lo = k1_layout(D, NY);
+    h->nf = Lo.nf;
+    h->inf = Lo.i_nf;
+    h->pitch = ((h->cfg.nchains + 31) / 32) * 32;
+    CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
+    CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
+    if (h->store_chains > 0) {
+      size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
+      CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (D + NY)));
+      CK(cudaMalloc(&h->d_store_cnt, sizeof(double) * rows));
+      CK(cudaMalloc(&h->d_store_s2, sizeof(double) * rows * NY));
+      CK(cudaMemsetAsync(h->d_store_rows, 0, sizeof(double) * rows * (D + NY), h->stream));
+      CK(cudaMemsetAsync(h->d_store_cnt, 0, sizeof(double) * rows, h->stream));
+      CK(cudaMemsetAsync(h->d_store_s2, 0, sizeof(double) * rows * NY, h->stream));
+    }
+    return 0;
+  }
+
+  static int init(mcmcb_handle h) {
+    K1Params p = params(h, 0);
+    int threads = 256;
+    long long blocks = (h->cfg.nchains + threads - 1) / threads;
+    k1_init_kernel<M><<<(unsigned)blocks, threads, 0, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <int L, bool SMEM>
+  static int launch_LS(mcmcb_handle h, const K1Params& p) {
+    auto kern = k1_step_kernel<M, L, SMEM>;
+    size_t smem = SMEM ? h->blob_bytes : 0;
+    if (!h->attr_set) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
+      if (occ < 1) occ = 1;
+      h->occ = occ;
+      h->attr_set = true;
+    }
+    long long tiles = (h->cfg.nchains * L + 31) / 32;
+    long long wpb = K1_THREADS / 32;
+    long long need = (tiles + wpb - 1) / wpb;
+    long long blocks = std::min<long long>((long long)h->num_sms * h->occ, need);
+    if (blocks < 1) blocks = 1;
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
+    kern<<<(unsigned)blocks, K1_THREADS, smem, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <int L>
+  static int launch_L(mcmcb_handle h, const K1Params& p) {
+    if (h->smem_blob) return launch_LS<L, true>(h, p);
+    return launch_LS<L, false>(h, p);
+  }
+
+  static int step(mcmcb_handle h, int nsteps) {
+    K1Params p = params(h, nsteps);
+    switch (h->L) {
+      case 1: return launch_L<1>(h, p);
+      case 2: return launch_L<2>(h, p);
+      case 4: return launch_L<4>(h, p);
+      case 8: return launch_L<8>(h, p);
+      case 16: return launch_L<16>(h, p);
+      default: return launch_L<32>(h, p);
+    }
+  }
+
+  static ModelEntry entry() {
+    ModelEntry e{};
+    e.name = M::name();
+    e.kernel = 1;
+    e.npar = D;
+    e.ny = NY;
+    e.alloc = &alloc;
+    e.init = &init;
+    e.step = &step;
+    return e;
+  }
+};
+
+struct BuiltinRegistrar {
+  BuiltinRegistrar() { register_model(K1<ExpReg>::entry()); }
+} builtin_registrar;
+
+const ModelEntry* find_model(const char* name, int kernel) {
+  for (auto& e : registry())
+    if (std::strcmp(e.name, name) == 0 && (kernel == 0 || e.kernel == kernel)) return &e;
+  return nullptr;
+}
+
+int pick_lanes(mcmcb_handle h) {
+  int L = h->cfg.lanes_per_chain;
+  if (L == 1 || L == 2 || L == 4 || L == 8 || L == 16 || L == 32) return L;
+  // auto: smallest group size that still fills every SM with K1_THREADS resident threads
+  long long fill = (long long)h->num_sms * K1_THREADS;
+  L = 1;
+  while (L < 32 && h->cfg.nchains * L < fill) L *= 2;
+  return L;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ config
+extern "C" int mcmcb_default_config(mcmcb_config* c) {  // mcmcinit.F90:184-230
+  if (!c) return MCMCB_EINVAL;
+  std::memset(c, 0, sizeof *c);
+  c->abi_version = MCMCB_ABI_VERSION;
+  c->method = MCMCB_DRAM;
+  c->nsimu = 0;
+  c->doadapt = 1;
+  c->doburnin = 0;
+  c->burnintime = 0;
+  c->badaptint = -1;
+  c->greedy = 0;
+  c->scalelimit = 0.05;
+  c->scalefactor = 2.5;
+  c->drscale = 0.0;
+  c->adaptint = 100;
+  c->adapthist = 0;
+  c->adaptend = 0;
+  c->initcmatn = 0;
+  c->N0 = 1.0;
+  c->S02 = 0.0;
+  c->updatesigma = 1;
+  c->condmax = 0.0;
+  c->alphatarget = 0.234;
+  c->nuparam = 0.7;
+  c->nchains = 1;
+  c->chain_offset = 0;
+  c->seed = 0;
+  c->rng_mode = MCMCB_RNG_PHILOX;
+  c->device = 0;
+  c->store_chains = 0;
+  c->lanes_per_chain = 0;
+  c->dump_stride = 0;
+  c->kernel = 0;
+  std::strcpy(c->model, "expreg");
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_check_config(mcmcb_config* c, int* dodr, int* doscam, int* usesvd) {  // mcmcinit.F90:235-368
+  if (!c) return MCMCB_EINVAL;
+  if (c->adapthist < 0) c->adapthist = 0;
+  if (c->adaptint < 0) { c->adaptint = 0; c->doadapt = 0; }
+  if (c->burnintime < 0) c->burnintime = 0;
+  if (c->badaptint <= 0) c->badaptint = c->adaptint;
+  if (c->badaptint == 0) c->doburnin = 0;
+  if (c->initcmatn < 0) c->initcmatn = 0;
+  if (c->scalelimit < 0.0 || c->scalelimit > 0.5) return MCMCB_EINVAL;  // reference stops, :254-257
+  if (c->scalefactor < 0.0) c->scalefactor = 1.0;
+  int sc = 0;
+  if (c->method == MCMCB_SCAM) {
+    sc = 1;
+    if (c->condmax <= 0.0) c->condmax = 1.0e15;
+    c->doburnin = 0;
+    c->drscale = 0.0;
+  }
+  if (c->method == MCMCB_RAM) c->drscale = 0.0;
+  if (dodr) *dodr = c->drscale > 0.0;
+  if (doscam) *doscam = sc;
+  if (usesvd) *usesvd = c->condmax > 0.0;
+  return MCMCB_OK;
+}
+
+// ------------------------------------------------------------------ lifecycle
+extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
+  if (!cfg || !out || cfg->abi_version != MCMCB_ABI_VERSION || cfg->nchains < 1 || cfg->nsimu < 1) return MCMCB_EINVAL;
+  mcmcb_handle h = new mcmcb_handle_s();
+  h->cfg = *cfg;
+  int rc = mcmcb_check_config(&h->cfg, &h->dodr, &h->doscam, &h->usesvd);
+  if (rc) { delete h; return rc; }
+  const mcmcb_config& c = h->cfg;
+  // configurations that need the stored row history of the reference (AP)
+  if (c.method == MCMCB_DRAM && (c.adapthist > 1 || (c.greedy && c.doburnin)) ) { delete h; return MCMCB_EUNSUPPORTED; }
+  if (c.method == MCMCB_DRAM && h->usesvd) { delete h; return MCMCB_EUNSUPPORTED; }
+  if (c.method == MCMCB_SCAM) { delete h; return MCMCB_EUNSUPPORTED; }
+  h->model = find_model(c.model, c.kernel);
+  if (!h->model) { delete h; return MCMCB_ENOMODEL; }
+  DevCfg& d = h->dc;
+  d.method = c.method; d.nsimu = c.nsimu; d.doadapt = c.doadapt; d.adaptint = c.adaptint; d.adapthist = c.adapthist;
+  d.adaptend = c.adaptend; d.initcmatn = c.initcmatn; d.doburnin = c.doburnin; d.burnintime = c.burnintime;
+  d.badaptint = c.badaptint; d.greedy = c.greedy; d.updatesigma = c.updatesigma; d.dodr = h->dodr;
+  d.doscam = h->doscam; d.usesvd = h->usesvd; d.scalelimit = c.scalelimit; d.scalefactor = c.scalefactor;
+  d.drscale = c.drscale; d.condmax = c.condmax; d.N0 = c.N0; d.S02 = c.S02; d.alphatarget = c.alphatarget;
+  d.nuparam = c.nuparam;
+  if (cudaSetDevice(c.device) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
+  h->num_sms = prop.multiProcessorCount;
+  h->max_smem = (size_t)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
+  h->store_chains = c.store_chains < 0 ? (int)std::min<long long>(c.nchains, 1 << 30) : (int)std::min<long long>(c.store_chains, c.nchains);
+  h->npar = h->model->npar;
+  h->nycol = h->model->ny;
+  *out = h;
+  return MCMCB_OK;
+}
+
+static void free_dev(mcmcb_handle h) {
+  void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
+                  h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& s : h->dump_slots) {
+    if (s.dev) cudaFree(s.dev);
+    if (s.host) cudaFreeHost(s.host);
+    if (s.ev) cudaEventDestroy(s.ev);
+    if (s.ready) cudaEventDestroy(s.ready);
+  }
+}
+
+extern "C" int mcmcb_destroy(mcmcb_handle h) {
+  if (!h) return MCMCB_EINVAL;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_stream);
+  free_dev(h);
+  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return MCMCB_OK;
+}
+
+extern "C" const char* mcmcb_last_error(mcmcb_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
+  if (!h || !blob || n == 0) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->d_blob) { cudaFree(h->d_blob); h->d_blob = nullptr; }
+  size_t bytes = ((n * sizeof(double) + 15) / 16) * 16;
+  CK(cudaMalloc(&h->d_blob, bytes));
+  CK(cudaMemsetAsync(h->d_blob, 0, bytes, h->stream));
+  CK(cudaMemcpyAsync(h->d_blob, blob, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->blob_n = n;
+  h->blob_bytes = bytes;
+  // TMA-stage the blob into shared memory when it fits beside the kernel's static smem
+  h->smem_blob = bytes + 1024 <= h->max_smem;
+  h->attr_set = false;
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_set_priors(mcmcb_handle h, const double* mu, const double* sig, int npar) {
+  if (!h) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->d_prior) { cudaFree(h->d_prior); h->d_prior = nullptr; }
+  if (!mu || !sig) return MCMCB_OK;
+  if (npar != h->npar && h->npar > 0) return MCMCB_EINVAL;
+  std::vector<double> buf(2 * (size_t)npar);
+  std::copy(mu, mu + npar, buf.begin());
+  std::copy(sig, sig + npar, buf.begin() + npar);
+  CK(cudaMalloc(&h->d_prior, sizeof(double) * buf.size()));
+  CK(cudaMemcpy(h->d_prior, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const double* par0, long long par0_stride,
+                                 const double* cmat0, const double* sigma2, const int* nobs) {
+  if (!h || !par0 || !cmat0 || !sigma2 || !nobs || npar < 1 || nycol < 1) return MCMCB_EINVAL;
+  if (h->model->npar > 0 && npar != h->model->npar) return MCMCB_EINVAL;
+  if (nycol != h->model->ny) return MCMCB_EINVAL;
+  if (par0_stride != 0 && par0_stride < npar) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  h->npar = npar;
+  h->nycol = nycol;
+  const long long N = h->cfg.nchains;
+  if (!h->d_par0) CK(cudaMalloc(&h->d_par0, sizeof(double) * (size_t)N * npar));
+  if (par0_stride == npar) {
+    CK(cudaMemcpyAsync(h->d_par0, par0, sizeof(double) * (size_t)N * npar, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    h->h_tmp.resize((size_t)N * npar);
+    for (long long c = 0; c < N; c++)
+      for (int k = 0; k < npar; k++) h->h_tmp[(size_t)c * npar + k] = par0[(size_t)c * par0_stride + k];
+    CK(cudaMemcpyAsync(h->d_par0, h->h_tmp.data(), sizeof(double) * (size_t)N * npar, cudaMemcpyHostToDevice, h->stream));
+  }
+  // packed upper triangle of cmat0 (column-major input; the upper part is authoritative, matutils.F90:73-75)
+  int T = npar * (npar + 1) / 2;
+  std::vector<double> pkd((size_t)T);
+  for (int j = 0; j < npar; j++)
+    for (int i = 0; i <= j; i++) pkd[(size_t)j * (j + 1) / 2 + i] = cmat0[(size_t)j * npar + i];
+  if (!h->d_cmat0) CK(cudaMalloc(&h->d_cmat0, sizeof(double) * T));
+  if (!h->d_sigma2) CK(cudaMalloc(&h->d_sigma2, sizeof(double) * nycol));
+  if (!h->d_nobs) CK(cudaMalloc(&h->d_nobs, sizeof(int) * nycol));
+  if (!h->d_tile) CK(cudaMalloc(&h->d_tile, sizeof(unsigned) * 4));
+  CK(cudaMemcpyAsync(h->d_cmat0, pkd.data(), sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_sigma2, sigma2, sizeof(double) * nycol, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_nobs, nobs, sizeof(int) * nycol, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->dc.S02 <= 0.0) h->dc.S02 = sigma2[0];  // MCMC_init.F90:114-116
+  if (!h->d_st) {
+    int rc = h->model->alloc(h);
+    if (rc) return rc;
+  }
+  h->L = pick_lanes(h);
+  int rc = h->model->init(h);
+  if (rc) return rc;
+  h->initial_set = true;
+  h->steps_done = 0;
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_inject_uniforms(mcmcb_handle h, const double* u, size_t per_chain) {
+  if (!h) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->d_inj) { cudaFree(h->d_inj); h->d_inj = nullptr; }
+  h->inj_per_chain = 0;
+  if (!u || per_chain == 0) return MCMCB_OK;
+  size_t n = (size_t)h->cfg.nchains * per_chain;
+  CK(cudaMalloc(&h->d_inj, sizeof(double) * n));
+  CK(cudaMemcpy(h->d_inj, u, sizeof(double) * n, cudaMemcpyHostToDevice));
+  h->inj_per_chain = per_chain;
+  return MCMCB_OK;
+}
+
+// ------------------------------------------------------------------ streamed dumps
+static int dump_enqueue(mcmcb_handle h) {
+  // snapshot theta (field-major, npar x pitch) device->device on the compute stream, then
+  // device->pinned host on the copy stream, so the next launch overlaps the PCIe copy
+  const size_t bytes = sizeof(double) * (size_t)h->npar * h->pitch;
+  if (h->dump_slots.empty()) {
+    h->dump_slots.resize(4);
+    for (auto& s : h->dump_slots) {
+      CK(cudaMalloc(&s.dev, bytes));
+      CK(cudaMallocHost(&s.host, bytes));
+      CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+      s.state = 0;
+    }
+  }
+  int k = h->dump_head % (int)h->dump_slots.size();
+  auto& s = h->dump_slots[k];
+  if (s.state != 0) {  // ring full: oldest snapshot is overwritten
+    CK(cudaEventSynchronize(s.ev));
+    for (auto it = h->dump_fifo.begin(); it != h->dump_fifo.end(); ++it)
+      if (*it == k) { h->dump_fifo.erase(it); break; }
+    h->dumps_dropped++;
+  }
+  CK(cudaMemcpyAsync(s.dev, h->d_st /* theta is field 0 */, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(s.ready, h->stream));
+  CK(cudaStreamWaitEvent(h->copy_stream, s.ready, 0));
+  CK(cudaMemcpyAsync(s.host, s.dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+  CK(cudaEventRecord(s.ev, h->copy_stream));
+  s.state = 1;
+  s.step = 1 + (int)h->steps_done;
+  h->dump_fifo.push_back(k);
+  h->dump_head++;
+  return 0;
+}
+
+extern "C" int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step) {
+  if (!h || !out) return MCMCB_EINVAL;
+  if (h->dump_fifo.empty()) return 0;
+  int k = h->dump_fifo.front();
+  auto& s = h->dump_slots[k];
+  if (cudaEventQuery(s.ev) != cudaSuccess) return 0;
+  const long long N = h->cfg.nchains;
+  if (out_bytes < sizeof(double) * (size_t)N * h->npar) return MCMCB_EINVAL;
+  for (int f = 0; f < h->npar; f++)
+    for (long long c = 0; c < N; c++) out[(size_t)c * h->npar + f] = s.host[(size_t)f * h->pitch + c];
+  if (step) *step = s.step;
+  s.state = 0;
+  h->dump_fifo.pop_front();
+  return 1;
+}
+
+// ------------------------------------------------------------------ run
+extern "C" int mcmcb_run(mcmcb_handle h, int nsteps) {
+  if (!h || nsteps < 0) return MCMCB_EINVAL;
+  if (!h->initial_set || !h->d_blob) return MCMCB_EINVAL;
+  if (h->cfg.rng_mode == MCMCB_RNG_INJECTED && !h->d_inj) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  int left = nsteps;
+  const int stride = h->cfg.dump_stride;
+  do {
+    int n = left;
+    if (stride > 0) {
+      int to_next = stride - (int)(h->steps_done % stride);
+      n = std::min(left, to_next);
+    }
+    int rc = h->model->step(h, n);
+    if (rc) return rc;
+    h->steps_done += n;
+    left -= n;
+    if (stride > 0 && h->steps_done % stride == 0 && n > 0) {
+      rc = dump_enqueue(h);
+      if (rc) return rc;
+    }
+  } while (left > 0);
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_sync(mcmcb_handle h) {
+  if (!h) return MCMCB_EINVAL;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->copy_stream));
+  return MCMCB_OK;
+}
+
+// ------------------------------------------------------------------ fetch
+static int fetch_fields(mcmcb_handle h, int f0, int nf, std::vector<double>& buf) {
+  buf.resize((size_t)nf * h->pitch);
+  CK(cudaMemcpyAsync(buf.data(), h->d_st + (size_t)f0 * h->pitch, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
+  if (!h || !what || !out || !h->d_st) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const long long N = h->cfg.nchains;
+  const int D = h->npar, NY = h->nycol, T = D * (D + 1) / 2;
+  const K1Layout Lo = k1_layout(D, NY);
+  std::string w(what);
+  std::vector<double> buf;
+  if (w == "counters") {
+    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
+    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
+    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long* o = (long long*)out;
+    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+    for (long long c = 0; c < N; c++) {
+      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
+      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
+      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+    }
+    return MCMCB_OK;
+  }
+  int f0 = -1, width = 0;
+  bool tri = false;
+  if (w == "par") { f0 = Lo.th; width = D; }
+  else if (w == "ss") { f0 = Lo.ss; width = NY; }
+  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
+  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
+  else if (w == "mean") { f0 = Lo.mean; width = D; }
+  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
+  else if (w == "cmat") { f0 = Lo.cm; tri = true; }
+  else if (w == "R") { f0 = Lo.r; tri = true; }
+  else if (w == "R2") { f0 = Lo.r2; tri = true; }
+  else if (w == "iC") { f0 = Lo.ic; tri = true; }
+  else return MCMCB_EINVAL;
+  double* o = (double*)out;
+  if (!tri) {
+    if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
+    int rc = fetch_fields(h, f0, width, buf);
+    if (rc) return rc;
+    for (int k = 0; k < width; k++)
+      for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
+  } else {
+    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
+    int rc = fetch_fields(h, f0, T, buf);
+    if (rc) return rc;
+    const bool sym = (w == "cmat" || w == "iC");
+    for (long long c = 0; c < N; c++)
+      for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+          double v = 0.0;
+          if (i <= j) v = buf[(size_t)(j * (j + 1) / 2 + i) * h->pitch + c];
+          else if (sym) v = buf[(size_t)(i * (i + 1) / 2 + j) * h->pitch + c];
+          o[(size_t)c * D * D + (size_t)j * D + i] = v;  // column-major
+        }
+  }
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                                 double* s2chain_out, int* nrows) {
+  if (!h || !h->d_st || chain < 0 || chain >= h->store_chains) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const int D = h->npar, NY = h->nycol, cap = h->cfg.nsimu;
+  const K1Layout Lo = k1_layout(D, NY);
+  int iv[3];
+  const int fld[3] = {Lo.i_chainind, Lo.i_cnt, Lo.i_simuind};
+  for (int k = 0; k < 3; k++)
+    CK(cudaMemcpyAsync(&iv[k], h->d_ist + (size_t)fld[k] * h->pitch + chain, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int rows = std::min(iv[0], cap), cnt = iv[1], simuind = iv[2];
+  if (nrows) *nrows = rows;
+  if (ld < rows || (s2chain_out && ld < simuind)) return MCMCB_EINVAL;
+  std::vector<double> r((size_t)rows * (D + NY)), cn((size_t)rows), s2((size_t)std::max(simuind, 1) * NY);
+  if (rows > 0) {
+    CK(cudaMemcpyAsync(r.data(), h->d_store_rows + (size_t)chain * cap * (D + NY), sizeof(double) * r.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cn.data(), h->d_store_cnt + (size_t)chain * cap, sizeof(double) * cn.size(), cudaMemcpyDeviceToHost,
+                       h->stream));
+  }
+  if (s2chain_out && simuind > 0)
+    CK(cudaMemcpyAsync(s2.data(), h->d_store_s2 + (size_t)chain * cap * NY, sizeof(double) * (size_t)simuind * NY,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (rows > 0) cn[rows - 1] = (double)cnt;  // the current row's count lives in the chain state
+  for (int i = 0; i < rows; i++) {
+    if (chain_out) {
+      for (int k = 0; k < D; k++) chain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + k];
+      chain_out[(size_t)D * ld + i] = cn[i];
+    }
+    if (sschain_out) {
+      for (int k = 0; k < NY; k++) sschain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + D + k];
+      sschain_out[(size_t)NY * ld + i] = cn[i];
+    }
+  }
+  if (s2chain_out)
+    for (int i = 0; i < simuind; i++)
+      for (int k = 0; k < NY; k++) s2chain_out[(size_t)k * ld + i] = s2[(size_t)i * NY + k];
+  return MCMCB_OK;
+}
+
+// ------------------------------------------------------------------ introspection
+extern "C" void* mcmcb_stream(mcmcb_handle h) { return h ? (void*)h->stream : nullptr; }
+extern "C" long long mcmcb_launch_count(mcmcb_handle h) { return h ? h->launches : 0; }
+extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int* kernel, int* tpb, int* blocks,
+                          size_t* smem) {
+  if (!h) return MCMCB_EINVAL;
+  if (npar) *npar = h->npar;
+  if (nycol) *nycol = h->nycol;
+  if (lanes) *lanes = h->L;
+  if (kernel) *kernel = h->model ? h->model->kernel : 0;
+  if (tpb) *tpb = K1_THREADS;
+  if (blocks) *blocks = h->blocks;
+  if (smem) *smem = h->smem;
+  return MCMCB_OK;
+}
+
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int mcmcb_dfma_peak(int device, double* tflops, double* ms_out) {
+  if (cudaSetDevice(device) != cudaSuccess) return MCMCB_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MCMCB_ECUDA;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return MCMCB_ECUDA;
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 20000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dfma_peak_kernel<<<blocks, threads>>>(d, 2000, 0.999999, 1e-7);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e != cudaSuccess) return MCMCB_ECUDA;
+  double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return MCMCB_OK;
+}

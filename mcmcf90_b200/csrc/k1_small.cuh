@@ -1,0 +1,640 @@
+// K1: small-npar register-resident sampler.
+//
+// One chain is owned by a group of L lanes (L = 1..32, power of two).  Every lane of the
+// group carries the chain's whole state in registers (theta, ss, sigma2, packed upper
+// factors R/R2/iC, streaming mean/covariance, counters, RNG position); the lanes only
+// split the data loop of ssfunction and add their partial sums with warp shuffles.  The
+// user-model blob is staged ONCE per CTA into shared memory by TMA (cp.async.bulk) and
+// reused by every chain the CTA processes.  Chain state lives in HBM as structure of
+// arrays (field-major, chain contiguous) and is touched only at launch begin / end: a
+// launch advances every chain by `nsteps` iterations of MCMC_LOOP.
+//
+// Lanes run a per-chain state machine whose only warp-converged section is the model
+// evaluation: phase -1 = initial point (MCMC_run.F90:27-36), 0 = first-stage proposal,
+// 1 = delayed-rejection second stage (MCMC_run.F90:65-91).  A lane whose first stage was
+// accepted starts its next step while its neighbour evaluates a DR proposal, so no lane
+// idles in the hot loop because of DR divergence.
+//
+// Reference map: loop MCMC_run.F90:41-107 / MCMC_run_ram.F90:45-80; primitives
+// MCMC_DRAM.F90; adaptation MCMC_adapt.F90:12-174,181-230 in streaming form (see
+// absorb()); covmat recursion matutils.F90:283-310; dpotf2/dpotri order as unblocked
+// LAPACK; dchud.f:122-139, dchdd.f:141-179.
+#pragma once
+#include "common.cuh"
+
+namespace mcmcb {
+
+constexpr int K1_THREADS = 512;
+
+// field offsets of the SoA state (doubles and ints), shared by host and device
+struct K1Layout {
+  int th, ss, pri, s2, r, r2, ic, cm, mean, wsum, spare, rama, nf;
+  int i_stayed, i_bnd, i_dracc, i_drtry, i_chainind, i_simuind, i_status, i_hasspare, i_cnt, i_pend, i_ndlo, i_ndhi,
+      i_nf;
+};
+__host__ __device__ constexpr K1Layout k1_layout(int D, int NY) {
+  K1Layout l{};
+  int T = D * (D + 1) / 2;
+  int o = 0;
+  l.th = o; o += D;
+  l.ss = o; o += NY;
+  l.pri = o; o += 1;
+  l.s2 = o; o += NY;
+  l.r = o; o += T;
+  l.r2 = o; o += T;
+  l.ic = o; o += T;
+  l.cm = o; o += T;
+  l.mean = o; o += D;
+  l.wsum = o; o += 1;
+  l.spare = o; o += 1;
+  l.rama = o; o += 1;
+  l.nf = o;
+  int k = 0;
+  l.i_stayed = k++; l.i_bnd = k++; l.i_dracc = k++; l.i_drtry = k++; l.i_chainind = k++; l.i_simuind = k++;
+  l.i_status = k++; l.i_hasspare = k++; l.i_cnt = k++; l.i_pend = k++; l.i_ndlo = k++; l.i_ndhi = k++;
+  l.i_nf = k;
+  return l;
+}
+
+struct K1Params {
+  DevCfg c;
+  long long nchains, pitch, chain_offset;
+  unsigned long long seed;
+  int nsteps;
+  double* st;  // [field][pitch]
+  int* ist;    // [field][pitch]
+  const double* par0;       // [nchains][D]
+  const double* cmat0;      // packed upper, T doubles
+  const double* sigma2_0;   // NY
+  const int* nobs;          // NY
+  const double* blob;       // global copy of the model blob
+  unsigned long long blob_n;  // doubles
+  unsigned blob_bytes;      // padded to 16
+  const double* prior;      // mu[D], sig[D] or nullptr
+  const double* inj;        // [nchains][inj_per_chain] or nullptr
+  unsigned long long inj_per_chain;
+  // stored run-length chains (first store_chains chains)
+  int store_chains, store_rows;
+  double* store_rows_p;     // [chain][row][D+NY]
+  double* store_cnt_p;      // [chain][row]
+  double* store_s2_p;       // [chain][step][NY]
+  unsigned int* tile_counter;
+};
+
+__host__ __device__ constexpr int pk(int i, int j) { return j * (j + 1) / 2 + i; }  // i <= j
+
+// R = chol(cm)*2.4/sqrt(D); iC = inv(R'R); R2 = R/drscale.  MCMC_adapt.F90:181-230 with
+// covtor (matutils.F90:345-374) = dpotf2('U') and dpotri('U') = dtrti2 + dlauu2.
+// Returns false (and leaves R,R2,iC untouched) if the factorisation fails.
+template <int D>
+__device__ __forceinline__ bool calculate_R(const double (&cm)[D * (D + 1) / 2], double (&R)[D * (D + 1) / 2],
+                                            double (&R2)[D * (D + 1) / 2], double (&iC)[D * (D + 1) / 2],
+                                            const DevCfg& c) {
+  constexpr int T = D * (D + 1) / 2;
+  double A[T];
+#pragma unroll
+  for (int k = 0; k < T; k++) A[k] = cm[k];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < j; i++) t += A[pk(i, j)] * A[pk(i, j)];
+    double ajj = A[pk(j, j)] - t;
+    if (!(ajj > 0.0)) ok = false;
+    ajj = sqrt(ajj);
+    A[pk(j, j)] = ajj;
+    double rajj = 1.0 / ajj;
+#pragma unroll
+    for (int k = j + 1; k < D; k++) {
+      double tt = 0.0;
+#pragma unroll
+      for (int i = 0; i < j; i++) tt += A[pk(i, k)] * A[pk(i, j)];
+      A[pk(j, k)] = (A[pk(j, k)] - tt) * rajj;
+    }
+  }
+  if (!ok) return false;
+  const double sq = sqrt((double)D);
+#pragma unroll
+  for (int k = 0; k < T; k++) R[k] = A[k] * 2.4 / sq;
+  if (c.dodr) {
+#pragma unroll
+    for (int k = 0; k < T; k++) A[k] = R[k];
+    // dtrti2 (upper, non-unit)
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      A[pk(j, j)] = 1.0 / A[pk(j, j)];
+      double ajj = -A[pk(j, j)];
+#pragma unroll
+      for (int jj = 0; jj < j; jj++) {  // dtrmv('U','N','N') on the leading j x j block
+        double temp = A[pk(jj, j)];
+#pragma unroll
+        for (int i = 0; i < jj; i++) A[pk(i, j)] += temp * A[pk(i, jj)];
+        A[pk(jj, j)] = temp * A[pk(jj, jj)];
+      }
+#pragma unroll
+      for (int i = 0; i < j; i++) A[pk(i, j)] *= ajj;
+    }
+    // dlauu2 (upper): A <- U * U'
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double aii = A[pk(i, i)];
+      if (i < D - 1) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = i; k < D; k++) t += A[pk(i, k)] * A[pk(i, k)];
+        A[pk(i, i)] = t;
+#pragma unroll
+        for (int r = 0; r < i; r++) A[pk(r, i)] *= aii;
+#pragma unroll
+        for (int k = i + 1; k < D; k++) {
+          double temp = A[pk(i, k)];
+#pragma unroll
+          for (int r = 0; r < i; r++) A[pk(r, i)] += temp * A[pk(r, k)];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r <= i; r++) A[pk(r, i)] *= aii;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+      iC[k] = A[k];
+      R2[k] = R[k] / c.drscale;
+    }
+  }
+  return true;
+}
+
+// v' * S * v for symmetric S stored as packed upper (dsymv('u') + dot, MCMC_DRAM.F90:182-183)
+template <int D>
+__device__ __forceinline__ double quadform(const double (&S)[D * (D + 1) / 2], const double (&v)[D]) {
+  double q = 0.0;
+#pragma unroll
+  for (int a = 0; a < D; a++) {
+    double w = 0.0;
+#pragma unroll
+    for (int b = 0; b < D; b++) w += S[a <= b ? pk(a, b) : pk(b, a)] * v[b];
+    q += w * v[a];
+  }
+  return q;
+}
+
+// One row of the covmat recursion (matutils.F90:283-310) applied to the streaming
+// accumulators.  The reference walks stored rows lastind..chainind at every adaptation
+// (MCMC_adapt.F90:141-157); feeding each row when it completes, and the partial current
+// row at the adaptation tick, performs the same updates in the same order.  With
+// wsum == 0 (initcmatn = 0) the reference uses the two-pass batch formula over the
+// window (matutils.F90:312-337); starting the recursion from the first row (mean = x,
+// cov = 0, wsum = w) is algebraically identical and differs only by rounding.
+template <int D>
+__device__ __forceinline__ void absorb(const double (&x)[D], double w, double (&cm)[D * (D + 1) / 2],
+                                       double (&mean)[D], double& wsum) {
+  if (wsum > 0.0) {
+    double d[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) d[k] = x[k] - mean[k];
+    double f1 = w / (wsum + w - 1.0);
+    double f2 = wsum / (wsum + w);
+#pragma unroll
+    for (int b = 0; b < D; b++)
+#pragma unroll
+      for (int a = 0; a <= b; a++) cm[pk(a, b)] = cm[pk(a, b)] + f1 * (f2 * (d[a] * d[b]) - cm[pk(a, b)]);
+    double f3 = w / (wsum + w);
+#pragma unroll
+    for (int k = 0; k < D; k++) mean[k] = mean[k] + f3 * d[k];
+    wsum = w + wsum;
+  } else if (w > 0.0) {
+#pragma unroll
+    for (int k = 0; k < D; k++) mean[k] = x[k];
+#pragma unroll
+    for (int k = 0; k < D * (D + 1) / 2; k++) cm[k] = 0.0;
+    wsum = w;
+  }
+}
+
+// dchud.f:122-139 on packed upper R
+template <int D>
+__device__ __forceinline__ void chud(double (&R)[D * (D + 1) / 2], const double (&x)[D]) {
+  double cs[D], sn[D];
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    double xj = x[j];
+#pragma unroll
+    for (int i = 0; i < j; i++) {
+      double t = cs[i] * R[pk(i, j)] + sn[i] * xj;
+      xj = cs[i] * xj - sn[i] * R[pk(i, j)];
+      R[pk(i, j)] = t;
+    }
+    drotg(R[pk(j, j)], xj, cs[j], sn[j]);
+  }
+}
+
+// dchdd.f:141-179 on packed upper R; returns false (R untouched) when not positive definite
+template <int D>
+__device__ __forceinline__ bool chdd(double (&R)[D * (D + 1) / 2], const double (&x)[D]) {
+  double s[D], c[D];
+  s[0] = x[0] / R[pk(0, 0)];
+#pragma unroll
+  for (int j = 1; j < D; j++) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < j; i++) t += R[pk(i, j)] * s[i];
+    s[j] = (x[j] - t) / R[pk(j, j)];
+  }
+  // classic dnrm2
+  double norm;
+  if (D == 1) {
+    norm = fabs(s[0]);
+  } else {
+    double scale = 0.0, ssq = 1.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (s[i] != 0.0) {
+        double a = fabs(s[i]);
+        if (scale < a) {
+          double t = scale / a;
+          ssq = 1.0 + ssq * t * t;
+          scale = a;
+        } else {
+          double t = a / scale;
+          ssq = ssq + t * t;
+        }
+      }
+    }
+    norm = scale * sqrt(ssq);
+  }
+  if (!(norm < 1.0)) return false;
+  double alpha = sqrt(1.0 - norm * norm);
+#pragma unroll
+  for (int i = D - 1; i >= 0; i--) {
+    double scale = alpha + fabs(s[i]);
+    double a = alpha / scale, b = s[i] / scale;
+    double nr = sqrt(a * a + b * b);
+    c[i] = a / nr;
+    s[i] = b / nr;
+    alpha = scale * nr;
+  }
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    double xx = 0.0;
+#pragma unroll
+    for (int i = j; i >= 0; i--) {
+      double t = c[i] * xx + s[i] * R[pk(i, j)];
+      R[pk(i, j)] = c[i] * R[pk(i, j)] - s[i] * xx;
+      xx = t;
+    }
+  }
+  return true;
+}
+
+// Initial state: what MCMC_init leaves behind (MCMC_init.F90:99-116,147-154)
+template <class M>
+__global__ void k1_init_kernel(K1Params p) {
+  constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+  constexpr K1Layout Lo = k1_layout(D, NY);
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.nchains) return;
+  double cm[T], R[T], R2[T], iC[T];
+#pragma unroll
+  for (int k = 0; k < T; k++) {
+    cm[k] = p.cmat0[k];
+    R[k] = 0.0; R2[k] = 0.0; iC[k] = 0.0;
+  }
+  bool ok = calculate_R<D>(cm, R, R2, iC, p.c);
+  double* st = p.st + c;
+  int* ist = p.ist + c;
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    double v = p.par0[c * D + k];
+    st[(Lo.th + k) * p.pitch] = v;
+    st[(Lo.mean + k) * p.pitch] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < NY; k++) {
+    st[(Lo.ss + k) * p.pitch] = 0.0;
+    st[(Lo.s2 + k) * p.pitch] = p.sigma2_0[k];
+  }
+  st[Lo.pri * p.pitch] = 0.0;
+#pragma unroll
+  for (int k = 0; k < T; k++) {
+    st[(Lo.r + k) * p.pitch] = R[k];
+    st[(Lo.r2 + k) * p.pitch] = R2[k];
+    st[(Lo.ic + k) * p.pitch] = iC[k];
+    st[(Lo.cm + k) * p.pitch] = cm[k];
+  }
+  st[Lo.wsum * p.pitch] = (double)p.c.initcmatn;
+  st[Lo.spare * p.pitch] = 0.0;
+  st[Lo.rama * p.pitch] = 0.0;
+#pragma unroll
+  for (int k = 0; k < Lo.i_nf; k++) ist[k * p.pitch] = 0;
+  if (!ok) ist[Lo.i_status * p.pitch] = MCMCB_ST_CHOLFAIL;
+}
+
+template <class M, int L, bool SMEM>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const K1Params p) {
+  constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+  constexpr K1Layout Lo = k1_layout(D, NY);
+  constexpr int CPW = 32 / L;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const double* data = p.blob;
+  if (SMEM) {
+    tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);
+    data = reinterpret_cast<const double*>(smem_raw);
+  }
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L, gl = lane % L;
+  mcmcb_ctx ctx;
+  ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
+  const DevCfg& c = p.c;
+
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if ((long long)tile * CPW >= p.nchains) break;
+    const long long ch = (long long)tile * CPW + sub;
+    const bool valid = ch < p.nchains;
+    const long long cc = valid ? ch : p.nchains - 1;
+    double* st = p.st + cc;
+    int* ist = p.ist + cc;
+
+    // ---- load state into registers
+    double th[D], ss1[NY], s2[NY], R[T], R2[T], iC[T], cm[T], mean[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) { th[k] = st[(Lo.th + k) * p.pitch]; mean[k] = st[(Lo.mean + k) * p.pitch]; }
+#pragma unroll
+    for (int k = 0; k < NY; k++) { ss1[k] = st[(Lo.ss + k) * p.pitch]; s2[k] = st[(Lo.s2 + k) * p.pitch]; }
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+      R[k] = st[(Lo.r + k) * p.pitch]; R2[k] = st[(Lo.r2 + k) * p.pitch];
+      iC[k] = st[(Lo.ic + k) * p.pitch]; cm[k] = st[(Lo.cm + k) * p.pitch];
+    }
+    double pri1 = st[Lo.pri * p.pitch], wsum = st[Lo.wsum * p.pitch], rama = st[Lo.rama * p.pitch];
+    int stayed = ist[Lo.i_stayed * p.pitch], bnd = ist[Lo.i_bnd * p.pitch], dracc = ist[Lo.i_dracc * p.pitch];
+    int drtry = ist[Lo.i_drtry * p.pitch], chainind = ist[Lo.i_chainind * p.pitch];
+    int simuind = ist[Lo.i_simuind * p.pitch], status = ist[Lo.i_status * p.pitch];
+    int cnt = ist[Lo.i_cnt * p.pitch], pend = ist[Lo.i_pend * p.pitch];
+    Rng g;
+    g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * p.pitch] << 32) | (unsigned)ist[Lo.i_ndlo * p.pitch];
+    g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
+    g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
+    g.inj_n = p.inj_per_chain;
+    g.cache_valid = false; g.cache_lo = g.cache_hi = 0;
+    g.has_spare = ist[Lo.i_hasspare * p.pitch] != 0;
+    g.spare = st[Lo.spare * p.pitch];
+    g.exhausted = 0;
+
+    const bool stored = valid && (ch < p.store_chains) && gl == 0;
+    double* srow = p.store_rows_p + (size_t)cc * p.store_rows * (D + NY);
+    double* scnt = p.store_cnt_p + (size_t)cc * p.store_rows;
+    double* ss2st = p.store_s2_p + (size_t)cc * p.store_rows * NY;
+
+    int phase = (simuind == 0) ? -1 : 0;
+    int done = 0;
+    double prop[D], y1[D], z1[D], ss2[NY];
+    double pri2 = 0.0, a12 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) { prop[k] = th[k]; y1[k] = th[k]; z1[k] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NY; k++) ss2[k] = 0.0;
+
+    for (;;) {
+      const bool act = valid && (phase < 0 || done < p.nsteps);
+      if (!__any_sync(FULL, act)) break;
+      // ---------------- prepare the next proposal (divergent, cheap)
+      bool inb = true;
+      if (act && phase >= 0) {
+        double z[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) z[k] = g.normal();
+        // theta + R' z, MCMC_DRAM.F90:29 (dtrmv('u','t','n') order)
+#pragma unroll
+        for (int j = D - 1; j >= 0; j--) {
+          double acc = z[j] * (phase == 0 ? R[pk(j, j)] : R2[pk(j, j)]);
+#pragma unroll
+          for (int i = j - 1; i >= 0; i--) acc += (phase == 0 ? R[pk(i, j)] : R2[pk(i, j)]) * z[i];
+          prop[j] = th[j] + acc;
+        }
+        if (phase == 0) {
+#pragma unroll
+          for (int k = 0; k < D; k++) z1[k] = z[k];
+        }
+        inb = M::checkbounds(prop, D, ctx);
+      }
+      __syncwarp();
+      // ---------------- user model: the hot, warp-converged section
+      double ssn[NY];
+      M::ssfunction(prop, D, NY, ctx, ssn);
+      if (L > 1) {
+#pragma unroll
+        for (int k = 0; k < NY; k++) {
+#pragma unroll
+          for (int off = L / 2; off > 0; off >>= 1) ssn[k] += __shfl_xor_sync(FULL, ssn[k], off);
+        }
+      }
+      const double prn = M::priorfun(prop, D, ctx);
+      if (!act) continue;
+      // ---------------- accept / reject (divergent, cheap)
+      bool step_end = false, reject = false;
+      if (phase < 0) {  // MCMC_run.F90:27-36: initial point, saved as row 1
+#pragma unroll
+        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
+        pri1 = prn;
+        chainind = 1; simuind = 1; cnt = 1; pend = 1;
+        if (stored) {
+#pragma unroll
+          for (int k = 0; k < D; k++) srow[k] = th[k];
+#pragma unroll
+          for (int k = 0; k < NY; k++) { srow[D + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
+        }
+        phase = 0;
+        continue;
+      }
+      if (phase == 0) {  // MCMC_run.F90:46-59
+        if (!inb) {
+          if (!c.dodr || c.method == MCMCB_RAM) bnd++;
+#pragma unroll
+          for (int k = 0; k < NY; k++) ssn[k] = DBL_HUGE;
+          if (c.method != MCMCB_RAM) a12 = 0.0;  // RAM keeps the stale alpha12 (MCMC_run_ram.F90:52-55)
+          else a12 = rama;
+          reject = true;
+        } else {
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
+          a12 = alpha_from_tst(-0.5 * (sum + (prn - pri1)));
+          reject = mh_reject(a12, g);
+        }
+        rama = a12;
+        if (reject && c.dodr) {  // MCMC_run.F90:65-68: one delayed-rejection try
+          drtry++;
+#pragma unroll
+          for (int k = 0; k < D; k++) y1[k] = prop[k];
+#pragma unroll
+          for (int k = 0; k < NY; k++) ss2[k] = ssn[k];
+          pri2 = inb ? prn : DBL_HUGE;
+          phase = 1;
+        } else {
+          step_end = true;
+        }
+      } else {  // MCMC_run.F90:69-91
+        if (!inb) {
+          bnd++;
+          reject = true;
+        } else {  // MCMC_DR_alpha13, MCMC_DRAM.F90:162-186
+          double a32;
+          if (a12 == 0.0) {
+            a32 = 0.0;
+          } else {
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < NY; k++) sum += (ss2[k] - ssn[k]) / s2[k];
+            a32 = fmin(1.0, exp(-0.5 * (sum + (pri2 - prn))));
+          }
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
+          double l2 = -0.5 * (sum + (prn - pri1));
+          double va[D], vb[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) { va[k] = prop[k] - y1[k]; vb[k] = th[k] - y1[k]; }
+          double q1 = -0.5 * (quadform<D>(iC, va) - quadform<D>(iC, vb));
+          double a13 = exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+          if (a13 == a13) a13 = fmin(1.0, a13);  // NaN rejects
+          reject = mh_reject(a13, g);
+          if (!reject) dracc++;
+        }
+        phase = 0;
+        step_end = true;
+      }
+      if (!step_end) continue;
+
+      // ---------------- end of one MCMC_LOOP iteration, MCMC_run.F90:93-105
+      const int i = simuind + 1;
+      simuind = i;
+      const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
+      if (reject) {
+        stayed++;
+        cnt++; pend++;
+      } else {
+        if (absorbing) absorb<D>(th, (double)pend, cm, mean, wsum);
+        if (stored && chainind - 1 < p.store_rows) scnt[chainind - 1] = (double)cnt;
+#pragma unroll
+        for (int k = 0; k < D; k++) th[k] = prop[k];
+#pragma unroll
+        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
+        pri1 = prn;
+        chainind++;
+        cnt = 1; pend = 1;
+      }
+      if (c.updatesigma) {  // MCMC_updatesigma2, MCMC_DRAM.F90:192-206
+#pragma unroll
+        for (int k = 0; k < NY; k++) {
+          double gg = g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + ss1[k]));
+          s2[k] = 1.0 / gg;
+        }
+      }
+      if (stored) {  // MCMC_savechain, MCMC_aux.F90:166-185
+        if (!reject) {
+          if (chainind - 1 < p.store_rows) {
+#pragma unroll
+            for (int k = 0; k < D; k++) srow[(size_t)(chainind - 1) * (D + NY) + k] = th[k];
+#pragma unroll
+            for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (D + NY) + D + k] = ss1[k];
+          } else {
+            status |= MCMCB_ST_STORE_FULL;
+          }
+        }
+        if (c.updatesigma && i - 1 < p.store_rows) {
+#pragma unroll
+          for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
+        }
+      }
+      if (c.method == MCMCB_RAM) {  // MCMC_adapt_ram, MCMC_run_ram.F90:104-179
+        if (c.doadapt && !(i < c.burnintime && c.doburnin)) {
+          double a = 1.0 / pow((double)(float)i, c.nuparam) * (rama - c.alphatarget);
+          double su2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) su2 += z1[k] * z1[k];
+          double xv[D];
+          if (a >= 0.0) {
+#pragma unroll
+            for (int k = 0; k < D; k++) xv[k] = z1[k] / su2 * a;
+            chud<D>(R, xv);
+          } else {
+#pragma unroll
+            for (int k = 0; k < D; k++) xv[k] = -z1[k] / su2 * a;
+            if (!chdd<D>(R, xv)) status |= MCMCB_ST_DOWNDATE_FAIL;
+          }
+        }
+      } else if ((c.doadapt || c.doburnin) && !(c.adaptend > 0 && i > c.adaptend)) {  // MCMC_adapt.F90:42-46
+        const int ma = c.adaptint > 0 ? i % c.adaptint : 1;
+        const int mb = c.badaptint > 0 ? i % c.badaptint : 1;
+        if (ma == 0 || mb == 0) {
+          if (i < c.burnintime && c.doburnin && mb == 0) {  // MCMC_adapt.F90:60-102
+            const double staypc = (double)stayed / (double)i;
+            if (staypc > 1.0 - c.scalelimit) {
+#pragma unroll
+              for (int k = 0; k < T; k++) {
+                R[k] = R[k] / c.scalefactor;
+                if (c.dodr) { R2[k] = R2[k] / c.scalefactor; iC[k] = iC[k] * c.scalefactor * c.scalefactor; }
+              }
+            } else if (staypc < c.scalelimit) {
+#pragma unroll
+              for (int k = 0; k < T; k++) {
+                R[k] = R[k] * c.scalefactor;
+                if (c.dodr) { R2[k] = R2[k] * c.scalefactor; iC[k] = iC[k] / c.scalefactor / c.scalefactor; }
+              }
+            } else {
+              // lastind = chainind (MCMC_adapt.F90:102): rows before the current one never enter the
+              // covariance, the current row enters with its full count (lastfreq stays 0); then
+              // MCMC_calculate_R(chaincmat) with chaincmat still == cmat0 (no AM update happened yet)
+              double c0[T];
+#pragma unroll
+              for (int k = 0; k < T; k++) { c0[k] = p.cmat0[k]; cm[k] = c0[k]; }
+#pragma unroll
+              for (int k = 0; k < D; k++) mean[k] = p.par0[cc * D + k];
+              wsum = (double)c.initcmatn;
+              pend = cnt;
+              if (!calculate_R<D>(c0, R, R2, iC, c)) status |= MCMCB_ST_CHOLFAIL;
+            }
+          } else if (i >= c.burnintime + c.adaptint + c.adapthist && c.doadapt) {  // MCMC_adapt.F90:105-159
+            absorb<D>(th, (double)pend, cm, mean, wsum);
+            pend = 0;
+            if (!calculate_R<D>(cm, R, R2, iC, c)) status |= MCMCB_ST_CHOLFAIL;
+          }
+        }
+      }
+      if (g.exhausted) status |= MCMCB_ST_RNG_EXHAUSTED;
+      done++;
+    }
+
+    // ---- write state back
+    if (valid && gl == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k++) { st[(Lo.th + k) * p.pitch] = th[k]; st[(Lo.mean + k) * p.pitch] = mean[k]; }
+#pragma unroll
+      for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = ss1[k]; st[(Lo.s2 + k) * p.pitch] = s2[k]; }
+#pragma unroll
+      for (int k = 0; k < T; k++) {
+        st[(Lo.r + k) * p.pitch] = R[k]; st[(Lo.r2 + k) * p.pitch] = R2[k];
+        st[(Lo.ic + k) * p.pitch] = iC[k]; st[(Lo.cm + k) * p.pitch] = cm[k];
+      }
+      st[Lo.pri * p.pitch] = pri1; st[Lo.wsum * p.pitch] = wsum; st[Lo.rama * p.pitch] = rama;
+      st[Lo.spare * p.pitch] = g.spare;
+      ist[Lo.i_stayed * p.pitch] = stayed; ist[Lo.i_bnd * p.pitch] = bnd; ist[Lo.i_dracc * p.pitch] = dracc;
+      ist[Lo.i_drtry * p.pitch] = drtry; ist[Lo.i_chainind * p.pitch] = chainind;
+      ist[Lo.i_simuind * p.pitch] = simuind; ist[Lo.i_status * p.pitch] = status;
+      ist[Lo.i_hasspare * p.pitch] = g.has_spare ? 1 : 0;
+      ist[Lo.i_cnt * p.pitch] = cnt; ist[Lo.i_pend * p.pitch] = pend;
+      ist[Lo.i_ndlo * p.pitch] = (int)(unsigned)(g.nd & 0xffffffffull);
+      ist[Lo.i_ndhi * p.pitch] = (int)(unsigned)(g.nd >> 32);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace mcmcb

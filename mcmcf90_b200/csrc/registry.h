@@ -1,0 +1,67 @@
+// Host-side handle and user-model registry (the run-time analogue of the reference's
+// link-time override of ssfunction/priorfun/checkbounds, external_inc.h:4-28).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "mcmcb200.h"
+
+struct mcmcb_handle_s;
+
+namespace mcmcb {
+
+struct ModelEntry {
+  const char* name;
+  int kernel;  // 1 = small-npar register kernel, 2 = large-npar warp kernel
+  int npar;    // compile-time npar, 0 = runtime
+  int ny;
+  int (*alloc)(mcmcb_handle_s*);
+  int (*init)(mcmcb_handle_s*);
+  int (*step)(mcmcb_handle_s*, int nsteps);
+};
+
+std::vector<ModelEntry>& registry();
+int register_model(const ModelEntry& e);
+
+struct DumpSlot {
+  double* dev = nullptr;
+  double* host = nullptr;
+  cudaEvent_t ev = nullptr, ready = nullptr;
+  int state = 0;  // 0 free, 1 in flight / ready
+  int step = 0;
+};
+
+}  // namespace mcmcb
+
+struct mcmcb_handle_s {
+  mcmcb_config cfg{};
+  mcmcb::DevCfg dc{};
+  int dodr = 0, doscam = 0, usesvd = 0;
+  const mcmcb::ModelEntry* model = nullptr;
+  int npar = 0, nycol = 0, L = 1;
+  int num_sms = 0, occ = 1, blocks = 0;
+  size_t max_smem = 0, smem = 0;
+  bool attr_set = false, smem_blob = false, initial_set = false;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  long long pitch = 0, launches = 0, steps_done = 0;
+  int nf = 0, inf = 0;
+  double* d_st = nullptr;
+  int* d_ist = nullptr;
+  double *d_par0 = nullptr, *d_cmat0 = nullptr, *d_sigma2 = nullptr, *d_blob = nullptr, *d_prior = nullptr,
+         *d_inj = nullptr;
+  int* d_nobs = nullptr;
+  size_t blob_n = 0, blob_bytes = 0, inj_per_chain = 0;
+  int store_chains = 0;
+  double *d_store_rows = nullptr, *d_store_cnt = nullptr, *d_store_s2 = nullptr;
+  unsigned* d_tile = nullptr;
+  std::vector<double> h_tmp;
+  std::vector<mcmcb::DumpSlot> dump_slots;
+  std::deque<int> dump_fifo;
+  int dump_head = 0;
+  long long dumps_dropped = 0;
+  std::string err;
+};
