@@ -135,6 +135,16 @@ struct Rng {
   }
 };
 
+// exp() whose subnormal results are (up to a 1e-13-wide window) the correctly rounded ones, as
+// host libm's are.  CUDA's exp() is 1 ulp, which at the bottom of the subnormal range means it can
+// return 0 where libm returns the smallest subnormal -- and "draw a uniform iff alpha > 0"
+// (MCMC_DRAM.F90:147-153) then consumes a different number of draws.  alpha13 has no underflow
+// clamp in the reference (MCMC_DRAM.F90:184), so this range is reachable.
+__device__ __forceinline__ double exp_subnormal_safe(double x) {
+  if (x < -708.0) return exp(x + 69.314718055994530942 /* 100 ln 2 */) * 7.8886090522101180541e-31 /* 2^-100 */;
+  return exp(x);
+}
+
 // MCMC_DRAM.F90:100-118 (tst is the caller's -0.5*(sum((ss2-ss1)/sigma2) + (sspri2-sspri1)))
 __device__ __forceinline__ double alpha_from_tst(double tst) {
   if (tst >= 0.0) return 1.0;

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const K1Params p
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < NY; k++) sum += (ss2[k] - ssn[k]) / s2[k];
-            a32 = fmin(1.0, exp(-0.5 * (sum + (pri2 - prn))));
+            a32 = fmin(1.0, exp_subnormal_safe(-0.5 * (sum + (pri2 - prn))));
           }
           double sum = 0.0;
 #pragma unroll
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const K1Params p
 #pragma unroll
           for (int k = 0; k < D; k++) { va[k] = prop[k] - y1[k]; vb[k] = th[k] - y1[k]; }
           double q1 = -0.5 * (quadform<D>(iC, va) - quadform<D>(iC, vb));
-          double a13 = exp(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+          double a13 = exp_subnormal_safe(l2 + q1) * (1.0 - a32) / (1.0 - a12);
           if (a13 == a13) a13 = fmin(1.0, a13);  // NaN rejects
           reject = mh_reject(a13, g);
           if (!reject) dracc++;

