@@ -111,7 +111,7 @@ struct K1 {
   template <int L, bool SMEM>
   static int launch_LS(mcmcb_handle h, const K1Params& p) {
     auto kern = k1_step_kernel<M, L, SMEM>;
-    size_t smem = SMEM ? h->blob_bytes : 0;
+    size_t smem = MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? h->blob_bytes : 0);
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
@@ -323,7 +323,7 @@ extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
   h->blob_n = n;
   h->blob_bytes = bytes;
   // TMA-stage the blob into shared memory when it fits beside the kernel's static smem
-  h->smem_blob = bytes + 1024 <= h->max_smem;
+  h->smem_blob = bytes + MCMCB_EXP_TAB_DOUBLES * sizeof(double) + 1024 <= h->max_smem;
   h->attr_set = false;
   return MCMCB_OK;
 }

@@ -24,7 +24,10 @@
 
 namespace mcmcb {
 
-constexpr int K1_THREADS = 512;
+#ifndef MCMCB_K1_THREADS
+#define MCMCB_K1_THREADS 512
+#endif
+constexpr int K1_THREADS = MCMCB_K1_THREADS;
 
 // field offsets of the SoA state (doubles and ints), shared by host and device
 struct K1Layout {
@@ -331,99 +334,353 @@ __global__ void k1_init_kernel(K1Params p) {
   if (!ok) ist[Lo.i_status * p.pitch] = MCMCB_ST_CHOLFAIL;
 }
 
-template <class M, int L, bool SMEM>
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const K1Params p) {
+// Everything one chain owns.  The struct is handed by pointer to the two non-inlined cold
+// routines below, so it lives in (L1-cached, lane-interleaved) local memory; the hot model
+// loop only keeps the proposal and its accumulators in registers.  That caps the kernel at
+// K1_REGS registers per thread and buys the occupancy the FP64 pipe needs to stay busy.
+template <int D, int NY>
+struct K1State {
+  static constexpr int T = D * (D + 1) / 2;
+  double th[D], ss1[NY], s2[NY], R[T], R2[T], iC[T], cm[T], mean[D];
+  double pri1, wsum, rama;
+  double y1[D], z1[D], ss2[NY], pri2, a12;  // first-stage proposal kept for DR / RAM
+  int stayed, bnd, dracc, drtry, chainind, simuind, status, cnt, pend;
+  int phase, done;
+  bool valid, stored;
+  long long cc;
+  Rng g;
+};
+
+template <class M>
+__device__ __forceinline__ void k1_load_state(K1State<M::NPAR, M::NY>& S, const K1Params& p, long long cc) {
   constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
   constexpr K1Layout Lo = k1_layout(D, NY);
+  const double* st = p.st + cc;
+  const int* ist = p.ist + cc;
+#pragma unroll
+  for (int k = 0; k < D; k++) { S.th[k] = st[(Lo.th + k) * p.pitch]; S.mean[k] = st[(Lo.mean + k) * p.pitch]; }
+#pragma unroll
+  for (int k = 0; k < NY; k++) { S.ss1[k] = st[(Lo.ss + k) * p.pitch]; S.s2[k] = st[(Lo.s2 + k) * p.pitch]; }
+#pragma unroll
+  for (int k = 0; k < T; k++) {
+    S.R[k] = st[(Lo.r + k) * p.pitch]; S.R2[k] = st[(Lo.r2 + k) * p.pitch];
+    S.iC[k] = st[(Lo.ic + k) * p.pitch]; S.cm[k] = st[(Lo.cm + k) * p.pitch];
+  }
+  S.pri1 = st[Lo.pri * p.pitch]; S.wsum = st[Lo.wsum * p.pitch]; S.rama = st[Lo.rama * p.pitch];
+  S.stayed = ist[Lo.i_stayed * p.pitch]; S.bnd = ist[Lo.i_bnd * p.pitch]; S.dracc = ist[Lo.i_dracc * p.pitch];
+  S.drtry = ist[Lo.i_drtry * p.pitch]; S.chainind = ist[Lo.i_chainind * p.pitch];
+  S.simuind = ist[Lo.i_simuind * p.pitch]; S.status = ist[Lo.i_status * p.pitch];
+  S.cnt = ist[Lo.i_cnt * p.pitch]; S.pend = ist[Lo.i_pend * p.pitch];
+  Rng& g = S.g;
+  g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * p.pitch] << 32) | (unsigned)ist[Lo.i_ndlo * p.pitch];
+  g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
+  g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
+  g.inj_n = p.inj_per_chain;
+  g.cache_valid = false; g.cache_lo = g.cache_hi = 0;
+  g.has_spare = ist[Lo.i_hasspare * p.pitch] != 0;
+  g.spare = st[Lo.spare * p.pitch];
+  g.exhausted = 0;
+  S.phase = (S.simuind == 0) ? -1 : 0;
+  S.done = 0;
+  S.pri2 = 0.0; S.a12 = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) { S.y1[k] = S.th[k]; S.z1[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NY; k++) S.ss2[k] = 0.0;
+  S.cc = cc;
+}
+
+template <class M>
+__device__ __forceinline__ void k1_store_state(const K1State<M::NPAR, M::NY>& S, const K1Params& p) {
+  constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+  constexpr K1Layout Lo = k1_layout(D, NY);
+  double* st = p.st + S.cc;
+  int* ist = p.ist + S.cc;
+#pragma unroll
+  for (int k = 0; k < D; k++) { st[(Lo.th + k) * p.pitch] = S.th[k]; st[(Lo.mean + k) * p.pitch] = S.mean[k]; }
+#pragma unroll
+  for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = S.ss1[k]; st[(Lo.s2 + k) * p.pitch] = S.s2[k]; }
+#pragma unroll
+  for (int k = 0; k < T; k++) {
+    st[(Lo.r + k) * p.pitch] = S.R[k]; st[(Lo.r2 + k) * p.pitch] = S.R2[k];
+    st[(Lo.ic + k) * p.pitch] = S.iC[k]; st[(Lo.cm + k) * p.pitch] = S.cm[k];
+  }
+  st[Lo.pri * p.pitch] = S.pri1; st[Lo.wsum * p.pitch] = S.wsum; st[Lo.rama * p.pitch] = S.rama;
+  st[Lo.spare * p.pitch] = S.g.spare;
+  ist[Lo.i_stayed * p.pitch] = S.stayed; ist[Lo.i_bnd * p.pitch] = S.bnd; ist[Lo.i_dracc * p.pitch] = S.dracc;
+  ist[Lo.i_drtry * p.pitch] = S.drtry; ist[Lo.i_chainind * p.pitch] = S.chainind;
+  ist[Lo.i_simuind * p.pitch] = S.simuind; ist[Lo.i_status * p.pitch] = S.status;
+  ist[Lo.i_hasspare * p.pitch] = S.g.has_spare ? 1 : 0;
+  ist[Lo.i_cnt * p.pitch] = S.cnt; ist[Lo.i_pend * p.pitch] = S.pend;
+  ist[Lo.i_ndlo * p.pitch] = (int)(unsigned)(S.g.nd & 0xffffffffull);
+  ist[Lo.i_ndhi * p.pitch] = (int)(unsigned)(S.g.nd >> 32);
+}
+
+// Next proposal of this chain (cold, divergent): theta + R'z, MCMC_DRAM.F90:20-31, with the
+// first- or second-stage factor.  Returns the bounds verdict (MCMC_DRAM.F90:37-46).
+template <class M>
+__device__ __noinline__ bool k1_prepare(K1State<M::NPAR, M::NY>* Sp, double* prop_out, const mcmcb_ctx* ctx) {
+  constexpr int D = M::NPAR;
+  K1State<M::NPAR, M::NY>& S = *Sp;
+  double prop[D];
+  if (S.phase < 0) {
+#pragma unroll
+    for (int k = 0; k < D; k++) prop_out[k] = S.th[k];
+    return true;
+  }
+  double z[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) z[k] = S.g.normal();
+  const bool first = S.phase == 0;
+#pragma unroll
+  for (int j = D - 1; j >= 0; j--) {  // dtrmv('u','t','n') order, matutils.F90:108-109
+    double acc = z[j] * (first ? S.R[pk(j, j)] : S.R2[pk(j, j)]);
+#pragma unroll
+    for (int i = j - 1; i >= 0; i--) acc += (first ? S.R[pk(i, j)] : S.R2[pk(i, j)]) * z[i];
+    prop[j] = S.th[j] + acc;
+  }
+  if (first) {
+#pragma unroll
+    for (int k = 0; k < D; k++) S.z1[k] = z[k];
+  }
+#pragma unroll
+  for (int k = 0; k < D; k++) prop_out[k] = prop[k];
+  return M::checkbounds(prop, D, *ctx);
+}
+
+// Accept / reject and, at the end of a step, everything MCMC_run.F90:93-105 does after it
+// (cold, divergent).
+template <class M>
+__device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Params* pp, const double* prop_in,
+                                       const double* ssn_in, double prn, bool inb) {
+  constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+  K1State<D, NY>& S = *Sp;
+  const K1Params& p = *pp;
+  const DevCfg& c = p.c;
+  Rng& g = S.g;
+  double prop[D], ssn[NY];
+#pragma unroll
+  for (int k = 0; k < D; k++) prop[k] = prop_in[k];
+#pragma unroll
+  for (int k = 0; k < NY; k++) ssn[k] = ssn_in[k];
+  double* srow = p.store_rows_p + (size_t)S.cc * p.store_rows * (D + NY);
+  double* scnt = p.store_cnt_p + (size_t)S.cc * p.store_rows;
+  double* ss2st = p.store_s2_p + (size_t)S.cc * p.store_rows * NY;
+  const bool stored = S.stored;
+
+  bool reject = false;
+  if (S.phase < 0) {  // MCMC_run.F90:27-36: initial point, saved as row 1
+#pragma unroll
+    for (int k = 0; k < NY; k++) S.ss1[k] = ssn[k];
+    S.pri1 = prn;
+    S.chainind = 1; S.simuind = 1; S.cnt = 1; S.pend = 1;
+    if (stored) {
+#pragma unroll
+      for (int k = 0; k < D; k++) srow[k] = S.th[k];
+#pragma unroll
+      for (int k = 0; k < NY; k++) { srow[D + k] = S.ss1[k]; if (c.updatesigma) ss2st[k] = S.s2[k]; }
+    }
+    S.phase = 0;
+    return;
+  }
+  if (S.phase == 0) {  // MCMC_run.F90:46-59
+    if (!inb) {
+      if (!c.dodr || c.method == MCMCB_RAM) S.bnd++;
+#pragma unroll
+      for (int k = 0; k < NY; k++) ssn[k] = DBL_HUGE;
+      S.a12 = (c.method != MCMCB_RAM) ? 0.0 : S.rama;  // RAM keeps the stale alpha12 (MCMC_run_ram.F90:52-55)
+      reject = true;
+    } else {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < NY; k++) sum += (ssn[k] - S.ss1[k]) / S.s2[k];
+      S.a12 = alpha_from_tst(-0.5 * (sum + (prn - S.pri1)));
+      reject = mh_reject(S.a12, g);
+    }
+    S.rama = S.a12;
+    if (reject && c.dodr) {  // MCMC_run.F90:65-68: one delayed-rejection try
+      S.drtry++;
+#pragma unroll
+      for (int k = 0; k < D; k++) S.y1[k] = prop[k];
+#pragma unroll
+      for (int k = 0; k < NY; k++) S.ss2[k] = ssn[k];
+      S.pri2 = inb ? prn : DBL_HUGE;
+      S.phase = 1;
+      return;
+    }
+  } else {  // MCMC_run.F90:69-91
+    if (!inb) {
+      S.bnd++;
+      reject = true;
+    } else {  // MCMC_DR_alpha13, MCMC_DRAM.F90:162-186
+      double a32;
+      if (S.a12 == 0.0) {
+        a32 = 0.0;
+      } else {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NY; k++) sum += (S.ss2[k] - ssn[k]) / S.s2[k];
+        a32 = fmin(1.0, exp_subnormal_safe(-0.5 * (sum + (S.pri2 - prn))));
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < NY; k++) sum += (ssn[k] - S.ss1[k]) / S.s2[k];
+      double l2 = -0.5 * (sum + (prn - S.pri1));
+      double va[D], vb[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) { va[k] = prop[k] - S.y1[k]; vb[k] = S.th[k] - S.y1[k]; }
+      double q1 = -0.5 * (quadform<D>(S.iC, va) - quadform<D>(S.iC, vb));
+      double a13 = exp_subnormal_safe(l2 + q1) * (1.0 - a32) / (1.0 - S.a12);
+      if (a13 == a13) a13 = fmin(1.0, a13);  // NaN rejects
+      reject = mh_reject(a13, g);
+      if (!reject) S.dracc++;
+    }
+    S.phase = 0;
+  }
+
+  // ---------------- end of one MCMC_LOOP iteration, MCMC_run.F90:93-105
+  const int i = S.simuind + 1;
+  S.simuind = i;
+  const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
+  if (reject) {
+    S.stayed++;
+    S.cnt++; S.pend++;
+  } else {
+    if (absorbing) absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
+    if (stored && S.chainind - 1 < p.store_rows) scnt[S.chainind - 1] = (double)S.cnt;
+#pragma unroll
+    for (int k = 0; k < D; k++) S.th[k] = prop[k];
+#pragma unroll
+    for (int k = 0; k < NY; k++) S.ss1[k] = ssn[k];
+    S.pri1 = prn;
+    S.chainind++;
+    S.cnt = 1; S.pend = 1;
+  }
+  if (c.updatesigma) {  // MCMC_updatesigma2, MCMC_DRAM.F90:192-206
+#pragma unroll
+    for (int k = 0; k < NY; k++) {
+      double gg = g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + S.ss1[k]));
+      S.s2[k] = 1.0 / gg;
+    }
+  }
+  if (stored) {  // MCMC_savechain, MCMC_aux.F90:166-185
+    if (!reject) {
+      if (S.chainind - 1 < p.store_rows) {
+#pragma unroll
+        for (int k = 0; k < D; k++) srow[(size_t)(S.chainind - 1) * (D + NY) + k] = S.th[k];
+#pragma unroll
+        for (int k = 0; k < NY; k++) srow[(size_t)(S.chainind - 1) * (D + NY) + D + k] = S.ss1[k];
+      } else {
+        S.status |= MCMCB_ST_STORE_FULL;
+      }
+    }
+    if (c.updatesigma && i - 1 < p.store_rows) {
+#pragma unroll
+      for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = S.s2[k];
+    }
+  }
+  if (c.method == MCMCB_RAM) {  // MCMC_adapt_ram, MCMC_run_ram.F90:104-179
+    if (c.doadapt && !(i < c.burnintime && c.doburnin)) {
+      double a = 1.0 / pow((double)(float)i, c.nuparam) * (S.rama - c.alphatarget);
+      double su2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; k++) su2 += S.z1[k] * S.z1[k];
+      double xv[D];
+      if (a >= 0.0) {
+#pragma unroll
+        for (int k = 0; k < D; k++) xv[k] = S.z1[k] / su2 * a;
+        chud<D>(S.R, xv);
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) xv[k] = -S.z1[k] / su2 * a;
+        if (!chdd<D>(S.R, xv)) S.status |= MCMCB_ST_DOWNDATE_FAIL;
+      }
+    }
+  } else if ((c.doadapt || c.doburnin) && !(c.adaptend > 0 && i > c.adaptend)) {  // MCMC_adapt.F90:42-46
+    const int ma = c.adaptint > 0 ? i % c.adaptint : 1;
+    const int mb = c.badaptint > 0 ? i % c.badaptint : 1;
+    if (ma == 0 || mb == 0) {
+      if (i < c.burnintime && c.doburnin && mb == 0) {  // MCMC_adapt.F90:60-102
+        const double staypc = (double)S.stayed / (double)i;
+        if (staypc > 1.0 - c.scalelimit) {
+#pragma unroll
+          for (int k = 0; k < T; k++) {
+            S.R[k] = S.R[k] / c.scalefactor;
+            if (c.dodr) { S.R2[k] = S.R2[k] / c.scalefactor; S.iC[k] = S.iC[k] * c.scalefactor * c.scalefactor; }
+          }
+        } else if (staypc < c.scalelimit) {
+#pragma unroll
+          for (int k = 0; k < T; k++) {
+            S.R[k] = S.R[k] * c.scalefactor;
+            if (c.dodr) { S.R2[k] = S.R2[k] * c.scalefactor; S.iC[k] = S.iC[k] / c.scalefactor / c.scalefactor; }
+          }
+        } else {
+          // lastind = chainind (MCMC_adapt.F90:102): rows before the current one never enter the
+          // covariance, the current row enters with its full count (lastfreq stays 0); then
+          // MCMC_calculate_R(chaincmat) with chaincmat still == cmat0 (no AM update happened yet)
+          double c0[T];
+#pragma unroll
+          for (int k = 0; k < T; k++) { c0[k] = p.cmat0[k]; S.cm[k] = c0[k]; }
+#pragma unroll
+          for (int k = 0; k < D; k++) S.mean[k] = p.par0[S.cc * D + k];
+          S.wsum = (double)c.initcmatn;
+          S.pend = S.cnt;
+          if (!calculate_R<D>(c0, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
+        }
+      } else if (i >= c.burnintime + c.adaptint + c.adapthist && c.doadapt) {  // MCMC_adapt.F90:105-159
+        absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
+        S.pend = 0;
+        if (!calculate_R<D>(S.cm, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
+      }
+    }
+  }
+  if (g.exhausted) S.status |= MCMCB_ST_RNG_EXHAUSTED;
+  S.done++;
+}
+
+template <class M, int L, bool SMEM>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_constant__ K1Params p) {
+  constexpr int D = M::NPAR, NY = M::NY;
   constexpr int CPW = 32 / L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
 
+  // dynamic shared memory: [exp2 table, 8 KB][model blob (when it fits)]
+  double* exp_tab = reinterpret_cast<double*>(smem_raw);
+  mcmcb_stage_exp_table(exp_tab);
   const double* data = p.blob;
   if (SMEM) {
-    tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);
-    data = reinterpret_cast<const double*>(smem_raw);
+    unsigned char* blob_s = smem_raw + MCMCB_EXP_TAB_DOUBLES * sizeof(double);
+    tma_stage_blob(blob_s, p.blob, p.blob_bytes, &mbar);  // contains a __syncthreads()
+    data = reinterpret_cast<const double*>(blob_s);
+  } else {
+    __syncthreads();
   }
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, gl = lane % L;
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
-  const DevCfg& c = p.c;
+  ctx.exp2_tab = exp_tab; ctx.tab_slot = lane & 15;
 
+  K1State<D, NY> S;
   for (;;) {
     unsigned tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
     tile = __shfl_sync(FULL, tile, 0);
     if ((long long)tile * CPW >= p.nchains) break;
     const long long ch = (long long)tile * CPW + sub;
-    const bool valid = ch < p.nchains;
-    const long long cc = valid ? ch : p.nchains - 1;
-    double* st = p.st + cc;
-    int* ist = p.ist + cc;
+    S.valid = ch < p.nchains;
+    k1_load_state<M>(S, p, S.valid ? ch : p.nchains - 1);
+    S.stored = S.valid && (ch < p.store_chains) && gl == 0;
 
-    // ---- load state into registers
-    double th[D], ss1[NY], s2[NY], R[T], R2[T], iC[T], cm[T], mean[D];
+    double prop[D];
 #pragma unroll
-    for (int k = 0; k < D; k++) { th[k] = st[(Lo.th + k) * p.pitch]; mean[k] = st[(Lo.mean + k) * p.pitch]; }
-#pragma unroll
-    for (int k = 0; k < NY; k++) { ss1[k] = st[(Lo.ss + k) * p.pitch]; s2[k] = st[(Lo.s2 + k) * p.pitch]; }
-#pragma unroll
-    for (int k = 0; k < T; k++) {
-      R[k] = st[(Lo.r + k) * p.pitch]; R2[k] = st[(Lo.r2 + k) * p.pitch];
-      iC[k] = st[(Lo.ic + k) * p.pitch]; cm[k] = st[(Lo.cm + k) * p.pitch];
-    }
-    double pri1 = st[Lo.pri * p.pitch], wsum = st[Lo.wsum * p.pitch], rama = st[Lo.rama * p.pitch];
-    int stayed = ist[Lo.i_stayed * p.pitch], bnd = ist[Lo.i_bnd * p.pitch], dracc = ist[Lo.i_dracc * p.pitch];
-    int drtry = ist[Lo.i_drtry * p.pitch], chainind = ist[Lo.i_chainind * p.pitch];
-    int simuind = ist[Lo.i_simuind * p.pitch], status = ist[Lo.i_status * p.pitch];
-    int cnt = ist[Lo.i_cnt * p.pitch], pend = ist[Lo.i_pend * p.pitch];
-    Rng g;
-    g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * p.pitch] << 32) | (unsigned)ist[Lo.i_ndlo * p.pitch];
-    g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
-    g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
-    g.inj_n = p.inj_per_chain;
-    g.cache_valid = false; g.cache_lo = g.cache_hi = 0;
-    g.has_spare = ist[Lo.i_hasspare * p.pitch] != 0;
-    g.spare = st[Lo.spare * p.pitch];
-    g.exhausted = 0;
-
-    const bool stored = valid && (ch < p.store_chains) && gl == 0;
-    double* srow = p.store_rows_p + (size_t)cc * p.store_rows * (D + NY);
-    double* scnt = p.store_cnt_p + (size_t)cc * p.store_rows;
-    double* ss2st = p.store_s2_p + (size_t)cc * p.store_rows * NY;
-
-    int phase = (simuind == 0) ? -1 : 0;
-    int done = 0;
-    double prop[D], y1[D], z1[D], ss2[NY];
-    double pri2 = 0.0, a12 = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; k++) { prop[k] = th[k]; y1[k] = th[k]; z1[k] = 0.0; }
-#pragma unroll
-    for (int k = 0; k < NY; k++) ss2[k] = 0.0;
-
+    for (int k = 0; k < D; k++) prop[k] = S.th[k];
     for (;;) {
-      const bool act = valid && (phase < 0 || done < p.nsteps);
+      const bool act = S.valid && (S.phase < 0 || S.done < p.nsteps);
       if (!__any_sync(FULL, act)) break;
-      // ---------------- prepare the next proposal (divergent, cheap)
       bool inb = true;
-      if (act && phase >= 0) {
-        double z[D];
-#pragma unroll
-        for (int k = 0; k < D; k++) z[k] = g.normal();
-        // theta + R' z, MCMC_DRAM.F90:29 (dtrmv('u','t','n') order)
-#pragma unroll
-        for (int j = D - 1; j >= 0; j--) {
-          double acc = z[j] * (phase == 0 ? R[pk(j, j)] : R2[pk(j, j)]);
-#pragma unroll
-          for (int i = j - 1; i >= 0; i--) acc += (phase == 0 ? R[pk(i, j)] : R2[pk(i, j)]) * z[i];
-          prop[j] = th[j] + acc;
-        }
-        if (phase == 0) {
-#pragma unroll
-          for (int k = 0; k < D; k++) z1[k] = z[k];
-        }
-        inb = M::checkbounds(prop, D, ctx);
-      }
+      if (act) inb = k1_prepare<M>(&S, prop, &ctx);
       __syncwarp();
       // ---------------- user model: the hot, warp-converged section
       double ssn[NY];
@@ -436,203 +693,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const K1Params p
         }
       }
       const double prn = M::priorfun(prop, D, ctx);
-      if (!act) continue;
-      // ---------------- accept / reject (divergent, cheap)
-      bool step_end = false, reject = false;
-      if (phase < 0) {  // MCMC_run.F90:27-36: initial point, saved as row 1
-#pragma unroll
-        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
-        pri1 = prn;
-        chainind = 1; simuind = 1; cnt = 1; pend = 1;
-        if (stored) {
-#pragma unroll
-          for (int k = 0; k < D; k++) srow[k] = th[k];
-#pragma unroll
-          for (int k = 0; k < NY; k++) { srow[D + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
-        }
-        phase = 0;
-        continue;
-      }
-      if (phase == 0) {  // MCMC_run.F90:46-59
-        if (!inb) {
-          if (!c.dodr || c.method == MCMCB_RAM) bnd++;
-#pragma unroll
-          for (int k = 0; k < NY; k++) ssn[k] = DBL_HUGE;
-          if (c.method != MCMCB_RAM) a12 = 0.0;  // RAM keeps the stale alpha12 (MCMC_run_ram.F90:52-55)
-          else a12 = rama;
-          reject = true;
-        } else {
-          double sum = 0.0;
-#pragma unroll
-          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
-          a12 = alpha_from_tst(-0.5 * (sum + (prn - pri1)));
-          reject = mh_reject(a12, g);
-        }
-        rama = a12;
-        if (reject && c.dodr) {  // MCMC_run.F90:65-68: one delayed-rejection try
-          drtry++;
-#pragma unroll
-          for (int k = 0; k < D; k++) y1[k] = prop[k];
-#pragma unroll
-          for (int k = 0; k < NY; k++) ss2[k] = ssn[k];
-          pri2 = inb ? prn : DBL_HUGE;
-          phase = 1;
-        } else {
-          step_end = true;
-        }
-      } else {  // MCMC_run.F90:69-91
-        if (!inb) {
-          bnd++;
-          reject = true;
-        } else {  // MCMC_DR_alpha13, MCMC_DRAM.F90:162-186
-          double a32;
-          if (a12 == 0.0) {
-            a32 = 0.0;
-          } else {
-            double sum = 0.0;
-#pragma unroll
-            for (int k = 0; k < NY; k++) sum += (ss2[k] - ssn[k]) / s2[k];
-            a32 = fmin(1.0, exp_subnormal_safe(-0.5 * (sum + (pri2 - prn))));
-          }
-          double sum = 0.0;
-#pragma unroll
-          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
-          double l2 = -0.5 * (sum + (prn - pri1));
-          double va[D], vb[D];
-#pragma unroll
-          for (int k = 0; k < D; k++) { va[k] = prop[k] - y1[k]; vb[k] = th[k] - y1[k]; }
-          double q1 = -0.5 * (quadform<D>(iC, va) - quadform<D>(iC, vb));
-          double a13 = exp_subnormal_safe(l2 + q1) * (1.0 - a32) / (1.0 - a12);
-          if (a13 == a13) a13 = fmin(1.0, a13);  // NaN rejects
-          reject = mh_reject(a13, g);
-          if (!reject) dracc++;
-        }
-        phase = 0;
-        step_end = true;
-      }
-      if (!step_end) continue;
-
-      // ---------------- end of one MCMC_LOOP iteration, MCMC_run.F90:93-105
-      const int i = simuind + 1;
-      simuind = i;
-      const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
-      if (reject) {
-        stayed++;
-        cnt++; pend++;
-      } else {
-        if (absorbing) absorb<D>(th, (double)pend, cm, mean, wsum);
-        if (stored && chainind - 1 < p.store_rows) scnt[chainind - 1] = (double)cnt;
-#pragma unroll
-        for (int k = 0; k < D; k++) th[k] = prop[k];
-#pragma unroll
-        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
-        pri1 = prn;
-        chainind++;
-        cnt = 1; pend = 1;
-      }
-      if (c.updatesigma) {  // MCMC_updatesigma2, MCMC_DRAM.F90:192-206
-#pragma unroll
-        for (int k = 0; k < NY; k++) {
-          double gg = g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + ss1[k]));
-          s2[k] = 1.0 / gg;
-        }
-      }
-      if (stored) {  // MCMC_savechain, MCMC_aux.F90:166-185
-        if (!reject) {
-          if (chainind - 1 < p.store_rows) {
-#pragma unroll
-            for (int k = 0; k < D; k++) srow[(size_t)(chainind - 1) * (D + NY) + k] = th[k];
-#pragma unroll
-            for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (D + NY) + D + k] = ss1[k];
-          } else {
-            status |= MCMCB_ST_STORE_FULL;
-          }
-        }
-        if (c.updatesigma && i - 1 < p.store_rows) {
-#pragma unroll
-          for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
-        }
-      }
-      if (c.method == MCMCB_RAM) {  // MCMC_adapt_ram, MCMC_run_ram.F90:104-179
-        if (c.doadapt && !(i < c.burnintime && c.doburnin)) {
-          double a = 1.0 / pow((double)(float)i, c.nuparam) * (rama - c.alphatarget);
-          double su2 = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; k++) su2 += z1[k] * z1[k];
-          double xv[D];
-          if (a >= 0.0) {
-#pragma unroll
-            for (int k = 0; k < D; k++) xv[k] = z1[k] / su2 * a;
-            chud<D>(R, xv);
-          } else {
-#pragma unroll
-            for (int k = 0; k < D; k++) xv[k] = -z1[k] / su2 * a;
-            if (!chdd<D>(R, xv)) status |= MCMCB_ST_DOWNDATE_FAIL;
-          }
-        }
-      } else if ((c.doadapt || c.doburnin) && !(c.adaptend > 0 && i > c.adaptend)) {  // MCMC_adapt.F90:42-46
-        const int ma = c.adaptint > 0 ? i % c.adaptint : 1;
-        const int mb = c.badaptint > 0 ? i % c.badaptint : 1;
-        if (ma == 0 || mb == 0) {
-          if (i < c.burnintime && c.doburnin && mb == 0) {  // MCMC_adapt.F90:60-102
-            const double staypc = (double)stayed / (double)i;
-            if (staypc > 1.0 - c.scalelimit) {
-#pragma unroll
-              for (int k = 0; k < T; k++) {
-                R[k] = R[k] / c.scalefactor;
-                if (c.dodr) { R2[k] = R2[k] / c.scalefactor; iC[k] = iC[k] * c.scalefactor * c.scalefactor; }
-              }
-            } else if (staypc < c.scalelimit) {
-#pragma unroll
-              for (int k = 0; k < T; k++) {
-                R[k] = R[k] * c.scalefactor;
-                if (c.dodr) { R2[k] = R2[k] * c.scalefactor; iC[k] = iC[k] / c.scalefactor / c.scalefactor; }
-              }
-            } else {
-              // lastind = chainind (MCMC_adapt.F90:102): rows before the current one never enter the
-              // covariance, the current row enters with its full count (lastfreq stays 0); then
-              // MCMC_calculate_R(chaincmat) with chaincmat still == cmat0 (no AM update happened yet)
-              double c0[T];
-#pragma unroll
-              for (int k = 0; k < T; k++) { c0[k] = p.cmat0[k]; cm[k] = c0[k]; }
-#pragma unroll
-              for (int k = 0; k < D; k++) mean[k] = p.par0[cc * D + k];
-              wsum = (double)c.initcmatn;
-              pend = cnt;
-              if (!calculate_R<D>(c0, R, R2, iC, c)) status |= MCMCB_ST_CHOLFAIL;
-            }
-          } else if (i >= c.burnintime + c.adaptint + c.adapthist && c.doadapt) {  // MCMC_adapt.F90:105-159
-            absorb<D>(th, (double)pend, cm, mean, wsum);
-            pend = 0;
-            if (!calculate_R<D>(cm, R, R2, iC, c)) status |= MCMCB_ST_CHOLFAIL;
-          }
-        }
-      }
-      if (g.exhausted) status |= MCMCB_ST_RNG_EXHAUSTED;
-      done++;
+      if (act) k1_finish<M>(&S, &p, prop, ssn, prn, inb);
     }
-
-    // ---- write state back
-    if (valid && gl == 0) {
-#pragma unroll
-      for (int k = 0; k < D; k++) { st[(Lo.th + k) * p.pitch] = th[k]; st[(Lo.mean + k) * p.pitch] = mean[k]; }
-#pragma unroll
-      for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = ss1[k]; st[(Lo.s2 + k) * p.pitch] = s2[k]; }
-#pragma unroll
-      for (int k = 0; k < T; k++) {
-        st[(Lo.r + k) * p.pitch] = R[k]; st[(Lo.r2 + k) * p.pitch] = R2[k];
-        st[(Lo.ic + k) * p.pitch] = iC[k]; st[(Lo.cm + k) * p.pitch] = cm[k];
-      }
-      st[Lo.pri * p.pitch] = pri1; st[Lo.wsum * p.pitch] = wsum; st[Lo.rama * p.pitch] = rama;
-      st[Lo.spare * p.pitch] = g.spare;
-      ist[Lo.i_stayed * p.pitch] = stayed; ist[Lo.i_bnd * p.pitch] = bnd; ist[Lo.i_dracc * p.pitch] = dracc;
-      ist[Lo.i_drtry * p.pitch] = drtry; ist[Lo.i_chainind * p.pitch] = chainind;
-      ist[Lo.i_simuind * p.pitch] = simuind; ist[Lo.i_status * p.pitch] = status;
-      ist[Lo.i_hasspare * p.pitch] = g.has_spare ? 1 : 0;
-      ist[Lo.i_cnt * p.pitch] = cnt; ist[Lo.i_pend * p.pitch] = pend;
-      ist[Lo.i_ndlo * p.pitch] = (int)(unsigned)(g.nd & 0xffffffffull);
-      ist[Lo.i_ndhi * p.pitch] = (int)(unsigned)(g.nd >> 32);
-    }
+    if (S.valid && gl == 0) k1_store_state<M>(S, p);
     __syncwarp();
   }
 }

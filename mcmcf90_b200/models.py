@@ -5,13 +5,14 @@ import numpy as np
 
 
 def blob_expreg(x, y):
-    """[n, 0, x[npad], y[npad]] for y = theta1*exp(-theta2*x) (testcases/mcmcrun.F90:104)."""
+    """[n, max|x|, x[npad], y[npad]] for y = theta1*exp(-theta2*x) (testcases/mcmcrun.F90:104)."""
     x = np.asarray(x, dtype=np.float64).ravel()
     y = np.asarray(y, dtype=np.float64).ravel()
     n = x.size
     npad = (n + 1) & ~1
     b = np.zeros(2 + 2 * npad)
     b[0] = n
+    b[1] = np.abs(x).max() if n else 0.0  # lets the device model range-check once per evaluation
     b[2:2 + n] = x
     b[2 + npad:2 + npad + n] = y
     return b
