@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "k1_small.cuh"
+#include "k2_large.cuh"
 #include "mcmcb200.h"
 #include "models.cuh"
 #include "registry.h"
@@ -45,6 +46,119 @@ int register_model(const ModelEntry& e) {
 
 // ------------------------------------------------------------------ K1 launcher
 namespace {
+
+static int fetch_fields(mcmcb_handle h, int f0, int nf, std::vector<double>& buf) {
+  buf.resize((size_t)nf * h->pitch);
+  CK(cudaMemcpyAsync(buf.data(), h->d_st + (size_t)f0 * h->pitch, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int k1_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
+  const long long N = h->cfg.nchains;
+  const int D = h->npar, NY = h->nycol, T = D * (D + 1) / 2;
+  const K1Layout Lo = k1_layout(D, NY);
+  std::string w(what);
+  std::vector<double> buf;
+  if (w == "counters") {
+    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
+    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
+    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long* o = (long long*)out;
+    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+    for (long long c = 0; c < N; c++) {
+      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
+      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
+      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+    }
+    return MCMCB_OK;
+  }
+  int f0 = -1, width = 0;
+  bool tri = false;
+  if (w == "par") { f0 = Lo.th; width = D; }
+  else if (w == "ss") { f0 = Lo.ss; width = NY; }
+  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
+  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
+  else if (w == "mean") { f0 = Lo.mean; width = D; }
+  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
+  else if (w == "cmat") { f0 = Lo.cm; tri = true; }
+  else if (w == "R") { f0 = Lo.r; tri = true; }
+  else if (w == "R2") { f0 = Lo.r2; tri = true; }
+  else if (w == "iC") { f0 = Lo.ic; tri = true; }
+  else return MCMCB_EINVAL;
+  double* o = (double*)out;
+  if (!tri) {
+    if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
+    int rc = fetch_fields(h, f0, width, buf);
+    if (rc) return rc;
+    for (int k = 0; k < width; k++)
+      for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
+  } else {
+    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
+    int rc = fetch_fields(h, f0, T, buf);
+    if (rc) return rc;
+    const bool sym = (w == "cmat" || w == "iC");
+    for (long long c = 0; c < N; c++)
+      for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+          double v = 0.0;
+          if (i <= j) v = buf[(size_t)(j * (j + 1) / 2 + i) * h->pitch + c];
+          else if (sym) v = buf[(size_t)(i * (i + 1) / 2 + j) * h->pitch + c];
+          o[(size_t)c * D * D + (size_t)j * D + i] = v;  // column-major
+        }
+  }
+  return MCMCB_OK;
+}
+
+// shared by K1 and K2: rows live in the common store, (chainind, cnt, simuind) in ist at the given fields
+static int store_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                             double* s2chain_out, int* nrows, int f_chainind, int f_cnt, int f_simuind) {
+  const int D = h->npar, NY = h->nycol, cap = h->cfg.nsimu;
+  int iv[3];
+  const int fld[3] = {f_chainind, f_cnt, f_simuind};
+  for (int k = 0; k < 3; k++)
+    CK(cudaMemcpyAsync(&iv[k], h->d_ist + (size_t)fld[k] * h->pitch + chain, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int rows = std::min(iv[0], cap), cnt = iv[1], simuind = iv[2];
+  if (nrows) *nrows = rows;
+  if (ld < rows || (s2chain_out && ld < simuind)) return MCMCB_EINVAL;
+  std::vector<double> r((size_t)rows * (D + NY)), cn((size_t)rows), s2((size_t)std::max(simuind, 1) * NY);
+  if (rows > 0) {
+    CK(cudaMemcpyAsync(r.data(), h->d_store_rows + (size_t)chain * cap * (D + NY), sizeof(double) * r.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cn.data(), h->d_store_cnt + (size_t)chain * cap, sizeof(double) * cn.size(), cudaMemcpyDeviceToHost,
+                       h->stream));
+  }
+  if (s2chain_out && simuind > 0)
+    CK(cudaMemcpyAsync(s2.data(), h->d_store_s2 + (size_t)chain * cap * NY, sizeof(double) * (size_t)simuind * NY,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (rows > 0) cn[rows - 1] = (double)cnt;  // the current row's count lives in the chain state
+  for (int i = 0; i < rows; i++) {
+    if (chain_out) {
+      for (int k = 0; k < D; k++) chain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + k];
+      chain_out[(size_t)D * ld + i] = cn[i];
+    }
+    if (sschain_out) {
+      for (int k = 0; k < NY; k++) sschain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + D + k];
+      sschain_out[(size_t)NY * ld + i] = cn[i];
+    }
+  }
+  if (s2chain_out)
+    for (int i = 0; i < simuind; i++)
+      for (int k = 0; k < NY; k++) s2chain_out[(size_t)k * ld + i] = s2[(size_t)i * NY + k];
+  return MCMCB_OK;
+}
+
+static int k1_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                          double* s2chain_out, int* nrows) {
+  const K1Layout Lo = k1_layout(h->npar, h->nycol);
+  return store_fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows, Lo.i_chainind, Lo.i_cnt,
+                           Lo.i_simuind);
+}
+
 
 template <class M>
 struct K1 {
@@ -161,12 +275,245 @@ struct K1 {
     e.alloc = &alloc;
     e.init = &init;
     e.step = &step;
+    e.fetch = &k1_fetch;
+    e.fetch_chain = &k1_fetch_chain;
+    return e;
+  }
+};
+
+// ------------------------------------------------------------------ K2 launcher (large npar)
+static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
+  const long long N = h->cfg.nchains;
+  const int D = h->npar, NY = h->nycol, dp = h->dp;
+  const K2Layout Lo = k2_layout(NY);
+  std::string w(what);
+  if (w == "counters") {
+    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
+    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
+    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long* o = (long long*)out;
+    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+    for (long long c = 0; c < N; c++) {
+      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
+      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
+      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+    }
+    return MCMCB_OK;
+  }
+  double* o = (double*)out;
+  std::vector<double> buf;
+  if (w == "par" || w == "mean") {
+    if (out_bytes < sizeof(double) * (size_t)D * N) return MCMCB_EINVAL;
+    buf.resize((size_t)N * dp);
+    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : h->d_mean, sizeof(double) * buf.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (long long c = 0; c < N; c++)
+      for (int k = 0; k < D; k++) o[(size_t)c * D + k] = buf[(size_t)c * dp + k];
+    return MCMCB_OK;
+  }
+  if (w == "cmat" || w == "R" || w == "R2") {
+    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
+    buf.resize((size_t)N * D * D);
+    CK(cudaMemcpyAsync(buf.data(), w == "cmat" ? h->d_cmat : h->d_Rm, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double sc = (w == "R2") ? 1.0 / h->dc.drscale : 1.0;
+    for (long long c = 0; c < N; c++)
+      for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+          // cmat is symmetric; the factor is stored row-major: element (i,j) at i*D+j -> column-major output
+          double v = buf[(size_t)c * D * D + (size_t)i * D + j];
+          o[(size_t)c * D * D + (size_t)j * D + i] = (w == "cmat") ? v : v * sc;
+        }
+    return MCMCB_OK;
+  }
+  int f0 = -1, width = 0;
+  if (w == "ss") { f0 = Lo.ss; width = NY; }
+  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
+  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
+  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
+  else return MCMCB_EINVAL;  // "iC" is never formed by this kernel (matrix-free DR ratio)
+  if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
+  int rc = fetch_fields(h, f0, width, buf);
+  if (rc) return rc;
+  for (int k = 0; k < width; k++)
+    for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
+  return MCMCB_OK;
+}
+
+static int k2_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                          double* s2chain_out, int* nrows) {
+  const K2Layout Lo = k2_layout(h->nycol);
+  return store_fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows, Lo.i_chainind, Lo.i_cnt,
+                           Lo.i_simuind);
+}
+
+template <class M>
+struct K2 {
+  static constexpr int NY = M::NY;
+
+  static K2Params params(mcmcb_handle h, int nsteps) {
+    K2Params p{};
+    p.c = h->dc;
+    p.nchains = h->cfg.nchains;
+    p.pitch = h->pitch;
+    p.chain_offset = h->cfg.chain_offset;
+    p.seed = h->cfg.seed;
+    p.nsteps = nsteps;
+    p.d = h->npar;
+    p.dp = h->dp;
+    p.st = h->d_st;
+    p.ist = h->d_ist;
+    p.theta = h->d_theta;
+    p.mean = h->d_mean;
+    p.Rm = h->d_Rm;
+    p.cmat = h->d_cmat;
+    p.rowbuf = h->d_rowbuf;
+    p.rowcap = h->rowcap;
+    p.par0 = h->d_par0;
+    p.cmat0 = h->d_cmat0_full;
+    p.sigma2_0 = h->d_sigma2;
+    p.nobs = h->d_nobs;
+    p.blob = h->d_blob;
+    p.blob_n = h->blob_n;
+    p.blob_bytes = (unsigned)h->blob_bytes;
+    p.prior = h->d_prior;
+    p.inj = h->d_inj;
+    p.inj_per_chain = h->inj_per_chain;
+    p.store_chains = h->store_chains;
+    p.store_rows = h->cfg.nsimu;
+    p.store_rows_p = h->d_store_rows;
+    p.store_cnt_p = h->d_store_cnt;
+    p.store_s2_p = h->d_store_s2;
+    p.tile_counter = h->d_tile;
+    p.tick_i = 0;
+    return p;
+  }
+
+  static int alloc(mcmcb_handle h) {
+    static_assert(NY == 1, "the large-npar kernel supports nycol = 1");
+    const K2Layout Lo = k2_layout(NY);
+    const int d = h->npar;
+    if (d > 32 * K2_MAXM) return MCMCB_EUNSUPPORTED;
+    const long long N = h->cfg.nchains;
+    h->nf = Lo.nf;
+    h->inf = Lo.i_nf;
+    h->pitch = ((N + 31) / 32) * 32;
+    h->dp = ((d + 31) / 32) * 32;
+    const mcmcb_config& c = h->cfg;
+    h->rowcap = c.burnintime + 2 * std::max(c.adaptint, 1) + c.adapthist + 2;
+    if (c.method == MCMCB_RAM || !c.doadapt) h->rowcap = 1;
+    CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
+    CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
+    CK(cudaMalloc(&h->d_theta, sizeof(double) * (size_t)N * h->dp));
+    CK(cudaMalloc(&h->d_mean, sizeof(double) * (size_t)N * h->dp));
+    CK(cudaMalloc(&h->d_Rm, sizeof(double) * (size_t)N * d * d));
+    CK(cudaMalloc(&h->d_cmat, sizeof(double) * (size_t)N * d * d));
+    CK(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d * d));
+    CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * h->rowcap * (d + 1)));
+    if (h->store_chains > 0) {
+      size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
+      CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (d + NY)));
+      CK(cudaMalloc(&h->d_store_cnt, sizeof(double) * rows));
+      CK(cudaMalloc(&h->d_store_s2, sizeof(double) * rows * NY));
+      CK(cudaMemsetAsync(h->d_store_rows, 0, sizeof(double) * rows * (d + NY), h->stream));
+      CK(cudaMemsetAsync(h->d_store_cnt, 0, sizeof(double) * rows, h->stream));
+      CK(cudaMemsetAsync(h->d_store_s2, 0, sizeof(double) * rows * NY, h->stream));
+    }
+    return 0;
+  }
+
+  static int init(mcmcb_handle h) {
+    K2Params p = params(h, 0);
+    k2_init_kernel<M><<<(unsigned)h->cfg.nchains, 128, 0, h->stream>>>(p);
+    k2_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
+    h->launches += 2;
+    h->k2_i = 1;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <bool SMEM>
+  static int launch_step(mcmcb_handle h, const K2Params& p) {
+    auto kern = k2_step_kernel<M, SMEM>;
+    size_t smem = sizeof(double) * (size_t)K2_WARPS * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0);
+    if (!h->attr_set) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K2_THREADS, smem));
+      h->occ = std::max(occ, 1);
+      h->attr_set = true;
+    }
+    long long need = (h->cfg.nchains + K2_WARPS - 1) / K2_WARPS;
+    long long blocks = std::max<long long>(1, std::min<long long>((long long)h->num_sms * h->occ, need));
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
+    kern<<<(unsigned)blocks, K2_THREADS, smem, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  static bool is_tick(const mcmcb_config& c, long long i) {
+    if (c.method == MCMCB_RAM) return false;
+    if (!c.doadapt && !c.doburnin) return false;
+    if (c.adaptend > 0 && i > c.adaptend) return false;
+    const bool ta = c.adaptint > 0 && i % c.adaptint == 0, tb = c.badaptint > 0 && i % c.badaptint == 0;
+    return ta || tb;
+  }
+
+  static int step(mcmcb_handle h, int nsteps) {
+    const mcmcb_config& c = h->cfg;
+    // the blob shares shared memory with the per-warp vectors
+    const size_t vec_bytes = sizeof(double) * (size_t)K2_WARPS * K2_NVEC * h->dp;
+    const bool smem_blob = h->blob_bytes + vec_bytes + 1024 <= h->max_smem;
+    int left = nsteps;
+    bool first = true;
+    while (left > 0 || first) {
+      first = false;
+      int seg = left;
+      for (int k = 1; k <= left; k++)
+        if (is_tick(c, h->k2_i + k)) { seg = k; break; }
+      K2Params p = params(h, seg);
+      int rc = smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p);
+      if (rc) return rc;
+      h->k2_i += seg;
+      left -= seg;
+      if (seg > 0 && is_tick(c, h->k2_i)) {
+        p.tick_i = (int)h->k2_i;
+        k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * h->npar, h->stream>>>(p, h->d_scratch);
+        h->launches++;
+        CK(cudaGetLastError());
+      }
+    }
+    return 0;
+  }
+
+  static ModelEntry entry() {
+    ModelEntry e{};
+    e.name = M::name();
+    e.kernel = 2;
+    e.npar = 0;
+    e.ny = NY;
+    e.alloc = &alloc;
+    e.init = &init;
+    e.step = &step;
+    e.fetch = &k2_fetch;
+    e.fetch_chain = &k2_fetch_chain;
     return e;
   }
 };
 
 struct BuiltinRegistrar {
-  BuiltinRegistrar() { register_model(K1<ExpReg>::entry()); }
+  BuiltinRegistrar() {
+    register_model(K1<ExpReg>::entry());
+    register_model(K2<GaussN>::entry());
+    register_model(K2<BananaN>::entry());
+    register_model(K2<HierN>::entry());
+  }
 } builtin_registrar;
 
 const ModelEntry* find_model(const char* name, int kernel) {
@@ -286,7 +633,8 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
-                  h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile};
+                  h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
+                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : h->dump_slots) {
@@ -370,6 +718,14 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   if (!h->d_sigma2) CK(cudaMalloc(&h->d_sigma2, sizeof(double) * nycol));
   if (!h->d_nobs) CK(cudaMalloc(&h->d_nobs, sizeof(int) * nycol));
   if (!h->d_tile) CK(cudaMalloc(&h->d_tile, sizeof(unsigned) * 4));
+  if (!h->d_cmat0_full) CK(cudaMalloc(&h->d_cmat0_full, sizeof(double) * (size_t)npar * npar));
+  {  // full symmetric copy built from the authoritative upper triangle
+    std::vector<double> full((size_t)npar * npar);
+    for (int j = 0; j < npar; j++)
+      for (int i = 0; i < npar; i++) full[(size_t)j * npar + i] = (i <= j) ? cmat0[(size_t)j * npar + i] : cmat0[(size_t)i * npar + j];
+    CK(cudaMemcpyAsync(h->d_cmat0_full, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   CK(cudaMemcpyAsync(h->d_cmat0, pkd.data(), sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_sigma2, sigma2, sizeof(double) * nycol, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_nobs, nobs, sizeof(int) * nycol, cudaMemcpyHostToDevice, h->stream));
@@ -379,7 +735,7 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
     int rc = h->model->alloc(h);
     if (rc) return rc;
   }
-  h->L = pick_lanes(h);
+  h->L = (h->model->kernel == 1) ? pick_lanes(h) : 32;
   int rc = h->model->init(h);
   if (rc) return rc;
   h->initial_set = true;
@@ -404,7 +760,8 @@ extern "C" int mcmcb_inject_uniforms(mcmcb_handle h, const double* u, size_t per
 static int dump_enqueue(mcmcb_handle h) {
   // snapshot theta (field-major, npar x pitch) device->device on the compute stream, then
   // device->pinned host on the copy stream, so the next launch overlaps the PCIe copy
-  const size_t bytes = sizeof(double) * (size_t)h->npar * h->pitch;
+  const bool k2 = h->model->kernel == 2;
+  const size_t bytes = k2 ? sizeof(double) * (size_t)h->cfg.nchains * h->dp : sizeof(double) * (size_t)h->npar * h->pitch;
   if (h->dump_slots.empty()) {
     h->dump_slots.resize(4);
     for (auto& s : h->dump_slots) {
@@ -423,7 +780,7 @@ static int dump_enqueue(mcmcb_handle h) {
       if (*it == k) { h->dump_fifo.erase(it); break; }
     h->dumps_dropped++;
   }
-  CK(cudaMemcpyAsync(s.dev, h->d_st /* theta is field 0 */, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(s.dev, k2 ? h->d_theta : h->d_st /* theta is field 0 */, bytes, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaEventRecord(s.ready, h->stream));
   CK(cudaStreamWaitEvent(h->copy_stream, s.ready, 0));
   CK(cudaMemcpyAsync(s.host, s.dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -443,8 +800,10 @@ extern "C" int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int
   if (cudaEventQuery(s.ev) != cudaSuccess) return 0;
   const long long N = h->cfg.nchains;
   if (out_bytes < sizeof(double) * (size_t)N * h->npar) return MCMCB_EINVAL;
+  const bool k2 = h->model->kernel == 2;
   for (int f = 0; f < h->npar; f++)
-    for (long long c = 0; c < N; c++) out[(size_t)c * h->npar + f] = s.host[(size_t)f * h->pitch + c];
+    for (long long c = 0; c < N; c++)
+      out[(size_t)c * h->npar + f] = k2 ? s.host[(size_t)c * h->dp + f] : s.host[(size_t)f * h->pitch + c];
   if (step) *step = s.step;
   s.state = 0;
   h->dump_fifo.pop_front();
@@ -485,113 +844,17 @@ extern "C" int mcmcb_sync(mcmcb_handle h) {
 }
 
 // ------------------------------------------------------------------ fetch
-static int fetch_fields(mcmcb_handle h, int f0, int nf, std::vector<double>& buf) {
-  buf.resize((size_t)nf * h->pitch);
-  CK(cudaMemcpyAsync(buf.data(), h->d_st + (size_t)f0 * h->pitch, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
-                     h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return 0;
-}
-
 extern "C" int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
-  if (!h || !what || !out || !h->d_st) return MCMCB_EINVAL;
+  if (!h || !what || !out || !h->initial_set) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
-  const long long N = h->cfg.nchains;
-  const int D = h->npar, NY = h->nycol, T = D * (D + 1) / 2;
-  const K1Layout Lo = k1_layout(D, NY);
-  std::string w(what);
-  std::vector<double> buf;
-  if (w == "counters") {
-    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
-    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
-    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    long long* o = (long long*)out;
-    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
-    for (long long c = 0; c < N; c++) {
-      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
-      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
-      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
-    }
-    return MCMCB_OK;
-  }
-  int f0 = -1, width = 0;
-  bool tri = false;
-  if (w == "par") { f0 = Lo.th; width = D; }
-  else if (w == "ss") { f0 = Lo.ss; width = NY; }
-  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
-  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
-  else if (w == "mean") { f0 = Lo.mean; width = D; }
-  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
-  else if (w == "cmat") { f0 = Lo.cm; tri = true; }
-  else if (w == "R") { f0 = Lo.r; tri = true; }
-  else if (w == "R2") { f0 = Lo.r2; tri = true; }
-  else if (w == "iC") { f0 = Lo.ic; tri = true; }
-  else return MCMCB_EINVAL;
-  double* o = (double*)out;
-  if (!tri) {
-    if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
-    int rc = fetch_fields(h, f0, width, buf);
-    if (rc) return rc;
-    for (int k = 0; k < width; k++)
-      for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
-  } else {
-    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
-    int rc = fetch_fields(h, f0, T, buf);
-    if (rc) return rc;
-    const bool sym = (w == "cmat" || w == "iC");
-    for (long long c = 0; c < N; c++)
-      for (int j = 0; j < D; j++)
-        for (int i = 0; i < D; i++) {
-          double v = 0.0;
-          if (i <= j) v = buf[(size_t)(j * (j + 1) / 2 + i) * h->pitch + c];
-          else if (sym) v = buf[(size_t)(i * (i + 1) / 2 + j) * h->pitch + c];
-          o[(size_t)c * D * D + (size_t)j * D + i] = v;  // column-major
-        }
-  }
-  return MCMCB_OK;
+  return h->model->fetch(h, what, out, out_bytes);
 }
 
 extern "C" int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
                                  double* s2chain_out, int* nrows) {
-  if (!h || !h->d_st || chain < 0 || chain >= h->store_chains) return MCMCB_EINVAL;
+  if (!h || !h->initial_set || chain < 0 || chain >= h->store_chains) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
-  const int D = h->npar, NY = h->nycol, cap = h->cfg.nsimu;
-  const K1Layout Lo = k1_layout(D, NY);
-  int iv[3];
-  const int fld[3] = {Lo.i_chainind, Lo.i_cnt, Lo.i_simuind};
-  for (int k = 0; k < 3; k++)
-    CK(cudaMemcpyAsync(&iv[k], h->d_ist + (size_t)fld[k] * h->pitch + chain, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  int rows = std::min(iv[0], cap), cnt = iv[1], simuind = iv[2];
-  if (nrows) *nrows = rows;
-  if (ld < rows || (s2chain_out && ld < simuind)) return MCMCB_EINVAL;
-  std::vector<double> r((size_t)rows * (D + NY)), cn((size_t)rows), s2((size_t)std::max(simuind, 1) * NY);
-  if (rows > 0) {
-    CK(cudaMemcpyAsync(r.data(), h->d_store_rows + (size_t)chain * cap * (D + NY), sizeof(double) * r.size(),
-                       cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(cn.data(), h->d_store_cnt + (size_t)chain * cap, sizeof(double) * cn.size(), cudaMemcpyDeviceToHost,
-                       h->stream));
-  }
-  if (s2chain_out && simuind > 0)
-    CK(cudaMemcpyAsync(s2.data(), h->d_store_s2 + (size_t)chain * cap * NY, sizeof(double) * (size_t)simuind * NY,
-                       cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (rows > 0) cn[rows - 1] = (double)cnt;  // the current row's count lives in the chain state
-  for (int i = 0; i < rows; i++) {
-    if (chain_out) {
-      for (int k = 0; k < D; k++) chain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + k];
-      chain_out[(size_t)D * ld + i] = cn[i];
-    }
-    if (sschain_out) {
-      for (int k = 0; k < NY; k++) sschain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + D + k];
-      sschain_out[(size_t)NY * ld + i] = cn[i];
-    }
-  }
-  if (s2chain_out)
-    for (int i = 0; i < simuind; i++)
-      for (int k = 0; k < NY; k++) s2chain_out[(size_t)k * ld + i] = s2[(size_t)i * NY + k];
-  return MCMCB_OK;
+  return h->model->fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows);
 }
 
 // ------------------------------------------------------------------ introspection
@@ -604,7 +867,7 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (nycol) *nycol = h->nycol;
   if (lanes) *lanes = h->L;
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
-  if (tpb) *tpb = K1_THREADS;
+  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? K2_THREADS : K1_THREADS;
   if (blocks) *blocks = h->blocks;
   if (smem) *smem = h->smem;
   return MCMCB_OK;

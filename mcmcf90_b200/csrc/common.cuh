@@ -51,10 +51,27 @@ struct Rng {
   const double* inj;      // injected stream of this chain (nullptr => Philox)
   unsigned long long inj_n;
   uint32_t cache_lo, cache_hi;
+  unsigned long long cache_blk;  // Philox block the cached upper half belongs to
   bool cache_valid;
   bool has_spare;  // polar spare, mcmcrand.F90:172-173
   double spare;
   int exhausted;
+
+  // uniform number k of this chain's stream, without touching the stream position
+  __device__ __forceinline__ double uniform_at(unsigned long long k) {
+    if (inj != nullptr) {
+      if (k < inj_n) return inj[k];
+      exhausted = 1;
+      return 0.5;
+    }
+    const unsigned long long blk = k >> 1;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), o);
+    const unsigned long long bits = (k & 1ull) ? (((unsigned long long)o[3] << 32) | o[2])
+                                               : (((unsigned long long)o[1] << 32) | o[0]);
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+  }
 
   __device__ __forceinline__ double uniform() {
     if (inj != nullptr) {
@@ -65,7 +82,7 @@ struct Rng {
     }
     unsigned long long k = nd++;
     uint32_t lo, hi;
-    if ((k & 1ull) && cache_valid) {
+    if ((k & 1ull) && cache_valid && cache_blk == (k >> 1)) {
       lo = cache_lo; hi = cache_hi;
       cache_valid = false;
     } else {
@@ -78,6 +95,7 @@ struct Rng {
       } else {
         lo = o[0]; hi = o[1];
         cache_lo = o[2]; cache_hi = o[3];
+        cache_blk = blk;
         cache_valid = true;
       }
     }

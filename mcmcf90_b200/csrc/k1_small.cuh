@@ -376,7 +376,7 @@ __device__ __forceinline__ void k1_load_state(K1State<M::NPAR, M::NY>& S, const 
   g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
   g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
   g.inj_n = p.inj_per_chain;
-  g.cache_valid = false; g.cache_lo = g.cache_hi = 0;
+  g.cache_valid = false; g.cache_lo = g.cache_hi = 0; g.cache_blk = 0;
   g.has_spare = ist[Lo.i_hasspare * p.pitch] != 0;
   g.spare = st[Lo.spare * p.pitch];
   g.exhausted = 0;

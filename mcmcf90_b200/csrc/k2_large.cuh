@@ -1,0 +1,655 @@
+// K2: large-npar sampler, one warp per chain, run-time npar (<= 256).
+//
+// The proposal factor no longer fits in registers (d=100: 5050 doubles), so it lives in HBM,
+// one private d x d matrix per chain, and is streamed through the warp once per proposal:
+// row-major upper triangle, lanes own output columns j = lane + 32 m, the loop runs over rows
+// i, so every row segment R(i, i..d-1) is one coalesced read and no reduction is needed
+// (p_j = sum_{i<=j} R(i,j) z_i accumulates in registers).  Vectors (theta, proposal, z) sit in
+// shared memory, one slab per warp; the user-model blob is TMA-staged once per CTA.
+//
+// What differs from the reference's arithmetic (all rounding-level):
+//  * second-stage proposal uses (R'z)/drscale instead of a stored R2 = R/drscale;
+//  * the DR ratio needs no inverse covariance: with y1 = x + R'z1, y2 = x + R'z2/drscale,
+//    (y2-y1)' iC (y2-y1) = |z2/drscale - z1|^2 and (x-y1)' iC (x-y1) = |z1|^2 exactly
+//    (MCMC_DRAM.F90:181-183 with iC = inv(R'R), MCMC_adapt.F90:216-224) -- no dpotri, no iC
+//    traffic, and more accurate than forming iC;
+//  * normals are generated 32 candidate pairs at a time (Philox is counter based) and compacted
+//    in stream order, which consumes exactly the draws the sequential polar loop would.
+//
+// Adaptation runs in a separate kernel (k2_adapt_kernel, one CTA per chain) at the ticks of
+// MCMC_adapt.F90:45-46: accepted rows are logged with their weights into a per-chain row buffer
+// by the step kernel and replayed through the covmat recursion (matutils.F90:283-310) in
+// order, then dpotf2-ordered Cholesky writes the new factor.
+#pragma once
+#include "common.cuh"
+
+namespace mcmcb {
+
+constexpr int K2_WARPS = 8;            // warps (= chains in flight) per CTA
+constexpr int K2_THREADS = K2_WARPS * 32;
+constexpr int K2_MAXM = 8;             // npar <= 32 * K2_MAXM
+constexpr int K2_NVEC = 6;             // per-warp shared vectors
+constexpr int K2_ADAPT_THREADS = 256;
+
+struct K2Layout {  // scalar SoA fields
+  int ss, pri, s2, wsum, spare, rama, nf;
+  int i_stayed, i_bnd, i_dracc, i_drtry, i_chainind, i_simuind, i_status, i_hasspare, i_cnt, i_pend, i_ndlo, i_ndhi,
+      i_nbuf, i_nf;
+};
+__host__ __device__ constexpr K2Layout k2_layout(int NY) {
+  K2Layout l{};
+  int o = 0;
+  l.ss = o; o += NY;
+  l.pri = o; o += 1;
+  l.s2 = o; o += NY;
+  l.wsum = o; o += 1;
+  l.spare = o; o += 1;
+  l.rama = o; o += 1;
+  l.nf = o;
+  int k = 0;
+  l.i_stayed = k++; l.i_bnd = k++; l.i_dracc = k++; l.i_drtry = k++; l.i_chainind = k++; l.i_simuind = k++;
+  l.i_status = k++; l.i_hasspare = k++; l.i_cnt = k++; l.i_pend = k++; l.i_ndlo = k++; l.i_ndhi = k++;
+  l.i_nbuf = k++;
+  l.i_nf = k;
+  return l;
+}
+
+struct K2Params {
+  DevCfg c;
+  long long nchains, pitch, chain_offset;
+  unsigned long long seed;
+  int nsteps, d, dp;  // dp = d rounded up to a multiple of 32
+  double* st;
+  int* ist;
+  double* theta;   // [chain][dp]
+  double* mean;    // [chain][dp]
+  double* Rm;      // [chain][d*d]  row-major upper factor (Cholesky mode)
+  double* cmat;    // [chain][d*d]  symmetric, full
+  double* rowbuf;  // [chain][cap][d+1]  completed rows + weights since the last adaptation
+  int rowcap;
+  const double* par0;      // [chain][d]
+  const double* cmat0;     // [d*d] column-major full
+  const double* sigma2_0;
+  const int* nobs;
+  const double* blob;
+  unsigned long long blob_n;
+  unsigned blob_bytes;
+  const double* prior;
+  const double* inj;
+  unsigned long long inj_per_chain;
+  int store_chains, store_rows;
+  double* store_rows_p;
+  double* store_cnt_p;
+  double* store_s2_p;
+  unsigned int* tile_counter;
+  int tick_i;      // adaptation kernel: the step index i of this tick
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+
+// n normals in the reference's draw order (mcmcrand.F90:60-83,166-190), produced by the whole
+// warp: lane l examines candidate pair l of the stream; accepted pairs are compacted in order.
+__device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane) {
+  int filled = 0;
+  if (g.has_spare && n > 0) {
+    if (lane == 0) zs[0] = g.spare;
+    g.has_spare = false;
+    filled = 1;
+  }
+  while (filled < n) {
+    const double u1 = g.uniform_at(g.nd + 2ull * lane), u2 = g.uniform_at(g.nd + 2ull * lane + 1ull);
+    const double x1 = 2.0 * u1 - 1.0, x2 = 2.0 * u2 - 1.0;
+    const double xx = x1 * x1 + x2 * x2;
+    const bool ok = (xx < 1.0 && xx != 0.0);
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (g.exhausted) {  // injected stream ran out: fill with zeros, flag is reported by the caller
+      for (int k = filled + lane; k < n; k += 32) zs[k] = 0.0;
+      filled = n;
+      break;
+    }
+    const int need = (n - filled + 1) >> 1;  // accepted pairs still needed
+    const int have = __popc(m);
+    const int use = have < need ? have : need;
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    double sp = 0.0;
+    bool made_spare = false;
+    if (ok && rank < use) {
+      const double z = sqrt(-2.0 * log(xx) / xx);
+      const int idx = filled + 2 * rank;
+      zs[idx] = z * x2;                 // second of the pair is returned first (mcmcrand.F90:183-185)
+      if (idx + 1 < n) zs[idx + 1] = z * x1;
+      else { sp = z * x1; made_spare = true; }
+    }
+    const unsigned ms = __ballot_sync(FULL, made_spare);
+    if (ms) {
+      g.spare = __shfl_sync(FULL, sp, __ffs(ms) - 1);
+      g.has_spare = true;
+    }
+    int consumed = 32;
+    if (have >= need) consumed = (int)__fns(m, 0, need) + 1;  // stop right after the last pair used
+    g.nd += 2ull * consumed;
+    filled += 2 * use;
+  }
+  __syncwarp();
+}
+
+// p_j = sum_{i<=j} R(i,j) v_i for the columns this lane owns; R row-major upper
+__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ R, const double* vs, int d, int lane,
+                                             double (&acc)[K2_MAXM]) {
+#pragma unroll
+  for (int m = 0; m < K2_MAXM; m++) acc[m] = 0.0;
+  for (int i = 0; i < d; i++) {
+    const double vi = vs[i];
+    const double* row = R + (size_t)i * d;
+#pragma unroll
+    for (int m = 0; m < K2_MAXM; m++) {
+      const int j = lane + 32 * m;
+      if (j >= i && j < d) acc[m] = fma(row[j], vi, acc[m]);
+    }
+  }
+}
+
+template <class M>
+__global__ void k2_init_kernel(K2Params p) {
+  constexpr int NY = M::NY;
+  constexpr K2Layout Lo = k2_layout(NY);
+  const long long c = blockIdx.x;
+  if (c >= p.nchains) return;
+  const int d = p.d;
+  for (int k = threadIdx.x; k < p.dp; k += blockDim.x) {
+    double v = k < d ? p.par0[c * d + k] : 0.0;
+    p.theta[c * p.dp + k] = v;
+    p.mean[c * p.dp + k] = v;
+  }
+  for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
+    p.cmat[(size_t)c * d * d + k] = p.cmat0[k];
+    p.Rm[(size_t)c * d * d + k] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    double* st = p.st + c;
+    int* ist = p.ist + c;
+    for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = 0.0; st[(Lo.s2 + k) * p.pitch] = p.sigma2_0[k]; }
+    st[Lo.pri * p.pitch] = 0.0;
+    st[Lo.wsum * p.pitch] = (double)p.c.initcmatn;
+    st[Lo.spare * p.pitch] = 0.0;
+    st[Lo.rama * p.pitch] = 0.0;
+    for (int k = 0; k < Lo.i_nf; k++) ist[k * p.pitch] = 0;
+  }
+}
+
+// dpotf2('U') order on a row-major copy (A(i,k) at i*d+k); whole CTA; returns 0 or failing column+1.
+// Only the upper triangle is read or written.
+__device__ __forceinline__ int cta_cholesky_rowmajor(double* A, int d, double* red /* >= blockDim/32 doubles */) {
+  __shared__ int fail;
+  if (threadIdx.x == 0) fail = 0;
+  __syncthreads();
+  for (int j = 0; j < d; j++) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < j; i += blockDim.x) { double a = A[(size_t)i * d + j]; t = fma(a, a, t); }
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+      double ajj = A[(size_t)j * d + j] - s;
+      if (!(ajj > 0.0)) fail = j + 1;
+      red[0] = sqrt(ajj);
+    }
+    __syncthreads();
+    if (fail) return fail;
+    const double ajj = red[0];
+    const double rajj = 1.0 / ajj;
+    for (int k = j + threadIdx.x; k < d; k += blockDim.x) {
+      if (k == j) { A[(size_t)j * d + j] = ajj; continue; }
+      double tt = 0.0;
+      for (int i = 0; i < j; i++) tt = fma(A[(size_t)i * d + k], A[(size_t)i * d + j], tt);
+      A[(size_t)j * d + k] = (A[(size_t)j * d + k] - tt) * rajj;
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+
+// R = chol(cm) * 2.4/sqrt(d) into row-major Rm; cm is full symmetric (either order).  Scratch = Rm itself:
+// on failure the old factor must survive (MCMC_adapt.F90:169-171), so work in `tmp` and copy on success.
+__device__ __forceinline__ bool cta_calculate_R(const double* cm, double* Rm, double* tmp, int d, double* red) {
+  for (int k = threadIdx.x; k < d * d; k += blockDim.x) tmp[k] = cm[k];
+  __syncthreads();
+  const int info = cta_cholesky_rowmajor(tmp, d, red);
+  if (info) return false;
+  const double sq = sqrt((double)d);
+  for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
+    const int i = k / d, j = k - i * d;
+    Rm[k] = (j >= i) ? tmp[k] * 2.4 / sq : 0.0;
+  }
+  __syncthreads();
+  return true;
+}
+
+// Initial factor, MCMC_init.F90:108-110.  One CTA per chain; tmp = that chain's slice of a scratch buffer.
+__global__ void k2_initR_kernel(K2Params p, double* scratch) {
+  __shared__ double red[K2_ADAPT_THREADS / 32];
+  const long long c = blockIdx.x;
+  const int d = p.d;
+  constexpr K2Layout Lo = k2_layout(1);
+  bool ok = cta_calculate_R(p.cmat + (size_t)c * d * d, p.Rm + (size_t)c * d * d, scratch + (size_t)c * d * d, d, red);
+  if (!ok && threadIdx.x == 0) p.ist[Lo.i_status * p.pitch + c] |= MCMCB_ST_CHOLFAIL;
+}
+
+// One row of the covmat recursion (matutils.F90:283-310) by the whole CTA; dvec = shared scratch of d doubles.
+__device__ __forceinline__ void cta_absorb(const double* x, double w, double* cm, double* mean, double& wsum, int d,
+                                           double* dvec) {
+  if (wsum > 0.0) {
+    for (int k = threadIdx.x; k < d; k += blockDim.x) dvec[k] = x[k] - mean[k];
+    __syncthreads();
+    const double f1 = w / (wsum + w - 1.0), f2 = wsum / (wsum + w), f3 = w / (wsum + w);
+    for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
+      const int a = k / d, b = k - a * d;
+      cm[k] = cm[k] + f1 * (f2 * (dvec[a] * dvec[b]) - cm[k]);
+    }
+    for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = mean[k] + f3 * dvec[k];
+    wsum = w + wsum;
+    __syncthreads();
+  } else if (w > 0.0) {
+    for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = x[k];
+    for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = 0.0;
+    wsum = w;
+    __syncthreads();
+  }
+}
+
+// MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
+__global__ void k2_adapt_kernel(K2Params p, double* scratch) {
+  extern __shared__ double sh[];  // d doubles
+  __shared__ double red[K2_ADAPT_THREADS / 32];
+  constexpr K2Layout Lo = k2_layout(1);
+  const long long c = blockIdx.x;
+  const DevCfg& cf = p.c;
+  const int d = p.d, i = p.tick_i;
+  double* st = p.st + c;
+  int* ist = p.ist + c;
+  double* cm = p.cmat + (size_t)c * d * d;
+  double* Rm = p.Rm + (size_t)c * d * d;
+  double* mean = p.mean + c * p.dp;
+  double* theta = p.theta + c * p.dp;
+  double* rb = p.rowbuf + (size_t)c * p.rowcap * (d + 1);
+  double* tmp = scratch + (size_t)c * d * d;
+  const int ma = cf.adaptint > 0 ? i % cf.adaptint : 1;
+  const int mb = cf.badaptint > 0 ? i % cf.badaptint : 1;
+  if (ma != 0 && mb != 0) return;
+  double wsum = st[Lo.wsum * p.pitch];
+  const int nbuf = ist[Lo.i_nbuf * p.pitch];
+  if (i < cf.burnintime && cf.doburnin && mb == 0) {  // MCMC_adapt.F90:60-102
+    const double staypc = (double)ist[Lo.i_stayed * p.pitch] / (double)i;
+    if (staypc > 1.0 - cf.scalelimit) {
+      for (int k = threadIdx.x; k < d * d; k += blockDim.x) Rm[k] = Rm[k] / cf.scalefactor;
+    } else if (staypc < cf.scalelimit) {
+      for (int k = threadIdx.x; k < d * d; k += blockDim.x) Rm[k] = Rm[k] * cf.scalefactor;
+    } else {
+      // restart the accumulation at the open row with its full count; R = chol(cmat0) (see K1)
+      for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = p.cmat0[k];
+      for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = p.par0[c * d + k];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        st[Lo.wsum * p.pitch] = (double)cf.initcmatn;
+        ist[Lo.i_pend * p.pitch] = ist[Lo.i_cnt * p.pitch];
+        ist[Lo.i_nbuf * p.pitch] = 0;
+      }
+      if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
+    }
+  } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
+    for (int r = 0; r < nbuf; r++) cta_absorb(rb + (size_t)r * (d + 1), rb[(size_t)r * (d + 1) + d], cm, mean, wsum, d, sh);
+    cta_absorb(theta, (double)ist[Lo.i_pend * p.pitch], cm, mean, wsum, d, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st[Lo.wsum * p.pitch] = wsum;
+      ist[Lo.i_pend * p.pitch] = 0;
+      ist[Lo.i_nbuf * p.pitch] = 0;
+    }
+    if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
+  }
+}
+
+// rank-1 update / downdate of the row-major upper factor by one warp (dchud.f:122-139, dchdd.f:141-179).
+// x in shared (overwritten); wk = 2 more shared vectors.
+__device__ __forceinline__ void warp_chud(double* R, double* x, int d, int lane) {
+  for (int i = 0; i < d; i++) {
+    double* row = R + (size_t)i * d;
+    double c = 0.0, s = 0.0;
+    if (lane == 0) {
+      double rii = row[i], xi = x[i];
+      drotg(rii, xi, c, s);
+      row[i] = rii;
+    }
+    c = __shfl_sync(FULL, c, 0);
+    s = __shfl_sync(FULL, s, 0);
+    for (int j = i + 1 + lane; j < d; j += 32) {
+      const double rij = row[j], xj = x[j];
+      row[j] = c * rij + s * xj;
+      x[j] = c * xj - s * rij;
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ bool warp_chdd(double* R, double* x, double* sv, double* cv, int d, int lane) {
+  // solve R' a = x (forward substitution, row sweep), result in sv
+  for (int k = lane; k < d; k += 32) sv[k] = x[k];
+  __syncwarp();
+  for (int i = 0; i < d; i++) {
+    const double* row = R + (size_t)i * d;
+    double ai = 0.0;
+    if (lane == 0) { ai = sv[i] / row[i]; sv[i] = ai; }
+    ai = __shfl_sync(FULL, ai, 0);
+    for (int j = i + 1 + lane; j < d; j += 32) sv[j] -= row[j] * ai;
+    __syncwarp();
+  }
+  // classic dnrm2 + rotation recurrences: short scalar loops, done redundantly by every lane
+  double norm;
+  if (d == 1) {
+    norm = fabs(sv[0]);
+  } else {
+    double scale = 0.0, ssq = 1.0;
+    for (int k = 0; k < d; k++) {
+      const double v = sv[k];
+      if (v != 0.0) {
+        const double a = fabs(v);
+        if (scale < a) { const double t = scale / a; ssq = 1.0 + ssq * t * t; scale = a; }
+        else { const double t = a / scale; ssq = ssq + t * t; }
+      }
+    }
+    norm = scale * sqrt(ssq);
+  }
+  if (!(norm < 1.0)) return false;
+  double alpha = sqrt(1.0 - norm * norm);
+  __syncwarp();
+  if (lane == 0) {
+    for (int i = d - 1; i >= 0; i--) {
+      const double scale = alpha + fabs(sv[i]);
+      const double a = alpha / scale, b = sv[i] / scale;
+      const double nr = sqrt(a * a + b * b);
+      cv[i] = a / nr;
+      sv[i] = b / nr;
+      alpha = scale * nr;
+    }
+  }
+  __syncwarp();
+  // apply: per column j, xx runs from row j down to row 0; lanes own columns
+  double xx[K2_MAXM];
+#pragma unroll
+  for (int m = 0; m < K2_MAXM; m++) xx[m] = 0.0;
+  for (int i = d - 1; i >= 0; i--) {
+    double* row = R + (size_t)i * d;
+    const double c = cv[i], s = sv[i];
+#pragma unroll
+    for (int m = 0; m < K2_MAXM; m++) {
+      const int j = lane + 32 * m;
+      if (j >= i && j < d) {
+        const double rij = row[j];
+        const double t = c * xx[m] + s * rij;
+        row[j] = c * rij - s * xx[m];
+        xx[m] = t;
+      }
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
+template <class M, bool SMEM>
+__global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_constant__ K2Params p) {
+  constexpr int NY = M::NY;
+  constexpr K2Layout Lo = k2_layout(NY);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int d = p.d, dp = p.dp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DevCfg& c = p.c;
+
+  // dynamic shared memory: [per-warp vectors][model blob]
+  double* vecs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * K2_NVEC * dp;
+  double *th = vecs, *prop = vecs + dp, *z1 = vecs + 2 * dp, *z2 = vecs + 3 * dp, *w1 = vecs + 4 * dp,
+         *w2 = vecs + 5 * dp;
+  const double* data = p.blob;
+  if (SMEM) {
+    unsigned char* blob_s = smem_raw + sizeof(double) * (size_t)K2_WARPS * K2_NVEC * dp;
+    tma_stage_blob(blob_s, p.blob, p.blob_bytes, &mbar);
+    data = reinterpret_cast<const double*>(blob_s);
+  }
+  mcmcb_ctx ctx;
+  ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = lane; ctx.nlanes = 32;
+  ctx.exp2_tab = nullptr; ctx.tab_slot = lane & 15;
+
+  for (;;) {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if ((long long)tile >= p.nchains) break;
+    const long long cc = tile;
+    double* st = p.st + cc;
+    int* ist = p.ist + cc;
+    double* Rm = p.Rm + (size_t)cc * d * d;
+    double* gth = p.theta + cc * dp;
+    double* rb = p.rowbuf + (size_t)cc * p.rowcap * (d + 1);
+
+    for (int k = lane; k < dp; k += 32) { th[k] = gth[k]; prop[k] = gth[k]; }
+    double ss1[NY], s2[NY];
+#pragma unroll
+    for (int k = 0; k < NY; k++) { ss1[k] = st[(Lo.ss + k) * p.pitch]; s2[k] = st[(Lo.s2 + k) * p.pitch]; }
+    double pri1 = st[Lo.pri * p.pitch], rama = st[Lo.rama * p.pitch];
+    int stayed = ist[Lo.i_stayed * p.pitch], bnd = ist[Lo.i_bnd * p.pitch], dracc = ist[Lo.i_dracc * p.pitch];
+    int drtry = ist[Lo.i_drtry * p.pitch], chainind = ist[Lo.i_chainind * p.pitch];
+    int simuind = ist[Lo.i_simuind * p.pitch], status = ist[Lo.i_status * p.pitch];
+    int cnt = ist[Lo.i_cnt * p.pitch], pend = ist[Lo.i_pend * p.pitch], nbuf = ist[Lo.i_nbuf * p.pitch];
+    Rng g;
+    g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * p.pitch] << 32) | (unsigned)ist[Lo.i_ndlo * p.pitch];
+    g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
+    g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
+    g.inj_n = p.inj_per_chain;
+    g.cache_valid = false; g.cache_lo = g.cache_hi = 0; g.cache_blk = 0;
+    g.has_spare = ist[Lo.i_hasspare * p.pitch] != 0;
+    g.spare = st[Lo.spare * p.pitch];
+    g.exhausted = 0;
+    const bool stored = (cc < p.store_chains);
+    double* srow = p.store_rows_p + (size_t)cc * p.store_rows * (d + NY);
+    double* scnt = p.store_cnt_p + (size_t)cc * p.store_rows;
+    double* ss2st = p.store_s2_p + (size_t)cc * p.store_rows * NY;
+    __syncwarp();
+
+    int phase = (simuind == 0) ? -1 : 0;
+    int done = 0;
+    double ss2[NY], pri2 = 0.0, a12 = 0.0, z1sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < NY; k++) ss2[k] = 0.0;
+
+    while (phase < 0 || done < p.nsteps) {
+      // ---------------- proposal
+      bool inb = true;
+      if (phase >= 0) {
+        double* zs = (phase == 0) ? z1 : z2;
+        warp_normals(g, zs, d, lane);
+        double acc[K2_MAXM];
+        tri_matvec_t(Rm, zs, d, lane, acc);
+        const double sc = (phase == 0) ? 1.0 : 1.0 / c.drscale;
+#pragma unroll
+        for (int m = 0; m < K2_MAXM; m++) {
+          const int j = lane + 32 * m;
+          if (j < d) prop[j] = th[j] + (phase == 0 ? acc[m] : acc[m] * sc);
+        }
+        __syncwarp();
+        inb = M::checkbounds(prop, d, ctx);
+      }
+      // ---------------- user model (cooperative over the 32 lanes)
+      double ssn[NY];
+      M::ssfunction(prop, d, NY, ctx, ssn);
+#pragma unroll
+      for (int k = 0; k < NY; k++) ssn[k] = warp_sum(ssn[k]);
+      const double prn = M::priorfun(prop, d, ctx);
+      // ---------------- accept / reject (warp uniform)
+      bool reject = false;
+      if (phase < 0) {
+#pragma unroll
+        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
+        pri1 = prn;
+        chainind = 1; simuind = 1; cnt = 1; pend = 1;
+        if (stored) {
+          for (int k = lane; k < d; k += 32) srow[k] = th[k];
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NY; k++) { srow[d + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
+          }
+        }
+        phase = 0;
+        continue;
+      }
+      if (phase == 0) {
+        if (!inb) {
+          if (!c.dodr || c.method == MCMCB_RAM) bnd++;
+#pragma unroll
+          for (int k = 0; k < NY; k++) ssn[k] = DBL_HUGE;
+          a12 = (c.method != MCMCB_RAM) ? 0.0 : rama;
+          reject = true;
+        } else {
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
+          a12 = alpha_from_tst(-0.5 * (sum + (prn - pri1)));
+          reject = mh_reject(a12, g);
+        }
+        rama = a12;
+        if (reject && c.dodr) {
+          drtry++;
+#pragma unroll
+          for (int k = 0; k < NY; k++) ss2[k] = ssn[k];
+          pri2 = inb ? prn : DBL_HUGE;
+          double t = 0.0;
+          for (int k = lane; k < d; k += 32) t = fma(z1[k], z1[k], t);
+          z1sq = warp_sum(t);
+          phase = 1;
+          continue;
+        }
+      } else {
+        if (!inb) {
+          bnd++;
+          reject = true;
+        } else {
+          double a32;
+          if (a12 == 0.0) {
+            a32 = 0.0;
+          } else {
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < NY; k++) sum += (ss2[k] - ssn[k]) / s2[k];
+            a32 = fmin(1.0, exp_subnormal_safe(-0.5 * (sum + (pri2 - prn))));
+          }
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
+          const double l2 = -0.5 * (sum + (prn - pri1));
+          double t = 0.0;
+          const double sc = 1.0 / c.drscale;
+          for (int k = lane; k < d; k += 32) { const double v = z2[k] * sc - z1[k]; t = fma(v, v, t); }
+          const double q1 = -0.5 * (warp_sum(t) - z1sq);
+          double a13 = exp_subnormal_safe(l2 + q1) * (1.0 - a32) / (1.0 - a12);
+          if (a13 == a13) a13 = fmin(1.0, a13);
+          reject = mh_reject(a13, g);
+          if (!reject) dracc++;
+        }
+        phase = 0;
+      }
+      // ---------------- end of step
+      const int i = simuind + 1;
+      simuind = i;
+      const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
+      if (reject) {
+        stayed++;
+        cnt++; pend++;
+      } else {
+        if (absorbing) {  // log the completed row and its not-yet-counted weight for the adaptation kernel
+          if (nbuf < p.rowcap) {
+            for (int k = lane; k < d; k += 32) rb[(size_t)nbuf * (d + 1) + k] = th[k];
+            if (lane == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)pend;
+            nbuf++;
+          } else {
+            status |= MCMCB_ST_STORE_FULL;
+          }
+        }
+        if (stored && chainind - 1 < p.store_rows && lane == 0) scnt[chainind - 1] = (double)cnt;
+        for (int k = lane; k < d; k += 32) th[k] = prop[k];
+#pragma unroll
+        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
+        pri1 = prn;
+        chainind++;
+        cnt = 1; pend = 1;
+        __syncwarp();
+      }
+      if (c.updatesigma) {
+#pragma unroll
+        for (int k = 0; k < NY; k++) {
+          const double gg = g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + ss1[k]));
+          s2[k] = 1.0 / gg;
+        }
+      }
+      if (stored) {
+        if (!reject) {
+          if (chainind - 1 < p.store_rows) {
+            for (int k = lane; k < d; k += 32) srow[(size_t)(chainind - 1) * (d + NY) + k] = th[k];
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (d + NY) + d + k] = ss1[k];
+            }
+          } else {
+            status |= MCMCB_ST_STORE_FULL;
+          }
+        }
+        if (c.updatesigma && i - 1 < p.store_rows && lane == 0) {
+#pragma unroll
+          for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
+        }
+      }
+      if (c.method == MCMCB_RAM && c.doadapt && !(i < c.burnintime && c.doburnin)) {  // MCMC_run_ram.F90:104-179
+        const double a = 1.0 / pow((double)(float)i, c.nuparam) * (rama - c.alphatarget);
+        double t = 0.0;
+        for (int k = lane; k < d; k += 32) t = fma(z1[k], z1[k], t);
+        // the reference sums u**2 sequentially; a lane-strided tree sum differs by rounding only
+        const double su2 = warp_sum(t);
+        if (a >= 0.0) {
+          for (int k = lane; k < d; k += 32) w1[k] = z1[k] / su2 * a;
+          __syncwarp();
+          warp_chud(Rm, w1, d, lane);
+        } else {
+          for (int k = lane; k < d; k += 32) w1[k] = -z1[k] / su2 * a;
+          __syncwarp();
+          if (!warp_chdd(Rm, w1, w2, z2, d, lane)) status |= MCMCB_ST_DOWNDATE_FAIL;
+        }
+        __threadfence_block();
+        __syncwarp();
+      }
+      if (g.exhausted) status |= MCMCB_ST_RNG_EXHAUSTED;
+      done++;
+    }
+
+    // ---- write state back
+    for (int k = lane; k < dp; k += 32) gth[k] = th[k];
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = ss1[k]; st[(Lo.s2 + k) * p.pitch] = s2[k]; }
+      st[Lo.pri * p.pitch] = pri1; st[Lo.rama * p.pitch] = rama; st[Lo.spare * p.pitch] = g.spare;
+      ist[Lo.i_stayed * p.pitch] = stayed; ist[Lo.i_bnd * p.pitch] = bnd; ist[Lo.i_dracc * p.pitch] = dracc;
+      ist[Lo.i_drtry * p.pitch] = drtry; ist[Lo.i_chainind * p.pitch] = chainind;
+      ist[Lo.i_simuind * p.pitch] = simuind; ist[Lo.i_status * p.pitch] = status;
+      ist[Lo.i_hasspare * p.pitch] = g.has_spare ? 1 : 0;
+      ist[Lo.i_cnt * p.pitch] = cnt; ist[Lo.i_pend * p.pitch] = pend; ist[Lo.i_nbuf * p.pitch] = nbuf;
+      ist[Lo.i_ndlo * p.pitch] = (int)(unsigned)(g.nd & 0xffffffffull);
+      ist[Lo.i_ndhi * p.pitch] = (int)(unsigned)(g.nd >> 32);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace mcmcb

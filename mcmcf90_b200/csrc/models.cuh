@@ -85,4 +85,86 @@ struct ExpReg {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// Run-time-npar models for the warp-per-chain kernel (NPAR = 0): theta lives in shared memory,
+// the 32 lanes of the warp split the work and the kernel adds their partial sums.
+
+// Gaussian target ss = (theta-mu)' Lam (theta-mu) (testcases/mcmcrun4.F90:47); BASELINE config C2.
+// blob: [d, 0, mu[dpad], Lam[d*d]]; Lam must be symmetric (row i is read as column i).
+struct GaussN {
+  static constexpr int NPAR = 0;
+  static constexpr int NY = 1;
+  static const char* name() { return "gauss"; }
+  __device__ __forceinline__ static bool checkbounds(const double*, int, const mcmcb_ctx&) { return true; }
+  __device__ __forceinline__ static double priorfun(const double* theta, int len, const mcmcb_ctx& c) {
+    return mcmcb_default_priorfun(theta, len, c);
+  }
+  __device__ __forceinline__ static void ssfunction(const double* theta, int npar, int, const mcmcb_ctx& c,
+                                                    double* ss) {
+    const int d = npar, dpad = (d + 1) & ~1;
+    const double* __restrict__ mu = c.data + 2;
+    const double* __restrict__ lam = c.data + 2 + dpad;
+    double acc = 0.0;
+    for (int i = c.lane; i < d; i += c.nlanes) {
+      double w = 0.0;
+      for (int j = 0; j < d; j++) w = fma(lam[(size_t)j * d + i], theta[j] - mu[j], w);
+      acc = fma(w, theta[i] - mu[i], acc);
+    }
+    ss[0] = acc;
+  }
+};
+
+// Twisted Gaussian ("banana"): phi = (t1, t2 + b t1^2 - 100 b, t3..td),
+// ss = phi1^2/100 + sum_{i>=2} phi_i^2.   blob: [d, b]
+struct BananaN {
+  static constexpr int NPAR = 0;
+  static constexpr int NY = 1;
+  static const char* name() { return "banana"; }
+  __device__ __forceinline__ static bool checkbounds(const double*, int, const mcmcb_ctx&) { return true; }
+  __device__ __forceinline__ static double priorfun(const double* theta, int len, const mcmcb_ctx& c) {
+    return mcmcb_default_priorfun(theta, len, c);
+  }
+  __device__ __forceinline__ static void ssfunction(const double* theta, int npar, int, const mcmcb_ctx& c,
+                                                    double* ss) {
+    const double b = c.data[1];
+    double acc = 0.0;
+    for (int i = c.lane; i < npar; i += c.nlanes) {
+      double v;
+      if (i == 0) { v = theta[0]; acc = fma(v, v / 100.0, acc); continue; }
+      if (i == 1) v = theta[1] + b * theta[0] * theta[0] - 100.0 * b;
+      else v = theta[i];
+      acc = fma(v, v, acc);
+    }
+    ss[0] = acc;
+  }
+};
+
+// Hierarchical normal means: params (theta_1..G, mu, log tau), y_gj ~ N(theta_g, 1),
+// theta_g ~ N(mu, tau^2), weak hyperpriors mu ~ N(0,10^2), log tau ~ N(0,2^2).   blob: [G, J, y[G*J]]
+struct HierN {
+  static constexpr int NPAR = 0;
+  static constexpr int NY = 1;
+  static const char* name() { return "hier"; }
+  __device__ __forceinline__ static bool checkbounds(const double*, int, const mcmcb_ctx&) { return true; }
+  __device__ __forceinline__ static double priorfun(const double* theta, int len, const mcmcb_ctx& c) {
+    return mcmcb_default_priorfun(theta, len, c);
+  }
+  __device__ __forceinline__ static void ssfunction(const double* theta, int, int, const mcmcb_ctx& c, double* ss) {
+    const int G = (int)c.data[0], J = (int)c.data[1];
+    const double* __restrict__ y = c.data + 2;
+    const double mu = theta[G], ltau = theta[G + 1];
+    const double itau2 = exp(-2.0 * ltau);
+    double acc = 0.0;
+    for (int g = c.lane; g < G; g += c.nlanes) {
+      const double tg = theta[g];
+      double a = 0.0;
+      for (int j = 0; j < J; j++) { const double r = y[(size_t)g * J + j] - tg; a = fma(r, r, a); }
+      const double dm = tg - mu;
+      acc += a + dm * dm * itau2;
+    }
+    if (c.lane == 0) acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
+    ss[0] = acc;
+  }
+};
+
 }  // namespace mcmcb

@@ -22,6 +22,9 @@ struct ModelEntry {
   int (*alloc)(mcmcb_handle_s*);
   int (*init)(mcmcb_handle_s*);
   int (*step)(mcmcb_handle_s*, int nsteps);
+  int (*fetch)(mcmcb_handle_s*, const char* what, void* out, size_t out_bytes);
+  int (*fetch_chain)(mcmcb_handle_s*, long long chain, int ld, double* chain_out, double* sschain_out,
+                     double* s2chain_out, int* nrows);
 };
 
 std::vector<ModelEntry>& registry();
@@ -58,6 +61,11 @@ struct mcmcb_handle_s {
   int store_chains = 0;
   double *d_store_rows = nullptr, *d_store_cnt = nullptr, *d_store_s2 = nullptr;
   unsigned* d_tile = nullptr;
+  // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
+  double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
+         *d_scratch = nullptr, *d_cmat0_full = nullptr;
+  int dp = 0, rowcap = 0;
+  long long k2_i = 1;  // simuind shared by all chains of the handle
   std::vector<double> h_tmp;
   std::vector<mcmcb::DumpSlot> dump_slots;
   std::deque<int> dump_fifo;
