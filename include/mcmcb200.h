@@ -137,6 +137,9 @@ int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes_per_chain, int*
 /* FP64 pipe microbenchmark: dependent-free DFMA chains on every SM; returns measured
  * TFLOP/s (2 flop per DFMA) and the elapsed milliseconds. */
 int mcmcb_dfma_peak(int device, double* tflops, double* ms);
+/* accuracy evidence for the device exp used by model code (include/mcmcb200_model.cuh):
+ * out_fast[i] = mcmcb_exp_fast(a[i]), out_mul[i] = mcmcb_expmul_fast(a[i], scale) = exp(a[i]*scale) */
+int mcmcb_exp_selftest(int device, const double* a, double scale, double* out_fast, double* out_mul, size_t n);
 
 #ifdef __cplusplus
 }

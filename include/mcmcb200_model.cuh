@@ -35,84 +35,140 @@ struct mcmcb_ctx {
   unsigned long long ndata; /* blob length in doubles */
   const double* prior;      /* default Gaussian prior: mu[npar] then sig[npar]; nullptr = flat */
   int lane, nlanes;         /* this thread's rank among the lanes that share the chain */
-  const double* exp2_tab;   /* shared memory: 2^(j/64), j=0..63, each entry replicated 16x (see mcmcb_exp) */
-  int tab_slot;             /* which of the 16 table copies this thread reads: physical lane id mod 16 */
+  double exp_c1, exp_c2;    /* MCMCB_EXP_C1L, MCMCB_EXP_C2L handed through the kernel-parameter bank (see mcmcb_expmul_fast) */
+  unsigned exp_tl;          /* shared-window byte address of this thread's column of the replicated 2^(j/256)
+                               table (see mcmcb_exp; mcmcb_exp_column()); 0 = no table staged, use exp() */
 };
 
 /* ---------------------------------------------------------------------------------------
  * mcmcb_exp: FP64 exp() for model code, built for the FP64 pipe of sm_100a.
- * exp(a) = 2^m * 2^(j/64) * e^r with k = round(a*64/ln2) = 64 m + j and |r| <= ln2/128, so a
- * degree-5 polynomial reaches double precision: 10 FP64-pipe instructions per call against 16
- * for libdevice's table-free exp().  2^(j/64) comes from a 64-entry table that the sampling
- * kernels stage in shared memory with every entry replicated 16 times -- hardware lane l reads copy
- * (l mod 16), so the 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs and the lookup
- * is conflict-free whatever j each lane needs.  The fast path is branch-free (independent
- * calls interleave in the instruction stream); mcmcb_exp_ok() tells whether the argument is
- * in the fast range (|a| < 708), otherwise the caller falls back to exp().
+ * exp(a) = 2^m * 2^(j/256) * e^u with k = round(a*256/ln2) = 256 m + j and |u| <= ln2/512, so a
+ * degree-4 polynomial reaches double precision (economised: max error 2.4e-18).  2^(j/256) comes
+ * from a 256-entry table that the sampling kernels stage in shared memory with every entry
+ * replicated 16 times -- hardware lane l reads copy (l mod 16), so the 16 lanes of a half-warp
+ * hit 16 distinct 8-byte bank pairs and the lookup is conflict-free whatever j each lane needs.
+ * The fast paths are branch-free (independent calls interleave in the instruction stream).
+ *
+ *   mcmcb_exp_fast(a)         9 FP64 instructions  (libdevice exp(): 16)
+ *   mcmcb_expmul_fast(x, ks)  8 FP64 instructions  = exp(x * s) with ks = mcmcb_expmul_scale(s)
+ *                             computed once per evaluation: the product, the range reduction
+ *                             and the change of units to ln2/256 are one DFMA pair.
+ *
+ * An FP64 warp instruction occupies the scheduler's issue port for two cycles on sm_100a, so
+ * the instruction COUNT of the datum loop, integer and load instructions included, is what
+ * sets the speed of a model evaluation.  mcmcb_exp_ok() tells whether an
+ * argument is in the fast range (|a| < 708: result normal, no overflow, not NaN).
  * ------------------------------------------------------------------------------------- */
-#define MCMCB_EXP_TAB_N 64
+#define MCMCB_EXP_TAB_N 256
 #define MCMCB_EXP_TAB_REP 16
 #define MCMCB_EXP_TAB_DOUBLES (MCMCB_EXP_TAB_N * MCMCB_EXP_TAB_REP)
 
 /* coefficients live in the constant bank so that DFMA/DMUL read them as c[][] operands instead
- * of re-materialising 64-bit immediates inside the loop (FP64 instructions hold the issue port
- * for two cycles on sm_100a, so every other instruction in the loop costs a full cycle) */
-__constant__ double MCMCB_EXPC[6] = {
-    92.33248261689366,          /* 64/ln2 */
-    -0x1.62e42fef00000p-7,      /* -ln2/64, high 33 bits */
-    -0x1.473de6af278edp-40,     /* -ln2/64, low part */
-    8.3333333333333332e-3,      /* 1/120 */
-    4.1666666666666664e-2,      /* 1/24 */
-    1.6666666666666666e-1};     /* 1/6 */
+ * of re-materialising 64-bit immediates inside the loop */
+__constant__ double MCMCB_EXPC[10] = {
+    0x1.71547652b82fep+8,   /* [0] 256/ln2 */
+    -0x1.62e42fee00000p-9,  /* [1] -ln2/256, high part (21 trailing zero bits: k*hi is exact) */
+    -0x1.a39ef35793c76p-41, /* [2] -ln2/256, low part */
+    /* e^u - 1 = u (c1 + u (1/2 + u (c3 + u/24))) on |u| <= h = ln2/512: degree-5 Taylor with the u^5
+     * term Chebyshev-economised into c1, c3 (max error 2.4e-18 against 3.8e-17 for plain degree 4) */
+    0x1.5555555555555p-5,   /* [3] 1/24 */
+    0x1.555557e54fd55p-3,   /* [4] c3 = 1/6 + h^2/96 */
+    /* the same polynomial in r = u/L, L = ln2/256, r in [-1/2, 1/2] */
+    0x1.62e42fefa39b9p-9,   /* [5] c1 L */
+    0x1.ebfbdff82c58fp-19,  /* [6] L^2/2 */
+    0x1.c6b090da1e082p-29,  /* [7] c3 L^3 */
+    0x1.3b2ab6fba4e77p-39,  /* [8] L^4/24 */
+    0x1.fffffffffffb1p-1};  /* [9] c1 = 1 - h^4/384 */
 
-__device__ __forceinline__ double mcmcb_exp_fast(double a, const double* __restrict__ tab, int lane16) {
-  const double MAGIC = 6755399441055744.0; /* 1.5 * 2^52: rounds to integer, k in the low word */
-  double t = fma(a, MCMCB_EXPC[0], MAGIC);
+/* [5] and [6] again as macros: the host writes them into the kernel parameters (mcmcb_ctx::exp_c1/c2) */
+#define MCMCB_EXP_C1L 0x1.62e42fefa39b9p-9
+#define MCMCB_EXP_C2L 0x1.ebfbdff82c58fp-19
+
+#define MCMCB_EXP_MAGIC 6755399441055744.0 /* 1.5 * 2^52: rounds to integer, k in the low word */
+
+/* 2^(k/256) * (1 + s) from the reduced pieces.  Three integer instructions: mask, address, and
+ * ONE multiply-add for the exponent: table entry j is stored with j*2^12 subtracted from its high
+ * word, so that adding k*2^12 = m*2^20 + j*2^12 to it yields the high word of 2^m * 2^(j/256)
+ * without isolating m.  `tl` is the shared-window address of the thread's own column of the
+ * replicated table; the load is spelled as ld.shared so that the address stays one mask and one
+ * shift-add of an opaque per-thread base. */
+__device__ __forceinline__ double mcmcb_exp_assemble(int k, double s, unsigned tl) {
+  double tj;
+  unsigned addr;
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(k & (MCMCB_EXP_TAB_N - 1)), "r"(tl));  /* 8 B * 16 columns */
+  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));
+  const double sc = __hiloint2double(k * 4096 + __double2hiint(tj), __double2loint(tj));
+  return fma(sc, s, sc);
+}
+/* address of this thread's column of a table staged at smem_tab (16 columns, lane mod 16) */
+__device__ __forceinline__ unsigned mcmcb_exp_column(const double* smem_tab) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem_tab) + 8u * (threadIdx.x & (MCMCB_EXP_TAB_REP - 1));
+  asm volatile("" : "+r"(a));  /* opaque: keeps the compiler from folding the lane term back into every lookup */
+  return a;
+}
+
+__device__ __forceinline__ double mcmcb_exp_fast(double a, unsigned tl) {
+  double t = fma(a, MCMCB_EXPC[0], MCMCB_EXP_MAGIC);
   const int k = __double2loint(t);
-  t -= MAGIC;
+  t -= MCMCB_EXP_MAGIC;
   double r = fma(t, MCMCB_EXPC[1], a);
   r = fma(t, MCMCB_EXPC[2], r);
   double q = fma(r, MCMCB_EXPC[3], MCMCB_EXPC[4]);
-  q = fma(r, q, MCMCB_EXPC[5]);
   q = fma(r, q, 0.5);
-  q = fma(r, q, 1.0);
-  const double s = r * q; /* e^r - 1 */
-  const double tj = tab[((k & (MCMCB_EXP_TAB_N - 1)) * MCMCB_EXP_TAB_REP) | lane16];
-  const double res = fma(tj, s, tj);
-  return __hiloint2double(__double2hiint(res) + (k >> 6) * 1048576, __double2loint(res));
+  q = fma(r, q, MCMCB_EXPC[9]);
+  return mcmcb_exp_assemble(k, r * q, tl);
 }
-/* true when mcmcb_exp_fast(a) is valid: |a| < 708 (result normal, no overflow) and a is not NaN */
+
+/* ks for mcmcb_expmul_fast: s * 256/ln2 */
+__device__ __forceinline__ double mcmcb_expmul_scale(double s) { return s * MCMCB_EXPC[0]; }
+
+/* exp(x * s), ks = mcmcb_expmul_scale(s).  The reduced argument r = x*ks - round(x*ks) is formed
+ * by one DFMA (exact product, one rounding of a value <= 1/2), so the only argument error is the
+ * rounding of ks itself: |x s| * 2^-52 relative in the result, the same size as the rounding of
+ * the product x*s inside exp(x*s).
+ *
+ * Operand placement matters: measured on B200 (scripts/ubench_fp64_operands.cu) a DFMA that reads
+ * three DISTINCT 64-bit registers holds the FP64 pipe for 3 cycles, one that reads at most two
+ * (plus a uniform-register / constant / immediate operand, or a repeated register) for 2.  The
+ * Horner steps below are (r, q, constant): the constant must not be hoisted into a vector
+ * register.  ptxas 12.9 keeps at most two hoisted constants per bank in uniform registers, so
+ * c1, c2 arrive through the kernel-parameter bank (c[0x0], mcmcb_ctx) and c3, c4 through the
+ * __constant__ bank (c[0x3]); the first step (r, c4, c3) then reads r + one register. */
+__device__ __forceinline__ double mcmcb_expmul_fast(double x, double ks, unsigned tl, double c1, double c2) {
+  const double t = fma(x, ks, MCMCB_EXP_MAGIC);
+  const int k = __double2loint(t);
+  const double r = fma(x, ks, MCMCB_EXP_MAGIC - t);
+  double q = fma(r, MCMCB_EXPC[8], MCMCB_EXPC[7]);
+  q = fma(r, q, c2);
+  q = fma(r, q, c1);
+  return mcmcb_exp_assemble(k, r * q, tl);
+}
+__device__ __forceinline__ double mcmcb_expmul_fast(double x, double ks, unsigned tl) {
+  return mcmcb_expmul_fast(x, ks, tl, MCMCB_EXPC[5], MCMCB_EXPC[6]);
+}
+
+/* true when the fast paths are valid for argument a: |a| < 708 and a is not NaN */
 __device__ __forceinline__ bool mcmcb_exp_ok(double a) {
   return (unsigned)(__double2hiint(a) & 0x7fffffff) < 0x40862000u;
 }
 __device__ __forceinline__ double mcmcb_exp(double a, const mcmcb_ctx& c) {
-  if (c.exp2_tab != nullptr && mcmcb_exp_ok(a)) return mcmcb_exp_fast(a, c.exp2_tab, c.tab_slot);
+  if (c.exp_tl != 0u && mcmcb_exp_ok(a)) return mcmcb_exp_fast(a, c.exp_tl);
   return exp(a);
 }
 
-/* correctly rounded 2^(j/64) (generated with mpmath at 60 digits) */
+/* correctly rounded 2^(j/256) (scripts/gen_exp_table.py, mpmath at 80 digits) */
 __device__ static const double MCMCB_EXP2_TABLE[MCMCB_EXP_TAB_N] = {
-    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
-    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
-    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
-    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
-    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
-    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
-    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+#include "mcmcb200_exp_table.inc"
+};
 
 /* stage the replicated table; call from every thread of the CTA, then __syncthreads() */
 __device__ __forceinline__ void mcmcb_stage_exp_table(double* smem_tab) {
   for (int i = threadIdx.x; i < MCMCB_EXP_TAB_DOUBLES; i += blockDim.x)
-    smem_tab[i] = MCMCB_EXP2_TABLE[i / MCMCB_EXP_TAB_REP];
+  {
+    const int j = i / MCMCB_EXP_TAB_REP;
+    const double v = MCMCB_EXP2_TABLE[j];
+    smem_tab[i] = __hiloint2double(__double2hiint(v) - j * 4096, __double2loint(v));  /* see mcmcb_exp_assemble */
+  }
 }
 
 /* default prior, priorfun.f90:97-100: sum(((theta-mu)/sig)**2, mask = sig>0) */

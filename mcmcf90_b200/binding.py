@@ -16,7 +16,7 @@ COUNTER_NAMES = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "si
 EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_destroy", "mcmcb_last_error",
            "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
            "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
-           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak"]
+           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak", "mcmcb_exp_selftest"]
 
 
 class MCMCBError(RuntimeError):
@@ -78,6 +78,7 @@ def load_library():
     L.mcmcb_launch_count.restype = C.c_longlong
     L.mcmcb_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_size_t)]
     L.mcmcb_dfma_peak.argtypes = [C.c_int, dp, dp]
+    L.mcmcb_exp_selftest.argtypes = [C.c_int, dp, C.c_double, dp, dp, C.c_size_t]
     _LIB = L
     return L
 
@@ -103,6 +104,16 @@ def dfma_peak(device=0):
     if rc:
         raise MCMCBError("mcmcb_dfma_peak failed: %s" % ERRORS.get(rc, rc))
     return t.value, ms.value
+
+
+def exp_selftest(a, scale=1.0, device=0):
+    """(mcmcb_exp_fast(a), mcmcb_expmul_fast(a, scale)) evaluated on the device."""
+    a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+    o1, o2 = np.empty_like(a), np.empty_like(a)
+    rc = load_library().mcmcb_exp_selftest(device, _dp(a), float(scale), _dp(o1), _dp(o2), a.size)
+    if rc:
+        raise MCMCBError("mcmcb_exp_selftest failed: %s" % ERRORS.get(rc, rc))
+    return o1, o2
 
 
 def _dp(a):

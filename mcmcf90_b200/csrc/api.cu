@@ -190,6 +190,8 @@ struct K1 {
     p.store_cnt_p = h->d_store_cnt;
     p.store_s2_p = h->d_store_s2;
     p.tile_counter = h->d_tile;
+    p.exp_c1 = MCMCB_EXP_C1L;
+    p.exp_c2 = MCMCB_EXP_C2L;
     return p;
   }
 
@@ -917,4 +919,35 @@ extern "C" int mcmcb_dfma_peak(int device, double* tflops, double* ms_out) {
   if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
   return MCMCB_OK;
+}
+
+// ------------------------------------------------------------------ exp self-test (accuracy evidence)
+__global__ void exp_selftest_kernel(const double* a, double sc, double* out_fast, double* out_mul, long long n) {
+  __shared__ double tab[MCMCB_EXP_TAB_DOUBLES];
+  mcmcb_stage_exp_table(tab);
+  __syncthreads();
+  const unsigned tl = mcmcb_exp_column(tab);
+  const double ks = mcmcb_expmul_scale(sc);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out_fast[i] = mcmcb_exp_ok(a[i]) ? mcmcb_exp_fast(a[i], tl) : exp(a[i]);
+    out_mul[i] = mcmcb_exp_ok(a[i] * sc) ? mcmcb_expmul_fast(a[i], ks, tl) : exp(a[i] * sc);
+  }
+}
+
+extern "C" int mcmcb_exp_selftest(int device, const double* a, double scale, double* out_fast, double* out_mul, size_t n) {
+  if (!a || !out_fast || !out_mul || n == 0) return MCMCB_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return MCMCB_ECUDA;
+  double *da = nullptr, *d1 = nullptr, *d2 = nullptr;
+  cudaError_t e = cudaMalloc(&da, 8 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d1, 8 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d2, 8 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, 8 * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    exp_selftest_kernel<<<296, 256>>>(da, scale, d1, d2, (long long)n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_fast, d1, 8 * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_mul, d2, 8 * n, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(d1); cudaFree(d2);
+  return e == cudaSuccess ? MCMCB_OK : MCMCB_ECUDA;
 }

@@ -82,6 +82,7 @@ struct K1Params {
   double* store_cnt_p;      // [chain][row]
   double* store_s2_p;       // [chain][step][NY]
   unsigned int* tile_counter;
+  double exp_c1, exp_c2;    // MCMCB_EXP_C1L / C2L: see mcmcb_expmul_fast for why they travel as parameters
 };
 
 __host__ __device__ constexpr int pk(int i, int j) { return j * (j + 1) / 2 + i; }  // i <= j
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
   const int sub = lane / L, gl = lane % L;
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
-  ctx.exp2_tab = exp_tab; ctx.tab_slot = lane & 15;
+  ctx.exp_tl = mcmcb_exp_column(exp_tab); ctx.exp_c1 = p.exp_c1; ctx.exp_c2 = p.exp_c2;
 
   K1State<D, NY> S;
   for (;;) {

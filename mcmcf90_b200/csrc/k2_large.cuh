@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_con
   }
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = lane; ctx.nlanes = 32;
-  ctx.exp2_tab = nullptr; ctx.tab_slot = lane & 15;
+  ctx.exp_tl = 0u; ctx.exp_c1 = MCMCB_EXP_C1L; ctx.exp_c2 = MCMCB_EXP_C2L;
 
   for (;;) {
     unsigned tile = 0;

@@ -30,14 +30,15 @@ struct ExpReg {
     const double* __restrict__ x = c.data + 2;
     const double* __restrict__ y = c.data + 2 + npad;
     const double t1 = theta[0], nt2 = -theta[1];
-    const double* __restrict__ tab = c.exp2_tab;
-    const int l16 = c.tab_slot;
+    const unsigned tl = c.exp_tl;  // this thread's column of the replicated 2^(j/256) table
+    const double c1 = c.exp_c1, c2 = c.exp_c2;
     double acc = 0.0;
     int i = c.lane;
     const int step = c.nlanes;
     // blob[1] = max|x| (set by blob_expreg): one range test per evaluation instead of one per
     // datum decides whether every exponent is inside mcmcb_exp_fast's range
-    const bool fast = tab != nullptr && fabs(nt2) * c.data[1] < 700.0;
+    const bool fast = tl != 0u && fabs(nt2) * c.data[1] < 700.0;
+    const double ks = mcmcb_expmul_scale(nt2);
     if (fast) {
       if (step == 1) {
         // one lane owns the whole chain: consecutive data, 16-byte shared loads, 8 exps in flight
@@ -50,7 +51,7 @@ struct ExpReg {
             xv[u] = xx.x; xv[u + 1] = xx.y; yv[u] = yy.x; yv[u + 1] = yy.y;
           }
 #pragma unroll
-          for (int u = 0; u < 8; u++) xv[u] = mcmcb_exp_fast(nt2 * xv[u], tab, l16);
+          for (int u = 0; u < 8; u++) xv[u] = mcmcb_expmul_fast(xv[u], ks, tl, c1, c2);
 #pragma unroll
           for (int u = 0; u < 8; u++) {
             const double r = fma(-t1, xv[u], yv[u]);
@@ -61,9 +62,9 @@ struct ExpReg {
         for (; i + 3 * step < n; i += 4 * step) {
           double e[4], yv[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) { e[u] = nt2 * x[i + u * step]; yv[u] = y[i + u * step]; }
+          for (int u = 0; u < 4; u++) { e[u] = x[i + u * step]; yv[u] = y[i + u * step]; }
 #pragma unroll
-          for (int u = 0; u < 4; u++) e[u] = mcmcb_exp_fast(e[u], tab, l16);
+          for (int u = 0; u < 4; u++) e[u] = mcmcb_expmul_fast(e[u], ks, tl, c1, c2);
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const double r = fma(-t1, e[u], yv[u]);
@@ -72,7 +73,7 @@ struct ExpReg {
         }
       }
       for (; i < n; i += step) {
-        const double r = fma(-t1, mcmcb_exp_fast(nt2 * x[i], tab, l16), y[i]);
+        const double r = fma(-t1, mcmcb_expmul_fast(x[i], ks, tl, c1, c2), y[i]);
         acc = fma(r, r, acc);
       }
     } else {
