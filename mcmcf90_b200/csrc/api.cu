@@ -12,6 +12,7 @@
 
 #include "k1_small.cuh"
 #include "k2_large.cuh"
+#include "k3_scam.cuh"
 #include "mcmcb200.h"
 #include "models.cuh"
 #include "registry.h"
@@ -197,6 +198,7 @@ struct K1 {
 
   static int alloc(mcmcb_handle h) {
     constexpr K1Layout Lo = k1_layout(D, NY);
+    if (h->doscam || h->usesvd) return MCMCB_EUNSUPPORTED;  // SVD factor paths live in the warp-per-chain kernels
     h->nf = Lo.nf;
     h->inf = Lo.i_nf;
     h->pitch = ((h->cfg.nchains + 31) / 32) * 32;
@@ -305,16 +307,17 @@ static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
   }
   double* o = (double*)out;
   std::vector<double> buf;
-  if (w == "par" || w == "mean") {
+  if (w == "par" || w == "mean" || w == "qcovstd") {
     if (out_bytes < sizeof(double) * (size_t)D * N) return MCMCB_EINVAL;
     buf.resize((size_t)N * dp);
-    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : h->d_mean, sizeof(double) * buf.size(),
+    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : (w == "mean" ? h->d_mean : h->d_qstd), sizeof(double) * buf.size(),
                        cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (long long c = 0; c < N; c++)
       for (int k = 0; k < D; k++) o[(size_t)c * D + k] = buf[(size_t)c * dp + k];
     return MCMCB_OK;
   }
+  if (w == "R2" && h->factor_mode != FACTOR_CHOL) return MCMCB_EINVAL;
   if (w == "cmat" || w == "R" || w == "R2") {
     if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
     buf.resize((size_t)N * D * D);
@@ -326,7 +329,8 @@ static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
       for (int j = 0; j < D; j++)
         for (int i = 0; i < D; i++) {
           // cmat is symmetric; the factor is stored row-major: element (i,j) at i*D+j -> column-major output
-          double v = buf[(size_t)c * D * D + (size_t)i * D + j];
+          double v = (w == "R" && h->factor_mode != FACTOR_CHOL) ? buf[(size_t)c * D * D + (size_t)j * D + i]  // SVD factor: column-major
+                                                                 : buf[(size_t)c * D * D + (size_t)i * D + j];
           o[(size_t)c * D * D + (size_t)j * D + i] = (w == "cmat") ? v : v * sc;
         }
     return MCMCB_OK;
@@ -391,6 +395,8 @@ struct K2 {
     p.store_s2_p = h->d_store_s2;
     p.tile_counter = h->d_tile;
     p.tick_i = 0;
+    p.qstd = h->d_qstd;
+    p.factor_mode = h->factor_mode;
     return p;
   }
 
@@ -400,6 +406,11 @@ struct K2 {
     const int d = h->npar;
     if (d > 32 * K2_MAXM) return MCMCB_EUNSUPPORTED;
     const long long N = h->cfg.nchains;
+    h->factor_mode = h->doscam ? FACTOR_SCAM : (h->usesvd ? FACTOR_SVD : FACTOR_CHOL);
+    // the SVD square root is a general matrix: no rank-1 Cholesky updates (RAM) on it, and the reference's
+    // second-stage ratio with usesvd inverts its upper triangle as if it were a Cholesky factor
+    // (MCMC_adapt.F90:216-219) -- not reproduced
+    if (h->factor_mode == FACTOR_SVD && (h->cfg.method == MCMCB_RAM || h->dodr)) return MCMCB_EUNSUPPORTED;
     h->nf = Lo.nf;
     h->inf = Lo.i_nf;
     h->pitch = ((N + 31) / 32) * 32;
@@ -413,7 +424,9 @@ struct K2 {
     CK(cudaMalloc(&h->d_mean, sizeof(double) * (size_t)N * h->dp));
     CK(cudaMalloc(&h->d_Rm, sizeof(double) * (size_t)N * d * d));
     CK(cudaMalloc(&h->d_cmat, sizeof(double) * (size_t)N * d * d));
-    CK(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d * d));
+    CK(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d * d * (h->factor_mode == FACTOR_CHOL ? 1 : 2)));
+    CK(cudaMalloc(&h->d_qstd, sizeof(double) * (size_t)N * h->dp));
+    CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * (size_t)N * h->dp, h->stream));
     CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * h->rowcap * (d + 1)));
     if (h->store_chains > 0) {
       size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
@@ -430,7 +443,11 @@ struct K2 {
   static int init(mcmcb_handle h) {
     K2Params p = params(h, 0);
     k2_init_kernel<M><<<(unsigned)h->cfg.nchains, 128, 0, h->stream>>>(p);
-    k2_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
+    if (h->factor_mode == FACTOR_CHOL)
+      k2_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
+    else
+      k3_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, sizeof(double) * 2 * h->npar, h->stream>>>(
+          p, h->d_scratch, h->factor_mode);
     h->launches += 2;
     h->k2_i = 1;
     CK(cudaGetLastError());
@@ -439,7 +456,7 @@ struct K2 {
 
   template <bool SMEM>
   static int launch_step(mcmcb_handle h, const K2Params& p) {
-    auto kern = k2_step_kernel<M, SMEM>;
+    auto kern = (h->factor_mode == FACTOR_SCAM) ? k3_scam_step_kernel<M, SMEM> : k2_step_kernel<M, SMEM>;
     size_t smem = sizeof(double) * (size_t)K2_WARPS * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0);
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -486,7 +503,11 @@ struct K2 {
       left -= seg;
       if (seg > 0 && is_tick(c, h->k2_i)) {
         p.tick_i = (int)h->k2_i;
-        k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * h->npar, h->stream>>>(p, h->d_scratch);
+        if (h->factor_mode == FACTOR_CHOL)
+          k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * h->npar, h->stream>>>(p, h->d_scratch);
+        else
+          k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * 3 * h->npar, h->stream>>>(
+              p, h->d_scratch, h->factor_mode);
         h->launches++;
         CK(cudaGetLastError());
       }
@@ -607,9 +628,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (rc) { delete h; return rc; }
   const mcmcb_config& c = h->cfg;
   // configurations that need the stored row history of the reference (AP)
-  if (c.method == MCMCB_DRAM && (c.adapthist > 1 || (c.greedy && c.doburnin)) ) { delete h; return MCMCB_EUNSUPPORTED; }
-  if (c.method == MCMCB_DRAM && h->usesvd) { delete h; return MCMCB_EUNSUPPORTED; }
-  if (c.method == MCMCB_SCAM) { delete h; return MCMCB_EUNSUPPORTED; }
+  if (c.method != MCMCB_RAM && (c.adapthist > 1 || (c.greedy && c.doburnin)) ) { delete h; return MCMCB_EUNSUPPORTED; }
   h->model = find_model(c.model, c.kernel);
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
   DevCfg& d = h->dc;
@@ -636,7 +655,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
-                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full};
+                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : h->dump_slots) {

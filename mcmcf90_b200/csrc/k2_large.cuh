@@ -83,6 +83,8 @@ struct K2Params {
   double* store_s2_p;
   unsigned int* tile_counter;
   int tick_i;      // adaptation kernel: the step index i of this tick
+  double* qstd;    // [chain][dp]  SCAM proposal standard deviations (k3_scam.cuh)
+  int factor_mode; // 0 = row-major upper Cholesky factor, 1 = column-major SVD factor (usesvd), 2 = SCAM
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -401,6 +403,23 @@ __device__ __forceinline__ bool warp_chdd(double* R, double* x, double* sv, doub
   return true;
 }
 
+// y_i = sum_j R(i,j) v_j for the rows this lane owns; R column-major general (dgemv 'N', matutils.F90:161,
+// the usesvd proposal of MCMC_DRAM.F90:27)
+__device__ __forceinline__ void gen_matvec_n(const double* __restrict__ R, const double* vs, int d, int lane,
+                                             double (&acc)[K2_MAXM]) {
+#pragma unroll
+  for (int m = 0; m < K2_MAXM; m++) acc[m] = 0.0;
+  for (int j = 0; j < d; j++) {
+    const double vj = vs[j];
+    const double* col = R + (size_t)j * d;
+#pragma unroll
+    for (int m = 0; m < K2_MAXM; m++) {
+      const int i = lane + 32 * m;
+      if (i < d) acc[m] = fma(col[i], vj, acc[m]);
+    }
+  }
+}
+
 template <class M, bool SMEM>
 __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
@@ -474,7 +493,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_con
         double* zs = (phase == 0) ? z1 : z2;
         warp_normals(g, zs, d, lane);
         double acc[K2_MAXM];
-        tri_matvec_t(Rm, zs, d, lane, acc);
+        if (p.factor_mode == 0) tri_matvec_t(Rm, zs, d, lane, acc);
+        else gen_matvec_n(Rm, zs, d, lane, acc);
         const double sc = (phase == 0) ? 1.0 : 1.0 / c.drscale;
 #pragma unroll
         for (int m = 0; m < K2_MAXM; m++) {

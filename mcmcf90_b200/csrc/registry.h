@@ -63,8 +63,8 @@ struct mcmcb_handle_s {
   unsigned* d_tile = nullptr;
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
-         *d_scratch = nullptr, *d_cmat0_full = nullptr;
-  int dp = 0, rowcap = 0;
+         *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr;
+  int dp = 0, rowcap = 0, factor_mode = 0;
   long long k2_i = 1;  // simuind shared by all chains of the handle
   std::vector<double> h_tmp;
   std::vector<mcmcb::DumpSlot> dump_slots;
