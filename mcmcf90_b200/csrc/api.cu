@@ -631,6 +631,8 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (c.method != MCMCB_RAM && (c.adapthist > 1 || (c.greedy && c.doburnin)) ) { delete h; return MCMCB_EUNSUPPORTED; }
   h->model = find_model(c.model, c.kernel);
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
+  // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
+  if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }
   DevCfg& d = h->dc;
   d.method = c.method; d.nsimu = c.nsimu; d.doadapt = c.doadapt; d.adaptint = c.adaptint; d.adapthist = c.adapthist;
   d.adaptend = c.adaptend; d.initcmatn = c.initcmatn; d.doburnin = c.doburnin; d.burnintime = c.burnintime;
