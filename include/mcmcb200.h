@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MCMCB_ABI_VERSION 1
+#define MCMCB_ABI_VERSION 2
 
 /* error codes */
 #define MCMCB_OK 0
@@ -74,6 +74,13 @@ typedef struct mcmcb_config {
   int lanes_per_chain; /* 0 = auto; 1,2,4,8,16,32 lanes cooperate on one chain's ssfunction */
   int dump_stride;     /* >0: every dump_stride steps all chains' theta are streamed to pinned host buffers */
   int kernel;          /* 0 = auto; 1 = small-npar register kernel; 2 = large-npar warp kernel */
+  int pool_adapt;      /* 1: cross-chain pooled adaptation -- at every adaptation tick the chains' (wsum, mean,
+                          cmat) accumulators are merged over ALL chains of ALL handles (mcmcb_set_allreduce)
+                          and every chain proposes from the factor of the pooled covariance; RAM: the chains'
+                          R'R are averaged every adaptint steps (no reference counterpart) */
+  int diag_stride;     /* >0: every diag_stride steps theta of every chain is folded into the per-chain running
+                          moments behind mcmcb_diagnostics (R-hat / ESS) */
+  int diag_lags;       /* autocovariance lags kept for the ESS, in units of diag_stride (0..MCMCB_DIAG_MAXLAGS) */
   char model[32];      /* user-model name: "expreg", "gauss", "banana", "hier", or a plugin's name */
 } mcmcb_config;
 
@@ -128,6 +135,31 @@ int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes);
  * chains' theta (nchains x npar, chain-major) from the pinned ring; returns 1 if one was
  * copied, 0 if none pending. *step receives simuind of the snapshot. */
 int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step);
+
+/* ---- multi-GPU collectives: chains never interact in the reference, so the step loop has no
+ * collective.  The two optional cross-chain features below reduce a few small vectors over every handle of
+ * the job.  The library does not link a communication library: the host hands it ONE callback that
+ * sum-reduces n doubles in place in DEVICE memory across all ranks, ordered on the given CUDA stream (or
+ * synchronously): ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, comm, stream) from C/Fortran,
+ * torch.distributed.all_reduce from Python (mcmcf90_b200/parallel.py).  Without a callback the reduction
+ * covers the handle's own chains only. */
+typedef int (*mcmcb_allreduce_fn)(void* user, double* device_buf, size_t n, void* cuda_stream);
+int mcmcb_set_allreduce(mcmcb_handle h, mcmcb_allreduce_fn fn, void* user);
+
+/* pooled statistics of the last pooled adaptation tick (pool_adapt = 1): wsum, mean[npar],
+ * cov[npar*npar] column-major.  Any pointer may be NULL. */
+int mcmcb_pool_fetch(mcmcb_handle h, double* wsum, double* mean, double* cov);
+
+#define MCMCB_DIAG_MAXLAGS 32
+/* Convergence diagnostics over every chain of every handle (diag_stride > 0): potential scale reduction
+ * R-hat (Gelman & Rubin 1992, between/within variances of the chains' snapshot means) and the effective
+ * sample size of the pooled snapshots from the chains' mean autocovariances at lags 1..diag_lags (Geyer
+ * initial-positive-sequence truncation).  Collective: every rank calls it at the same point.
+ * rhat, ess, mean, var have npar entries (any may be NULL); *nsnap / *nchains_total receive the snapshots
+ * per chain and the number of chains pooled. */
+int mcmcb_diagnostics(mcmcb_handle h, double* rhat, double* ess, double* mean, double* var, long long* nsnap,
+                      long long* nchains_total);
+int mcmcb_diag_reset(mcmcb_handle h);
 
 /* introspection for measurement */
 void* mcmcb_stream(mcmcb_handle h);              /* cudaStream_t the kernels run on */

@@ -16,7 +16,11 @@ COUNTER_NAMES = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "si
 EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_destroy", "mcmcb_last_error",
            "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
            "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
-           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak", "mcmcb_exp_selftest"]
+           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak", "mcmcb_exp_selftest",
+           "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset"]
+
+# int fn(void* user, double* device_buf, size_t n, void* cuda_stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
 class MCMCBError(RuntimeError):
@@ -38,6 +42,7 @@ class Config(C.Structure):
         ("nchains", C.c_longlong), ("chain_offset", C.c_longlong), ("seed", C.c_ulonglong),
         ("rng_mode", C.c_int), ("device", C.c_int), ("store_chains", C.c_int), ("lanes_per_chain", C.c_int),
         ("dump_stride", C.c_int), ("kernel", C.c_int),
+        ("pool_adapt", C.c_int), ("diag_stride", C.c_int), ("diag_lags", C.c_int),
         ("model", C.c_char * 32),
     ]
 
@@ -79,6 +84,10 @@ def load_library():
     L.mcmcb_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_size_t)]
     L.mcmcb_dfma_peak.argtypes = [C.c_int, dp, dp]
     L.mcmcb_exp_selftest.argtypes = [C.c_int, dp, C.c_double, dp, dp, C.c_size_t]
+    L.mcmcb_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
+    L.mcmcb_pool_fetch.argtypes = [C.c_void_p, dp, dp, dp]
+    L.mcmcb_diagnostics.argtypes = [C.c_void_p, dp, dp, dp, dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.mcmcb_diag_reset.argtypes = [C.c_void_p]
     _LIB = L
     return L
 
@@ -208,6 +217,41 @@ class Sampler:
                   "mcmcb_fetch_chain")
         n = nrows.value
         return dict(chain=ch[:n].copy(), sschain=ss[:n].copy(), s2chain=s2.copy(), nrows=n)
+
+    def set_allreduce(self, fn):
+        """fn(device_ptr:int, n:int, cuda_stream:int) -> None sum-reduces n doubles in place over all
+        ranks (mcmcf90_b200.parallel.attach builds it from torch.distributed); None detaches."""
+        if fn is None:
+            self._ar = ALLREDUCE_FN(0)
+        else:
+            def _cb(user, ptr, n, stream):
+                try:
+                    fn(int(ptr), int(n), int(stream or 0))
+                    return 0
+                except Exception as e:  # the C side turns this into an error code
+                    self._ar_error = e
+                    return 1
+            self._ar = ALLREDUCE_FN(_cb)
+        self._chk(self.L.mcmcb_set_allreduce(self.h, self._ar, None), "mcmcb_set_allreduce")
+
+    def pool_fetch(self):
+        """(wsum, mean[npar], cov[npar, npar]) of the last pooled adaptation tick."""
+        d = self.npar
+        w, m, cv = C.c_double(0), np.zeros(d), np.zeros((d, d), order="F")
+        self._chk(self.L.mcmcb_pool_fetch(self.h, C.byref(w), _dp(m), _dp(cv)), "mcmcb_pool_fetch")
+        return w.value, m, np.ascontiguousarray(cv)
+
+    def diagnostics(self):
+        """dict(rhat, ess, mean, var (npar,), nsnap, nchains): collective over the attached ranks."""
+        d = self.npar
+        r, e, m, v = np.zeros(d), np.zeros(d), np.zeros(d), np.zeros(d)
+        ns, nc = C.c_longlong(0), C.c_longlong(0)
+        self._chk(self.L.mcmcb_diagnostics(self.h, _dp(r), _dp(e), _dp(m), _dp(v), C.byref(ns), C.byref(nc)),
+                  "mcmcb_diagnostics")
+        return dict(rhat=r, ess=e, mean=m, var=v, nsnap=ns.value, nchains=nc.value)
+
+    def diag_reset(self):
+        self._chk(self.L.mcmcb_diag_reset(self.h), "mcmcb_diag_reset")
 
     def dump_pop(self):
         out = np.zeros((self.nchains, self.npar))

@@ -13,6 +13,8 @@
 #include "k1_small.cuh"
 #include "k2_large.cuh"
 #include "k3_scam.cuh"
+#include "pool.cuh"
+#include "diag.cuh"
 #include "mcmcb200.h"
 #include "models.cuh"
 #include "registry.h"
@@ -270,8 +272,27 @@ struct K1 {
     }
   }
 
+  // pooled adaptation, pool.cuh
+  static int pool(mcmcb_handle h, int phase) {
+    K1Params p = params(h, 0);
+    if (phase == 3) {
+      const int threads = 256;
+      k1_pool_apply_kernel<D, NY><<<(unsigned)((h->cfg.nchains + threads - 1) / threads), threads, 0, h->stream>>>(p, h->d_pool);
+      h->launches++;
+    } else {
+      const int nv = phase == 1 ? 1 + D : D * D;
+      double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + D;
+      k1_pool_moments_kernel<D, NY><<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
+      pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   static ModelEntry entry() {
     ModelEntry e{};
+    e.pool = &pool;
     e.name = M::name();
     e.kernel = 1;
     e.npar = D;
@@ -310,9 +331,12 @@ static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
   if (w == "par" || w == "mean" || w == "qcovstd") {
     if (out_bytes < sizeof(double) * (size_t)D * N) return MCMCB_EINVAL;
     buf.resize((size_t)N * dp);
-    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : (w == "mean" ? h->d_mean : h->d_qstd), sizeof(double) * buf.size(),
-                       cudaMemcpyDeviceToHost, h->stream));
+    const bool shared = (w == "qcovstd") && h->q_stride == 0;
+    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : (w == "mean" ? h->d_mean : h->d_qstd),
+                       sizeof(double) * (shared ? (size_t)dp : buf.size()), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (shared)
+      for (long long c = 1; c < N; c++) std::copy(buf.begin(), buf.begin() + dp, buf.begin() + (size_t)c * dp);
     for (long long c = 0; c < N; c++)
       for (int k = 0; k < D; k++) o[(size_t)c * D + k] = buf[(size_t)c * dp + k];
     return MCMCB_OK;
@@ -321,9 +345,12 @@ static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
   if (w == "cmat" || w == "R" || w == "R2") {
     if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
     buf.resize((size_t)N * D * D);
-    CK(cudaMemcpyAsync(buf.data(), w == "cmat" ? h->d_cmat : h->d_Rm, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
-                       h->stream));
+    const bool shared = (w != "cmat") && h->r_stride == 0;  // pooled adaptation: one factor for every chain
+    CK(cudaMemcpyAsync(buf.data(), w == "cmat" ? h->d_cmat : h->d_Rm, sizeof(double) * (shared ? (size_t)D * D : buf.size()),
+                       cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (shared)
+      for (long long c = 1; c < N; c++) std::copy(buf.begin(), buf.begin() + (size_t)D * D, buf.begin() + (size_t)c * D * D);
     const double sc = (w == "R2") ? 1.0 / h->dc.drscale : 1.0;
     for (long long c = 0; c < N; c++)
       for (int j = 0; j < D; j++)
@@ -397,6 +424,8 @@ struct K2 {
     p.tick_i = 0;
     p.qstd = h->d_qstd;
     p.factor_mode = h->factor_mode;
+    p.r_stride = h->r_stride;
+    p.q_stride = h->q_stride;
     return p;
   }
 
@@ -406,6 +435,7 @@ struct K2 {
     const int d = h->npar;
     if (d > 32 * K2_MAXM) return MCMCB_EUNSUPPORTED;
     const long long N = h->cfg.nchains;
+    const mcmcb_config& c = h->cfg;
     h->factor_mode = h->doscam ? FACTOR_SCAM : (h->usesvd ? FACTOR_SVD : FACTOR_CHOL);
     // the SVD square root is a general matrix: no rank-1 Cholesky updates (RAM) on it, and the reference's
     // second-stage ratio with usesvd inverts its upper triangle as if it were a Cholesky factor
@@ -415,18 +445,23 @@ struct K2 {
     h->inf = Lo.i_nf;
     h->pitch = ((N + 31) / 32) * 32;
     h->dp = ((d + 31) / 32) * 32;
-    const mcmcb_config& c = h->cfg;
     h->rowcap = c.burnintime + 2 * std::max(c.adaptint, 1) + c.adapthist + 2;
     if (c.method == MCMCB_RAM || !c.doadapt) h->rowcap = 1;
     CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
     CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
     CK(cudaMalloc(&h->d_theta, sizeof(double) * (size_t)N * h->dp));
     CK(cudaMalloc(&h->d_mean, sizeof(double) * (size_t)N * h->dp));
-    CK(cudaMalloc(&h->d_Rm, sizeof(double) * (size_t)N * d * d));
+    // pooled adaptation: every chain proposes from ONE shared factor (stride 0) -- except RAM, whose chains
+    // keep private factors between the averaging ticks
+    const bool shared_factor = c.pool_adapt && c.method != MCMCB_RAM;
+    h->r_stride = shared_factor ? 0 : (long long)d * d;
+    h->q_stride = shared_factor ? 0 : h->dp;
+    const size_t NR = shared_factor ? 1 : (size_t)N;
+    CK(cudaMalloc(&h->d_Rm, sizeof(double) * NR * d * d));
     CK(cudaMalloc(&h->d_cmat, sizeof(double) * (size_t)N * d * d));
-    CK(cudaMalloc(&h->d_scratch, sizeof(double) * (size_t)N * d * d * (h->factor_mode == FACTOR_CHOL ? 1 : 2)));
-    CK(cudaMalloc(&h->d_qstd, sizeof(double) * (size_t)N * h->dp));
-    CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * (size_t)N * h->dp, h->stream));
+    CK(cudaMalloc(&h->d_scratch, sizeof(double) * NR * d * d * (h->factor_mode == FACTOR_CHOL ? 1 : 2)));
+    CK(cudaMalloc(&h->d_qstd, sizeof(double) * NR * h->dp));
+    CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * NR * h->dp, h->stream));
     CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * h->rowcap * (d + 1)));
     if (h->store_chains > 0) {
       size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
@@ -443,11 +478,12 @@ struct K2 {
   static int init(mcmcb_handle h) {
     K2Params p = params(h, 0);
     k2_init_kernel<M><<<(unsigned)h->cfg.nchains, 128, 0, h->stream>>>(p);
+    const unsigned nfac = h->r_stride == 0 ? 1u : (unsigned)h->cfg.nchains;  // shared factor: chain 0's cmat == cmat0
     if (h->factor_mode == FACTOR_CHOL)
-      k2_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
+      k2_initR_kernel<<<nfac, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
     else
-      k3_initR_kernel<<<(unsigned)h->cfg.nchains, K2_ADAPT_THREADS, sizeof(double) * 2 * h->npar, h->stream>>>(
-          p, h->d_scratch, h->factor_mode);
+      k3_initR_kernel<<<nfac, K2_ADAPT_THREADS, sizeof(double) * 2 * h->npar, h->stream>>>(p, h->d_scratch,
+                                                                                            h->factor_mode);
     h->launches += 2;
     h->k2_i = 1;
     CK(cudaGetLastError());
@@ -515,8 +551,33 @@ struct K2 {
     return 0;
   }
 
+  // pooled adaptation, pool.cuh
+  static int pool(mcmcb_handle h, int phase) {
+    K2Params p = params(h, 0);
+    const int d = h->npar;
+    if (phase == 3) {
+      k2_pool_factor_kernel<<<1, K2_ADAPT_THREADS, sizeof(double) * 3 * d, h->stream>>>(p, h->d_pool, h->d_scratch,
+                                                                                       h->d_Rpool, h->d_fail);
+      if (h->cfg.method == MCMCB_RAM)
+        k2_pool_broadcast_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(p, h->d_Rpool, h->d_fail);
+      const K2Layout Lo = k2_layout(NY);
+      pool_flag_kernel<<<h->num_sms, 256, 0, h->stream>>>(h->d_ist + (size_t)Lo.i_status * h->pitch, h->pitch,
+                                                          h->cfg.nchains, h->d_fail);
+      h->launches += 3;
+    } else {
+      const int nv = phase == 1 ? 1 + d : d * d;
+      double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + d;
+      k2_pool_moments_kernel<<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
+      pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   static ModelEntry entry() {
     ModelEntry e{};
+    e.pool = &pool;
     e.name = M::name();
     e.kernel = 2;
     e.npar = 0;
@@ -591,6 +652,9 @@ extern "C" int mcmcb_default_config(mcmcb_config* c) {  // mcmcinit.F90:184-230
   c->lanes_per_chain = 0;
   c->dump_stride = 0;
   c->kernel = 0;
+  c->pool_adapt = 0;
+  c->diag_stride = 0;
+  c->diag_lags = 8;
   std::strcpy(c->model, "expreg");
   return MCMCB_OK;
 }
@@ -633,7 +697,12 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
   // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
   if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }
+  // pooled adaptation replaces the chains' own factor updates at the AM ticks; the burn-in scaling branch
+  // (per-chain acceptance driven) and the usesvd DR combination stay per chain and are not pooled
+  if (c.pool_adapt && (c.doburnin || !c.doadapt || c.adaptint <= 0)) { delete h; return MCMCB_EUNSUPPORTED; }
+  if (c.diag_stride < 0 || c.diag_lags < 0 || c.diag_lags > MCMCB_DIAG_MAXLAGS) { delete h; return MCMCB_EINVAL; }
   DevCfg& d = h->dc;
+  d.pool = c.pool_adapt ? 1 : 0;
   d.method = c.method; d.nsimu = c.nsimu; d.doadapt = c.doadapt; d.adaptint = c.adaptint; d.adapthist = c.adapthist;
   d.adaptend = c.adaptend; d.initcmatn = c.initcmatn; d.doburnin = c.doburnin; d.burnintime = c.burnintime;
   d.badaptint = c.badaptint; d.greedy = c.greedy; d.updatesigma = c.updatesigma; d.dodr = h->dodr;
@@ -657,7 +726,8 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
-                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd};
+                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
+                  h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : h->dump_slots) {
@@ -758,6 +828,23 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
     int rc = h->model->alloc(h);
     if (rc) return rc;
   }
+  if (h->cfg.pool_adapt && !h->d_pool) {
+    const size_t nd = (size_t)npar * npar, pn = 1 + (size_t)npar + nd;
+    CK(cudaMalloc(&h->d_pool, sizeof(double) * pn));
+    CK(cudaMemsetAsync(h->d_pool, 0, sizeof(double) * pn, h->stream));
+    CK(cudaMalloc(&h->d_pool_partial, sizeof(double) * (size_t)POOL_BLOCKS * nd));
+    CK(cudaMalloc(&h->d_Rpool, sizeof(double) * nd));
+    CK(cudaMalloc(&h->d_fail, sizeof(int)));
+    CK(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+  }
+  if (h->cfg.diag_stride > 0 && !h->d_diag) {
+    h->diag_K = h->cfg.diag_lags;
+    const size_t ne = (size_t)N * npar, nf = 3 + 3 * (size_t)h->diag_K, nv = 2 + (size_t)h->diag_K;
+    CK(cudaMalloc(&h->d_diag, sizeof(double) * nf * ne));
+    CK(cudaMalloc(&h->d_diag_buf, sizeof(double) * (1 + (size_t)npar + nv * npar)));
+    CK(cudaMalloc(&h->d_diag_partial, sizeof(double) * (size_t)POOL_BLOCKS * nv * npar));
+  }
+  h->diag_n = 0;
   h->L = (h->model->kernel == 1) ? pick_lanes(h) : 32;
   int rc = h->model->init(h);
   if (rc) return rc;
@@ -833,29 +920,175 @@ extern "C" int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int
   return 1;
 }
 
+// ------------------------------------------------------------------ pooled adaptation / diagnostics
+static int do_allreduce(mcmcb_handle h, double* dev, size_t n) {
+  if (!h->ar_fn) return 0;  // single handle: the local sums are the global sums
+  const int rc = h->ar_fn(h->ar_user, dev, n, (void*)h->stream);
+  if (rc) { h->err = "allreduce callback failed"; return MCMCB_ECUDA; }
+  return 0;
+}
+
+// step index i (= simuind after the step) at which the pooled factor is rebuilt: the AM branch of
+// MCMC_adapt (MCMC_adapt.F90:105) for DRAM/AM/SCAM, every adaptint steps for RAM
+static bool is_pool_tick(const mcmcb_config& c, long long i) {
+  if (!c.pool_adapt || c.adaptint <= 0 || i % c.adaptint != 0) return false;
+  if (c.adaptend > 0 && i > c.adaptend) return false;
+  if (c.method == MCMCB_RAM) return true;
+  return i >= (long long)c.burnintime + c.adaptint + c.adapthist;
+}
+
+static int pool_tick(mcmcb_handle h) {
+  const size_t d = (size_t)h->npar;
+  int rc = h->model->pool(h, 1);
+  if (!rc) rc = do_allreduce(h, h->d_pool, 1 + d);
+  if (!rc) rc = h->model->pool(h, 2);
+  if (!rc) rc = do_allreduce(h, h->d_pool + 1 + d, d * d);
+  if (!rc) rc = h->model->pool(h, 3);
+  h->pool_ticks++;
+  return rc;
+}
+
+static DiagParams diag_params(mcmcb_handle h) {
+  DiagParams p{};
+  if (h->model->kernel == 2) { p.theta = h->d_theta; p.chain_stride = h->dp; p.comp_stride = 1; }
+  else { p.theta = h->d_st; p.chain_stride = 1; p.comp_stride = h->pitch; }  // theta = fields 0..npar-1 of the SoA state
+  p.nchains = h->cfg.nchains;
+  p.d = h->npar;
+  p.K = h->diag_K;
+  p.nsnap = h->diag_n;
+  p.ds = h->d_diag;
+  return p;
+}
+
+static int diag_snapshot(mcmcb_handle h) {
+  DiagParams p = diag_params(h);
+  const long long ne = p.nchains * p.d;
+  diag_update_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(p);
+  h->launches++;
+  h->diag_n++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ run
 extern "C" int mcmcb_run(mcmcb_handle h, int nsteps) {
   if (!h || nsteps < 0) return MCMCB_EINVAL;
   if (!h->initial_set || !h->d_blob) return MCMCB_EINVAL;
   if (h->cfg.rng_mode == MCMCB_RNG_INJECTED && !h->d_inj) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
+  const mcmcb_config& c = h->cfg;
   int left = nsteps;
-  const int stride = h->cfg.dump_stride;
   do {
+    // a launch ends where the host has something to do: streamed dump, diagnostics snapshot, pooled tick.
+    // simuind after k more steps = 1 + steps_done + k (the first launch also evaluates the initial point)
     int n = left;
-    if (stride > 0) {
-      int to_next = stride - (int)(h->steps_done % stride);
-      n = std::min(left, to_next);
-    }
+    if (c.dump_stride > 0) n = std::min<long long>(n, c.dump_stride - h->steps_done % c.dump_stride);
+    if (c.diag_stride > 0) n = std::min<long long>(n, c.diag_stride - h->steps_done % c.diag_stride);
+    if (c.pool_adapt) n = std::min<long long>(n, c.adaptint - (1 + h->steps_done) % c.adaptint);
     int rc = h->model->step(h, n);
     if (rc) return rc;
     h->steps_done += n;
     left -= n;
-    if (stride > 0 && h->steps_done % stride == 0 && n > 0) {
+    if (n > 0 && is_pool_tick(c, 1 + h->steps_done)) {
+      rc = pool_tick(h);
+      if (rc) return rc;
+    }
+    if (n > 0 && c.diag_stride > 0 && h->steps_done % c.diag_stride == 0) {
+      rc = diag_snapshot(h);
+      if (rc) return rc;
+    }
+    if (n > 0 && c.dump_stride > 0 && h->steps_done % c.dump_stride == 0) {
       rc = dump_enqueue(h);
       if (rc) return rc;
     }
   } while (left > 0);
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_set_allreduce(mcmcb_handle h, mcmcb_allreduce_fn fn, void* user) {
+  if (!h) return MCMCB_EINVAL;
+  h->ar_fn = fn;
+  h->ar_user = user;
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_pool_fetch(mcmcb_handle h, double* wsum, double* mean, double* cov) {
+  if (!h || !h->d_pool) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t d = (size_t)h->npar, n = 1 + d + d * d;
+  std::vector<double> b(n);
+  CK(cudaMemcpyAsync(b.data(), h->d_pool, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  // after a tick the S2 block holds the pooled covariance itself (k2_pool_factor_kernel divides in place;
+  // the K1 path leaves the raw sums) -- normalise here so both kernels report the same thing
+  const double W = b[0];
+  const bool ram = h->cfg.method == MCMCB_RAM;
+  const double den = (h->model->kernel == 2) ? 1.0 : (ram ? W : W - 1.0);
+  if (wsum) *wsum = W;
+  if (mean) for (size_t k = 0; k < d; k++) mean[k] = W > 0.0 ? b[1 + k] / W : 0.0;
+  if (cov) for (size_t k = 0; k < d * d; k++) cov[k] = b[1 + d + k] / den;
+  return MCMCB_OK;
+}
+
+extern "C" int mcmcb_diag_reset(mcmcb_handle h) {
+  if (!h) return MCMCB_EINVAL;
+  h->diag_n = 0;
+  return MCMCB_OK;
+}
+
+// R-hat and ESS from the chain-summed moments (Gelman et al., BDA3 11.4-11.5; Stan's multi-chain ESS with
+// Geyer's initial positive sequence, lags limited to diag_lags)
+extern "C" int mcmcb_diagnostics(mcmcb_handle h, double* rhat, double* ess, double* mean, double* var, long long* nsnap,
+                                 long long* nchains_total) {
+  if (!h || !h->d_diag || h->diag_n < 2) return MCMCB_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const int d = h->npar, K = h->diag_K, nv = 2 + K;
+  DiagParams p = diag_params(h);
+  double* buf = h->d_diag_buf;
+  dim3 grid(POOL_BLOCKS, d);
+  diag_reduce_kernel<<<grid, POOL_THREADS, 0, h->stream>>>(p, 1, buf, h->d_diag_partial);
+  diag_final_kernel<<<(d * 2 + 255) / 256, 256, 0, h->stream>>>(h->d_diag_partial, POOL_BLOCKS, 2, d, 1, buf);
+  CK(cudaGetLastError());
+  int rc = do_allreduce(h, buf, 1 + (size_t)d);
+  if (rc) return rc;
+  diag_reduce_kernel<<<grid, POOL_THREADS, 0, h->stream>>>(p, 2, buf, h->d_diag_partial);
+  diag_final_kernel<<<(d * nv + 255) / 256, 256, 0, h->stream>>>(h->d_diag_partial, POOL_BLOCKS, nv, d, 2, buf + 1 + d);
+  CK(cudaGetLastError());
+  rc = do_allreduce(h, buf + 1 + d, (size_t)nv * d);
+  if (rc) return rc;
+  h->launches += 4;
+  std::vector<double> b(1 + (size_t)d + (size_t)nv * d);
+  CK(cudaMemcpyAsync(b.data(), buf, sizeof(double) * b.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const double M = b[0], n = (double)h->diag_n;
+  if (nsnap) *nsnap = h->diag_n;
+  if (nchains_total) *nchains_total = (long long)(M + 0.5);
+  for (int k = 0; k < d; k++) {
+    const double* s = &b[1 + d + (size_t)k * nv];
+    const double mu = b[1 + k] / M;
+    const double Wv = s[1] / M;                              // mean within-chain variance
+    const double Bn = M > 1.0 ? s[0] / (M - 1.0) : 0.0;      // variance of the chain means = B / n
+    const double varp = (n - 1.0) / n * Wv + Bn;             // marginal posterior variance estimate
+    if (mean) mean[k] = mu;
+    if (var) var[k] = varp;
+    if (rhat) rhat[k] = std::sqrt(varp / Wv);
+    if (ess) {
+      // rho_t = 1 - (W - mean_c acov_t,c) / var+, acov scaled n/(n-1) like the within variance
+      auto rho = [&](int t) {
+        if (t == 0) return 1.0 - (Wv - Wv) / varp;
+        return 1.0 - (Wv - (s[1 + t] / M) * n / (n - 1.0)) / varp;
+      };
+      const int T = (int)std::min<long long>(K, h->diag_n - 1);
+      double tau = -1.0;
+      for (int t = 0; t <= T; t += 2) {
+        const double pair = rho(t) + (t + 1 <= T ? rho(t + 1) : 0.0);
+        if (pair <= 0.0 && t > 0) break;
+        tau += 2.0 * pair;
+      }
+      if (tau < 1.0 / std::log10(M * n + 10.0)) tau = 1.0 / std::log10(M * n + 10.0);  // Stan's cap on super-efficiency
+      ess[k] = M * n / tau;
+    }
+  }
   return MCMCB_OK;
 }
 

@@ -17,6 +17,7 @@ struct DevCfg {
   int doadapt, adaptint, adapthist, adaptend, initcmatn;
   int doburnin, burnintime, badaptint, greedy;
   int updatesigma, dodr, doscam, usesvd;
+  int pool;  // pooled cross-chain adaptation: factors are written by the pool kernels, not at the chain's own ticks
   double scalelimit, scalefactor, drscale, condmax;
   double N0, S02;
   double alphatarget, nuparam;

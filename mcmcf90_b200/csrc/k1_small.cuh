@@ -87,17 +87,9 @@ struct K1Params {
 
 __host__ __device__ constexpr int pk(int i, int j) { return j * (j + 1) / 2 + i; }  // i <= j
 
-// R = chol(cm)*2.4/sqrt(D); iC = inv(R'R); R2 = R/drscale.  MCMC_adapt.F90:181-230 with
-// covtor (matutils.F90:345-374) = dpotf2('U') and dpotri('U') = dtrti2 + dlauu2.
-// Returns false (and leaves R,R2,iC untouched) if the factorisation fails.
+// dpotf2('U') on a packed upper triangle, in place; false if a pivot is not positive (A is then garbage)
 template <int D>
-__device__ __forceinline__ bool calculate_R(const double (&cm)[D * (D + 1) / 2], double (&R)[D * (D + 1) / 2],
-                                            double (&R2)[D * (D + 1) / 2], double (&iC)[D * (D + 1) / 2],
-                                            const DevCfg& c) {
-  constexpr int T = D * (D + 1) / 2;
-  double A[T];
-#pragma unroll
-  for (int k = 0; k < T; k++) A[k] = cm[k];
+__device__ __forceinline__ bool chol_packed(double (&A)[D * (D + 1) / 2]) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < D; j++) {
@@ -117,6 +109,21 @@ __device__ __forceinline__ bool calculate_R(const double (&cm)[D * (D + 1) / 2],
       A[pk(j, k)] = (A[pk(j, k)] - tt) * rajj;
     }
   }
+  return ok;
+}
+
+// R = chol(cm)*2.4/sqrt(D); iC = inv(R'R); R2 = R/drscale.  MCMC_adapt.F90:181-230 with
+// covtor (matutils.F90:345-374) = dpotf2('U') and dpotri('U') = dtrti2 + dlauu2.
+// Returns false (and leaves R,R2,iC untouched) if the factorisation fails.
+template <int D>
+__device__ __forceinline__ bool calculate_R(const double (&cm)[D * (D + 1) / 2], double (&R)[D * (D + 1) / 2],
+                                            double (&R2)[D * (D + 1) / 2], double (&iC)[D * (D + 1) / 2],
+                                            const DevCfg& c) {
+  constexpr int T = D * (D + 1) / 2;
+  double A[T];
+#pragma unroll
+  for (int k = 0; k < T; k++) A[k] = cm[k];
+  const bool ok = chol_packed<D>(A);
   if (!ok) return false;
   const double sq = sqrt((double)D);
 #pragma unroll
@@ -631,7 +638,8 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
       } else if (i >= c.burnintime + c.adaptint + c.adapthist && c.doadapt) {  // MCMC_adapt.F90:105-159
         absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
         S.pend = 0;
-        if (!calculate_R<D>(S.cm, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
+        // pooled adaptation: the factor comes from the covariance pooled over all chains (pool.cuh)
+        if (!c.pool && !calculate_R<D>(S.cm, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
       }
     }
   }

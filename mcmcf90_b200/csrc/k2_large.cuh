@@ -85,6 +85,7 @@ struct K2Params {
   int tick_i;      // adaptation kernel: the step index i of this tick
   double* qstd;    // [chain][dp]  SCAM proposal standard deviations (k3_scam.cuh)
   int factor_mode; // 0 = row-major upper Cholesky factor, 1 = column-major SVD factor (usesvd), 2 = SCAM
+  long long r_stride, q_stride;  // per-chain strides of Rm / qstd: d*d / dp, or 0 when every chain shares the pooled factor
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -169,7 +170,7 @@ __global__ void k2_init_kernel(K2Params p) {
   }
   for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
     p.cmat[(size_t)c * d * d + k] = p.cmat0[k];
-    p.Rm[(size_t)c * d * d + k] = 0.0;
+    p.Rm[(size_t)c * p.r_stride + k] = 0.0;
   }
   if (threadIdx.x == 0) {
     double* st = p.st + c;
@@ -239,7 +240,7 @@ __global__ void k2_initR_kernel(K2Params p, double* scratch) {
   const long long c = blockIdx.x;
   const int d = p.d;
   constexpr K2Layout Lo = k2_layout(1);
-  bool ok = cta_calculate_R(p.cmat + (size_t)c * d * d, p.Rm + (size_t)c * d * d, scratch + (size_t)c * d * d, d, red);
+  bool ok = cta_calculate_R(p.cmat + (size_t)c * d * d, p.Rm + (size_t)c * p.r_stride, scratch + (size_t)c * d * d, d, red);
   if (!ok && threadIdx.x == 0) p.ist[Lo.i_status * p.pitch + c] |= MCMCB_ST_CHOLFAIL;
 }
 
@@ -276,7 +277,7 @@ __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   double* st = p.st + c;
   int* ist = p.ist + c;
   double* cm = p.cmat + (size_t)c * d * d;
-  double* Rm = p.Rm + (size_t)c * d * d;
+  double* Rm = p.Rm + (size_t)c * p.r_stride;
   double* mean = p.mean + c * p.dp;
   double* theta = p.theta + c * p.dp;
   double* rb = p.rowbuf + (size_t)c * p.rowcap * (d + 1);
@@ -313,7 +314,7 @@ __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       ist[Lo.i_pend * p.pitch] = 0;
       ist[Lo.i_nbuf * p.pitch] = 0;
     }
-    if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
+    if (!cf.pool && !cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
   }
 }
 
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_con
     const long long cc = tile;
     double* st = p.st + cc;
     int* ist = p.ist + cc;
-    double* Rm = p.Rm + (size_t)cc * d * d;
+    double* Rm = p.Rm + (size_t)cc * p.r_stride;
     double* gth = p.theta + cc * dp;
     double* rb = p.rowbuf + (size_t)cc * p.rowcap * (d + 1);
 

@@ -176,7 +176,7 @@ __global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
   const int d = p.d;
   double* sv = sh;
   int* perm = reinterpret_cast<int*>(sh + d);
-  const int st = cta_calculate_R_svd(p.cmat + (size_t)c * d * d, p.Rm + (size_t)c * d * d, p.qstd + c * p.dp,
+  const int st = cta_calculate_R_svd(p.cmat + (size_t)c * d * d, p.Rm + (size_t)c * p.r_stride, p.qstd + c * p.q_stride,
                                      scratch + (size_t)c * 2 * d * d, scratch + (size_t)c * 2 * d * d + (size_t)d * d, d,
                                      mode, p.c.condmax, sv, perm, red);
   if (st && threadIdx.x == 0) p.ist[Lo.i_status * p.pitch + c] |= st;
@@ -196,7 +196,7 @@ __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
   double* st = p.st + c;
   int* ist = p.ist + c;
   double* cm = p.cmat + (size_t)c * d * d;
-  double* Rm = p.Rm + (size_t)c * d * d;
+  double* Rm = p.Rm + (size_t)c * p.r_stride;
   double* mean = p.mean + c * p.dp;
   double* theta = p.theta + c * p.dp;
   double* rb = p.rowbuf + (size_t)c * p.rowcap * (d + 1);
@@ -223,7 +223,7 @@ __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
         ist[Lo.i_pend * p.pitch] = ist[Lo.i_cnt * p.pitch];
         ist[Lo.i_nbuf * p.pitch] = 0;
       }
-      status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.dp, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
+      status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
     }
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
     for (int r = 0; r < nbuf; r++) cta_absorb(rb + (size_t)r * (d + 1), rb[(size_t)r * (d + 1) + d], cm, mean, wsum, d, dvec);
@@ -234,7 +234,7 @@ __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
       ist[Lo.i_pend * p.pitch] = 0;
       ist[Lo.i_nbuf * p.pitch] = 0;
     }
-    status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.dp, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
+    if (!cf.pool) status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
   }
   if (status && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= status;
 }
@@ -271,9 +271,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k3_scam_step_kernel(const __gri
     const long long cc = tile;
     double* st = p.st + cc;
     int* ist = p.ist + cc;
-    const double* U = p.Rm + (size_t)cc * d * d;
+    const double* U = p.Rm + (size_t)cc * p.r_stride;
     double* gth = p.theta + cc * dp;
-    const double* gq = p.qstd + cc * dp;
+    const double* gq = p.qstd + cc * p.q_stride;
     double* rb = p.rowbuf + (size_t)cc * p.rowcap * (d + 1);
 
     for (int k = lane; k < dp; k += 32) { th[k] = gth[k]; prop[k] = gth[k]; qs[k] = gq[k]; }

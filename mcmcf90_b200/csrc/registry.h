@@ -25,6 +25,8 @@ struct ModelEntry {
   int (*fetch)(mcmcb_handle_s*, const char* what, void* out, size_t out_bytes);
   int (*fetch_chain)(mcmcb_handle_s*, long long chain, int ld, double* chain_out, double* sschain_out,
                      double* s2chain_out, int* nrows);
+  // pooled adaptation (pool.cuh): phase 1/2 = local moment sums into h->d_pool, 3 = apply the pooled factor
+  int (*pool)(mcmcb_handle_s*, int phase);
 };
 
 std::vector<ModelEntry>& registry();
@@ -65,7 +67,17 @@ struct mcmcb_handle_s {
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
          *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr;
   int dp = 0, rowcap = 0, factor_mode = 0;
+  long long r_stride = 0, q_stride = 0;
   long long k2_i = 1;  // simuind shared by all chains of the handle
+  // pooled adaptation + diagnostics (pool.cuh, diag.cuh)
+  mcmcb_allreduce_fn ar_fn = nullptr;
+  void* ar_user = nullptr;
+  double *d_pool = nullptr, *d_pool_partial = nullptr, *d_Rpool = nullptr;
+  int* d_fail = nullptr;
+  long long pool_ticks = 0;
+  double *d_diag = nullptr, *d_diag_buf = nullptr, *d_diag_partial = nullptr;
+  long long diag_n = 0;
+  int diag_K = 0;
   std::vector<double> h_tmp;
   std::vector<mcmcb::DumpSlot> dump_slots;
   std::deque<int> dump_fifo;

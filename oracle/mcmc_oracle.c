@@ -58,6 +58,11 @@ struct orc_chain {
   orc_rng rng;
   int status;
   double S02;
+  /* loop-carried locals of MCMC_run / MCMC_run_ram / MCMC_run_scam, kept here so that a run can be
+   * advanced in pieces (orc_advance) -- the pooled-adaptation tests stop every chain at the ticks */
+  double *ss1, sspri1, alpha12;
+  int started, next_i;
+  int pool; /* 1: MCMC_adapt updates chaincmat/chainmean only; R comes from orc_factor_from_cov */
 };
 
 /* ------------------------------------------------------------------ Philox */
@@ -859,25 +864,31 @@ static void mcmc_adapt(orc_chain* ch, int simuind) {
   } else {
     return;                                                      /* :161-166 */
   }
-  calculate_R(ch, ch->chaincmat);                                /* :168-171: on failure keep old R */
+  if (!ch->pool) calculate_R(ch, ch->chaincmat);                 /* :168-171: on failure keep old R */
 }
 
 /* MCMC_run.F90:12-114 */
-static void run_dram(orc_chain* ch) {
+static void run_dram(orc_chain* ch, int upto) {
   const orc_cfg* c = &ch->cfg;
   int n = ch->npar, m = ch->nycol;
   double* oldpar = ch->oldpar;
   double* newpar = (double*)malloc(sizeof(double) * (size_t)n * 2);
   double* newpar2 = newpar + n;
-  double* ss1 = (double*)malloc(sizeof(double) * (size_t)m * 3);
-  double *ss2 = ss1 + m, *ss3 = ss1 + 2 * m;
-  double sspri1, sspri2 = 0, sspri3 = 0, alpha12 = 0, alpha13;
-  memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
-  sspri1 = model_priorfun(&ch->model, oldpar);
-  model_ss(&ch->model, oldpar, ss1);
+  double* ss1 = ch->ss1;
+  double* ss2 = (double*)malloc(sizeof(double) * (size_t)m * 2);
+  double* ss3 = ss2 + m;
+  double sspri1 = ch->sspri1, sspri2 = 0, sspri3 = 0, alpha12 = 0, alpha13;
   int reject = 0;
-  savechain(ch, oldpar, ss1, reject);
-  for (int i = 2; i <= c->nsimu; i++) {
+  if (!ch->started) {
+    memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
+    sspri1 = model_priorfun(&ch->model, oldpar);
+    model_ss(&ch->model, oldpar, ss1);
+    savechain(ch, oldpar, ss1, reject);
+    ch->started = 1;
+    ch->next_i = 2;
+  }
+  int i;
+  for (i = ch->next_i; i <= upto; i++) {
     ch->simuind = i;
     propose(ch, oldpar, ch->R, newpar, NULL);
     int inbounds = model_checkbounds(&ch->model, newpar);
@@ -925,29 +936,36 @@ static void run_dram(orc_chain* ch) {
     savechain(ch, oldpar, ss1, reject);
     mcmc_adapt(ch, i);
     if (getenv("ORC_TRACE")) fprintf(stderr, "step i=%d a12=%.17g rej=%d stayed=%d bnd=%d nd=%llu th=%.17g %.17g s2=%.17g\n", i, alpha12, reject, ch->stayed, ch->bndstayed, (unsigned long long)ch->rng.ndrawn, oldpar[0], oldpar[1], ch->sigma2[0]);
-    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; break; }
+    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; i++; break; }
   }
+  ch->next_i = i;
+  ch->sspri1 = sspri1;
   free(newpar);
-  free(ss1);
+  free(ss2);
 }
 
 /* MCMC_run_ram.F90:13-83, 87-101, 104-179 */
-static void run_ram(orc_chain* ch) {
+static void run_ram(orc_chain* ch, int upto) {
   const orc_cfg* c = &ch->cfg;
   int n = ch->npar, m = ch->nycol;
   double* oldpar = ch->oldpar;
   double* newpar = (double*)malloc(sizeof(double) * (size_t)n * 5);
   double *u = newpar + n, *xv = newpar + 2 * n, *cc = newpar + 3 * n, *sv = newpar + 4 * n;
-  double* ss1 = (double*)malloc(sizeof(double) * (size_t)m * 2);
-  double* ss2 = ss1 + m;
-  double sspri1, sspri2 = 0;
-  double alpha12 = 0.0; /* undefined in the reference before the first in-bounds proposal: declared 0 */
-  memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
-  sspri1 = model_priorfun(&ch->model, oldpar);
-  model_ss(&ch->model, oldpar, ss1);
+  double* ss1 = ch->ss1;
+  double* ss2 = (double*)malloc(sizeof(double) * (size_t)m);
+  double sspri1 = ch->sspri1, sspri2 = 0;
+  double alpha12 = ch->alpha12; /* undefined in the reference before the first in-bounds proposal: declared 0 */
   int reject = 0;
-  savechain(ch, oldpar, ss1, reject);
-  for (int i = 2; i <= c->nsimu; i++) {
+  if (!ch->started) {
+    memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
+    sspri1 = model_priorfun(&ch->model, oldpar);
+    model_ss(&ch->model, oldpar, ss1);
+    savechain(ch, oldpar, ss1, reject);
+    ch->started = 1;
+    ch->next_i = 2;
+  }
+  int i;
+  for (i = ch->next_i; i <= upto; i++) {
     ch->simuind = i;
     propose(ch, oldpar, ch->R, newpar, u);
     int inbounds = model_checkbounds(&ch->model, newpar);
@@ -983,28 +1001,36 @@ static void run_ram(orc_chain* ch) {
         if (info != 0) ch->status |= ORC_ST_DOWNDATE_FAIL; /* reference stops: declared flag+skip */
       }
     }
-    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; break; }
+    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; i++; break; }
   }
+  ch->next_i = i;
+  ch->sspri1 = sspri1;
+  ch->alpha12 = alpha12;
   free(newpar);
-  free(ss1);
+  free(ss2);
 }
 
 /* MCMC_run_scam.F90:12-91, 94-138 */
-static void run_scam(orc_chain* ch) {
+static void run_scam(orc_chain* ch, int upto) {
   const orc_cfg* c = &ch->cfg;
   int n = ch->npar, m = ch->nycol, ld = c->nsimu;
   double* oldpar = ch->oldpar;
   double* newpar = (double*)malloc(sizeof(double) * (size_t)n * 2);
   double* rotpar = newpar + n;
-  double* ss1 = (double*)malloc(sizeof(double) * (size_t)m * 2);
-  double* ss2 = ss1 + m;
-  double sspri1, sspri2 = 0, alpha12;
-  memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
-  sspri1 = model_priorfun(&ch->model, oldpar);
-  model_ss(&ch->model, oldpar, ss1);
+  double* ss1 = ch->ss1;
+  double* ss2 = (double*)malloc(sizeof(double) * (size_t)m);
+  double sspri1 = ch->sspri1, sspri2 = 0, alpha12;
   int rejall = 0, reject;
-  savechain(ch, oldpar, ss1, rejall);
-  for (int i = 2; i <= c->nsimu; i++) {
+  if (!ch->started) {
+    memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
+    sspri1 = model_priorfun(&ch->model, oldpar);
+    model_ss(&ch->model, oldpar, ss1);
+    savechain(ch, oldpar, ss1, rejall);
+    ch->started = 1;
+    ch->next_i = 2;
+  }
+  int i;
+  for (i = ch->next_i; i <= upto; i++) {
     ch->simuind = i;
     rejall = 1;
     for (int j = 1; j <= n; j++) {
@@ -1038,10 +1064,12 @@ static void run_scam(orc_chain* ch) {
     updatesigma2(ch, ss1);
     savechain(ch, oldpar, ss1, rejall);
     mcmc_adapt(ch, i);
-    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; break; }
+    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; i++; break; }
   }
+  ch->next_i = i;
+  ch->sspri1 = sspri1;
   free(newpar);
-  free(ss1);
+  free(ss2);
 }
 
 /* ------------------------------------------------------------ lifecycle */
@@ -1081,6 +1109,8 @@ orc_chain* orc_create(const orc_cfg* cfg, int model_id, const double* blob, long
   free(c0);
   ch->S02 = ch->cfg.S02;
   if (ch->S02 <= 0.0) ch->S02 = ch->sigma2[0]; /* MCMC_init.F90:114-116 */
+  ch->ss1 = (double*)calloc((size_t)nycol, sizeof(double));
+  ch->alpha12 = 0.0;
   return ch;
 }
 
@@ -1099,21 +1129,45 @@ void orc_set_rng_philox(orc_chain* ch, uint64_t seed, uint64_t chain_id) {
   ch->rng.mode = 1; ch->rng.seed = seed; ch->rng.chain = chain_id;
 }
 
-int orc_run(orc_chain* ch) { /* mcmc_main.F90:29-37 */
+/* advance to step index `upto` (= simuind; <= nsimu); the first call also does the initial point */
+int orc_advance(orc_chain* ch, int upto) { /* mcmc_main.F90:29-37 */
   if (ch->cfg.nsimu < 1) return -1;
+  if (upto > ch->cfg.nsimu) upto = ch->cfg.nsimu;
   switch (ch->cfg.method) {
-    case ORC_SCAM: run_scam(ch); break;
-    case ORC_RAM: run_ram(ch); break;
-    default: run_dram(ch);
+    case ORC_SCAM: run_scam(ch, upto); break;
+    case ORC_RAM: run_ram(ch, upto); break;
+    default: run_dram(ch, upto);
   }
   return ch->status;
 }
+
+int orc_run(orc_chain* ch) { return orc_advance(ch, ch->cfg.nsimu); }
+
+/* pooled adaptation (an extension of the build, see mcmcf90_b200/csrc/pool.cuh): MCMC_adapt keeps
+ * updating chaincmat/chainmean/chainwsum but leaves R alone; the test harness merges the chains'
+ * accumulators and hands every chain the factor of the pooled covariance */
+void orc_set_pool(orc_chain* ch, int on) { ch->pool = on; }
+/* MCMC_calculate_R (MCMC_adapt.F90:181-230) on a caller-supplied covariance (column-major n x n) */
+int orc_factor_from_cov(orc_chain* ch, const double* cov) {
+  size_t nn = (size_t)ch->npar * ch->npar;
+  double* c = (double*)malloc(sizeof(double) * nn);
+  memcpy(c, cov, sizeof(double) * nn);
+  int before = ch->status;
+  ch->status = 0;
+  int info = calculate_R(ch, c);
+  int st = ch->status;
+  ch->status = before | st;
+  free(c);
+  return info != 0 || st != 0;
+}
+/* overwrite the proposal factor (RAM pooling: R = chol(mean R'R)) */
+void orc_set_R(orc_chain* ch, const double* R) { memcpy(ch->R, R, sizeof(double) * (size_t)ch->npar * ch->npar); }
 
 void orc_free(orc_chain* ch) {
   if (!ch) return;
   free(ch->par0); free(ch->oldpar); free(ch->cmat0); free(ch->sigma2); free(ch->nobs);
   free(ch->R); free(ch->R2); free(ch->iC); free(ch->qcovstd); free(ch->chaincmat); free(ch->chainmean);
-  free(ch->chain); free(ch->sschain); free(ch->s2chain);
+  free(ch->chain); free(ch->sschain); free(ch->s2chain); free(ch->ss1);
   free(ch->model.pmu); free(ch->model.psig);
   free(ch);
 }

@@ -62,6 +62,11 @@ void orc_set_prior(orc_chain* ch, const double* mu, const double* sig);   /* pri
 void orc_set_rng_injected(orc_chain* ch, const double* u, long n);
 void orc_set_rng_philox(orc_chain* ch, uint64_t seed, uint64_t chain_id);
 int  orc_run(orc_chain* ch);               /* dispatch, mcmc_main.F90:29-37 */
+int  orc_advance(orc_chain* ch, int upto); /* the same loop, stopped at step index `upto` and resumable */
+/* pooled adaptation (extension of the build, no reference counterpart; mcmcf90_b200/csrc/pool.cuh) */
+void orc_set_pool(orc_chain* ch, int on);
+int  orc_factor_from_cov(orc_chain* ch, const double* cov);   /* MCMC_calculate_R on a given covariance */
+void orc_set_R(orc_chain* ch, const double* R);
 void orc_free(orc_chain* ch);
 
 /* results (column-major like the Fortran arrays; leading dimension nsimu) */

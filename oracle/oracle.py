@@ -54,6 +54,10 @@ def lib():
         L.orc_set_rng_injected.argtypes = [C.c_void_p, dp, C.c_long]
         L.orc_set_rng_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.orc_run.argtypes = [C.c_void_p]
+        L.orc_advance.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_pool.argtypes = [C.c_void_p, C.c_int]
+        L.orc_factor_from_cov.argtypes = [C.c_void_p, dp]
+        L.orc_set_R.argtypes = [C.c_void_p, dp]
         L.orc_free.argtypes = [C.c_void_p]
         for n in ("chain", "sschain", "s2chain", "R", "R2", "iC", "qcovstd", "cmat", "mean", "sigma2", "par"):
             f = getattr(L, "orc_%s_ptr" % n)
@@ -178,6 +182,21 @@ class Chain:
     def run(self):
         return lib().orc_run(self.h)
 
+    def advance(self, upto):
+        """Run up to step index `upto` (simuind); resumable."""
+        return lib().orc_advance(self.h, int(upto))
+
+    def set_pool(self, on=True):
+        lib().orc_set_pool(self.h, 1 if on else 0)
+
+    def factor_from_cov(self, cov):
+        cov = np.asfortranarray(np.asarray(cov, dtype=np.float64))
+        return lib().orc_factor_from_cov(self.h, _dp(cov))
+
+    def set_R(self, R):
+        R = np.asfortranarray(np.asarray(R, dtype=np.float64))
+        lib().orc_set_R(self.h, _dp(R))
+
     def _arr(self, name, shape, order="F"):
         p = getattr(lib(), "orc_%s_ptr" % name)(self.h)
         n = int(np.prod(shape))
@@ -241,3 +260,64 @@ def run_batch(cfg, model_id, blob, par0, cmat0, sigma2, nobs, seed=0, chain0=0, 
                     _dp(last), _dp(mean), _dp(cm), cnt.ctypes.data_as(C.POINTER(C.c_long)),
                     _dp(cmean), _dp(ccov), C.byref(sec))
     return dict(par=last, mean=mean, cmat=cm, counters=cnt, chain_mean=cmean, chain_cov=ccov, seconds=sec.value)
+
+
+def pooled_moments(wsum, mean, cmat):
+    """Merge of per-chain accumulators (wsum (N,), mean (N,d), cmat (N,d,d)) the way
+    mcmcf90_b200/csrc/pool.cuh defines it: W, mu, cov = S2 / (W - 1)."""
+    w = np.asarray(wsum, dtype=np.float64)
+    use = w > 0
+    w, mean, cmat = w[use], np.asarray(mean)[use], np.asarray(cmat)[use]
+    W = w.sum()
+    mu = (w[:, None] * mean).sum(0) / W
+    dm = mean - mu
+    S2 = ((w - 1.0)[:, None, None] * cmat + w[:, None, None] * dm[:, :, None] * dm[:, None, :]).sum(0)
+    return W, mu, S2 / (W - 1.0)
+
+
+def run_pooled(cfg, model_id, blob, par0, cmat0, sigma2, nobs, seed=0, chain0=0, prior=None):
+    """Reference for pool_adapt = 1: N chains advanced in lockstep; at every pooled tick (the AM
+    branch of MCMC_adapt for DRAM/AM/SCAM, every adaptint steps for RAM) the accumulators are
+    merged and every chain takes the factor of the pooled covariance.  Returns the Chain objects and
+    the list of (step, W, mu, cov) ticks."""
+    par0 = np.asarray(par0, dtype=np.float64)
+    N, d = par0.shape
+    chains = []
+    for c in range(N):
+        ch = Chain(cfg, model_id, blob, par0[c], cmat0, sigma2, nobs, prior=prior)
+        ch.philox(seed, chain0 + c)
+        ch.set_pool(True)
+        chains.append(ch)
+    cc = chains[0].cfg
+    lib().orc_check_params(C.byref(cc))
+    ram = cc.method == RAM
+    ticks = []
+    i = 1
+    while i < cc.nsimu:
+        nxt = min(cc.nsimu, (i // cc.adaptint + 1) * cc.adaptint)
+        for ch in chains:
+            ch.advance(nxt)
+        i = nxt
+        is_tick = i % cc.adaptint == 0 and not (cc.adaptend > 0 and i > cc.adaptend)
+        if not ram:
+            is_tick = is_tick and i >= cc.burnintime + cc.adaptint + cc.adapthist
+        if not is_tick:
+            continue
+        if ram:
+            Rs = np.array([ch._arr("R", (d, d)) for ch in chains])
+            Rs = np.triu(Rs)
+            S = np.einsum("cki,ckj->ij", Rs, Rs) / N
+            R = np.linalg.cholesky(S).T
+            for ch in chains:
+                ch.set_R(R)
+            ticks.append((i, float(N), None, S))
+        else:
+            w = np.array([lib().orc_wsum(ch.h) for ch in chains])
+            m = np.array([ch._arr("mean", (d,)) for ch in chains])
+            cm = np.array([ch._arr("cmat", (d, d)) for ch in chains])
+            cm = np.triu(cm) + np.transpose(np.triu(cm, 1), (0, 2, 1))
+            W, mu, cov = pooled_moments(w, m, cm)
+            for ch in chains:
+                ch.factor_from_cov(cov)
+            ticks.append((i, W, mu, cov))
+    return chains, ticks
