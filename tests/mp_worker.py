@@ -148,4 +148,5 @@ def run_nccl():
 
 if __name__ == "__main__":
     {"gloo": run_gloo, "nccl": run_nccl}[sys.argv[1]]()
-    print("WORKER_OK", os.environ.get("RANK", "0"), flush=True)
+    sys.stdout.write("WORKER_OK %s\n" % os.environ.get("RANK", "0"))
+    sys.stdout.flush()
