@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -426,6 +427,7 @@ struct K2 {
     p.factor_mode = h->factor_mode;
     p.r_stride = h->r_stride;
     p.q_stride = h->q_stride;
+    p.r_resident = h->r_resident ? 1 : 0;
     return p;
   }
 
@@ -462,7 +464,7 @@ struct K2 {
     CK(cudaMalloc(&h->d_scratch, sizeof(double) * NR * d * d * (h->factor_mode == FACTOR_CHOL ? 1 : 2)));
     CK(cudaMalloc(&h->d_qstd, sizeof(double) * NR * h->dp));
     CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * NR * h->dp, h->stream));
-    CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * h->rowcap * (d + 1)));
+    CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * (h->rowcap + 1) * (d + 1)));
     if (h->store_chains > 0) {
       size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
       CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (d + NY)));
@@ -493,20 +495,22 @@ struct K2 {
   template <bool SMEM>
   static int launch_step(mcmcb_handle h, const K2Params& p) {
     auto kern = (h->factor_mode == FACTOR_SCAM) ? k3_scam_step_kernel<M, SMEM> : k2_step_kernel<M, SMEM>;
-    size_t smem = sizeof(double) * (size_t)K2_WARPS * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0);
+    const int W = h->k2_warps;
+    size_t smem = sizeof(double) * (size_t)W * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0) +
+                  (h->r_resident ? sizeof(double) * (size_t)W * h->npar * h->npar : 0);
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K2_THREADS, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
       h->occ = std::max(occ, 1);
       h->attr_set = true;
     }
-    long long need = (h->cfg.nchains + K2_WARPS - 1) / K2_WARPS;
+    long long need = (h->cfg.nchains + W - 1) / W;
     long long blocks = std::max<long long>(1, std::min<long long>((long long)h->num_sms * h->occ, need));
     h->blocks = (int)blocks;
     h->smem = smem;
     CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
-    kern<<<(unsigned)blocks, K2_THREADS, smem, h->stream>>>(p);
+    kern<<<(unsigned)blocks, W * 32, smem, h->stream>>>(p);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -523,8 +527,26 @@ struct K2 {
   static int step(mcmcb_handle h, int nsteps) {
     const mcmcb_config& c = h->cfg;
     // the blob shares shared memory with the per-warp vectors
-    const size_t vec_bytes = sizeof(double) * (size_t)K2_WARPS * K2_NVEC * h->dp;
-    const bool smem_blob = h->blob_bytes + vec_bytes + 1024 <= h->max_smem;
+    // shared-memory plan: K2_MAX_WARPS warps per CTA (latency hiding: these kernels are issue/latency bound),
+    // the model blob beside the per-warp vectors when it fits.  RAM rewrites its factor every step, so for RAM
+    // a per-warp resident copy of the factor comes first, with as many warps as still fit.
+    const size_t d2 = sizeof(double) * (size_t)h->npar * h->npar, vec1 = sizeof(double) * (size_t)K2_NVEC * h->dp;
+    const bool ram = c.method == MCMCB_RAM && c.doadapt;
+    int W = K2_MAX_WARPS;
+    bool resident = false, smem_blob = false;
+    const char* force = getenv("MCMCB_K2_RESIDENT");  // tuning experiments only
+    if (h->factor_mode != FACTOR_SCAM && (ram || (force && force[0] == '1')) && !(force && force[0] == '0')) {
+      int w = (int)std::min<size_t>(K2_MAX_WARPS, (h->max_smem - 1024) / (vec1 + d2));
+      if (w >= 4) { resident = true; W = w; }
+    }
+    const size_t used = (size_t)W * (vec1 + (resident ? d2 : 0));
+    if (used + 1024 > h->max_smem) W = (int)std::max<size_t>(1, (h->max_smem - 1024) / vec1);
+    smem_blob = (size_t)W * (vec1 + (resident ? d2 : 0)) + h->blob_bytes + 1024 <= h->max_smem;
+    if (!smem_blob && !resident && W > 8 && (size_t)8 * vec1 + h->blob_bytes + 1024 <= h->max_smem) {
+      W = 8;  // a blob in shared memory beats the extra warps
+      smem_blob = true;
+    }
+    if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
     int left = nsteps;
     bool first = true;
     while (left > 0 || first) {
@@ -540,9 +562,11 @@ struct K2 {
       if (seg > 0 && is_tick(c, h->k2_i)) {
         p.tick_i = (int)h->k2_i;
         if (h->factor_mode == FACTOR_CHOL)
-          k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * h->npar, h->stream>>>(p, h->d_scratch);
+          k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
+                            sizeof(double) * absorb_smem_doubles(h->rowcap, h->npar), h->stream>>>(p, h->d_scratch);
         else
-          k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS, sizeof(double) * 3 * h->npar, h->stream>>>(
+          k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
+                            sizeof(double) * (2 * h->npar + absorb_smem_doubles(h->rowcap, h->npar)), h->stream>>>(
               p, h->d_scratch, h->factor_mode);
         h->launches++;
         CK(cudaGetLastError());
@@ -1123,7 +1147,7 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (nycol) *nycol = h->nycol;
   if (lanes) *lanes = h->L;
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
-  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? K2_THREADS : K1_THREADS;
+  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : K1_THREADS;
   if (blocks) *blocks = h->blocks;
   if (smem) *smem = h->smem;
   return MCMCB_OK;

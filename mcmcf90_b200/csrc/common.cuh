@@ -74,6 +74,21 @@ struct Rng {
     return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
   }
 
+  // uniforms k and k+1 of the stream: one Philox block when k is even (both halves of block k/2)
+  __device__ __forceinline__ void uniform_pair_at(unsigned long long k, double& u1, double& u2) {
+    if (inj != nullptr || (k & 1ull)) {
+      u1 = uniform_at(k);
+      u2 = uniform_at(k + 1ull);
+      return;
+    }
+    const unsigned long long blk = k >> 1;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), o);
+    u1 = (double)((((unsigned long long)o[1] << 32) | o[0]) >> 11) * (1.0 / 9007199254740992.0);
+    u2 = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * (1.0 / 9007199254740992.0);
+  }
+
   __device__ __forceinline__ double uniform() {
     if (inj != nullptr) {
       double u = 0.5;

@@ -25,8 +25,8 @@
 
 namespace mcmcb {
 
-constexpr int K2_WARPS = 8;            // warps (= chains in flight) per CTA
-constexpr int K2_THREADS = K2_WARPS * 32;
+constexpr int K2_MAX_WARPS = 16;       // warps (= chains in flight) per CTA: 16, or 8 when the resident factor needs the room
+constexpr int K2_MAX_THREADS = K2_MAX_WARPS * 32;
 constexpr int K2_MAXM = 8;             // npar <= 32 * K2_MAXM
 constexpr int K2_NVEC = 6;             // per-warp shared vectors
 constexpr int K2_ADAPT_THREADS = 256;
@@ -86,6 +86,7 @@ struct K2Params {
   double* qstd;    // [chain][dp]  SCAM proposal standard deviations (k3_scam.cuh)
   int factor_mode; // 0 = row-major upper Cholesky factor, 1 = column-major SVD factor (usesvd), 2 = SCAM
   long long r_stride, q_stride;  // per-chain strides of Rm / qstd: d*d / dp, or 0 when every chain shares the pooled factor
+  int r_resident;  // 1: the warp keeps its chain's factor in shared memory for the whole launch (d*d doubles per warp)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -104,7 +105,8 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
     filled = 1;
   }
   while (filled < n) {
-    const double u1 = g.uniform_at(g.nd + 2ull * lane), u2 = g.uniform_at(g.nd + 2ull * lane + 1ull);
+    double u1, u2;
+    g.uniform_pair_at(g.nd + 2ull * lane, u1, u2);
     const double x1 = 2.0 * u1 - 1.0, x2 = 2.0 * u2 - 1.0;
     const double xx = x1 * x1 + x2 * x2;
     const bool ok = (xx < 1.0 && xx != 0.0);
@@ -140,18 +142,47 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
   __syncwarp();
 }
 
-// p_j = sum_{i<=j} R(i,j) v_i for the columns this lane owns; R row-major upper
-__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ R, const double* vs, int d, int lane,
+// p_j = sum_{i<=j} R(i,j) v_i for the columns this lane owns; R row-major upper.
+// Column group m (columns 32m .. 32m+31) is a rectangle of rows 0 .. 32m, where every lane is above the
+// diagonal, on top of a 31-row triangle.  The rectangle -- most of the factor -- is two instructions per
+// element (load, DFMA) with U row loads in flight per lane before the first FMA consumes one; predicated
+// loads would be fused with their FMAs and issue one at a time, so out-of-range lanes of the last group
+// load a clamped (valid) column and their sums are simply never used.  Every column still accumulates its
+// rows in ascending order: results are bit-identical to the rolled reference loop.
+template <int U>
+__device__ __forceinline__ double tri_matvec_col(const double* R, const double* vs, int d, int j, int jc) {
+  // j = this lane's column (may be >= d), jc = min(j, d - 1); returns sum_{i <= min(j, d-1)} R(i, jc) v_i
+  const int m32 = j & ~31;                      // first column of the group = last fully rectangular row
+  const int nrect = min(m32 + 1, d);            // rows 0 .. nrect-1: all 32 lanes active
+  double acc = 0.0;
+  int i = 0;
+  for (; i + U <= nrect; i += U) {
+    double r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) r[u] = R[(size_t)(i + u) * d + jc];
+#pragma unroll
+    for (int u = 0; u < U; u++) acc = fma(r[u], vs[i + u], acc);
+  }
+  for (; i < nrect; i++) acc = fma(R[(size_t)i * d + jc], vs[i], acc);
+  // the triangle: rows m32+1 .. m32+31 (clipped to d), lane active while row <= its column
+  const int iend = min(m32 + 32, d);
+  for (; i < iend; i++) {
+    const double r = R[(size_t)i * d + max(jc, i)];
+    const double t = fma(r, vs[i], acc);
+    acc = (i <= j) ? t : acc;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void tri_matvec_t(const double* R, const double* vs, int d, int lane,
                                              double (&acc)[K2_MAXM]) {
+  const int mm = (d + 31) >> 5;
 #pragma unroll
-  for (int m = 0; m < K2_MAXM; m++) acc[m] = 0.0;
-  for (int i = 0; i < d; i++) {
-    const double vi = vs[i];
-    const double* row = R + (size_t)i * d;
-#pragma unroll
-    for (int m = 0; m < K2_MAXM; m++) {
+  for (int m = 0; m < K2_MAXM; m++) {
+    acc[m] = 0.0;
+    if (m < mm) {
       const int j = lane + 32 * m;
-      if (j >= i && j < d) acc[m] = fma(row[j], vi, acc[m]);
+      acc[m] = tri_matvec_col<8>(R, vs, d, j, min(j, d - 1));
     }
   }
 }
@@ -244,31 +275,102 @@ __global__ void k2_initR_kernel(K2Params p, double* scratch) {
   if (!ok && threadIdx.x == 0) p.ist[Lo.i_status * p.pitch + c] |= MCMCB_ST_CHOLFAIL;
 }
 
-// One row of the covmat recursion (matutils.F90:283-310) by the whole CTA; dvec = shared scratch of d doubles.
-__device__ __forceinline__ void cta_absorb(const double* x, double w, double* cm, double* mean, double& wsum, int d,
-                                           double* dvec) {
-  if (wsum > 0.0) {
-    for (int k = threadIdx.x; k < d; k += blockDim.x) dvec[k] = x[k] - mean[k];
-    __syncthreads();
-    const double f1 = w / (wsum + w - 1.0), f2 = wsum / (wsum + w), f3 = w / (wsum + w);
-    for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
-      const int a = k / d, b = k - a * d;
-      cm[k] = cm[k] + f1 * (f2 * (dvec[a] * dvec[b]) - cm[k]);
+// The covmat recursion (matutils.F90:283-310) over all logged rows of one chain by the whole CTA.
+//
+// The reference applies one rank-1 update per row to the whole matrix: cm <- cm + f1 (f2 dv dv' - cm) with
+// dv = x - mean, then mean <- mean + f3 dv.  Doing that row by row is one read+write pass over cm per row
+// (d*d*16 bytes x ~adaptint rows: the tick then costs more than the sampling between ticks).  Here:
+//  phase 1 runs the cheap O(d) part of every row in order -- dv (stored over the row in the row buffer),
+//          the mean, wsum and the per-row coefficients (shared memory) -- thread k owns mean[k];
+//  phase 2 keeps a tile of cm entries in registers and applies the rows' updates to it in order, reading
+//          the dv rows from shared-memory chunks, so cm is read and written ONCE per tick.
+// Every entry sees exactly the reference's sequence of operations, so the result is bit-identical to the
+// row-by-row loop.  Only the upper triangle is computed; the mirror image is written beside it.
+constexpr int ABS_E = 8;    // cm entries per thread and tile
+constexpr int ABS_RC = 8;   // dv rows per shared-memory chunk
+
+// shared scratch: coef[2 * nrows] then chunk[ABS_RC * d]
+__host__ __device__ __forceinline__ size_t absorb_smem_doubles(int rowcap, int d) { return 2 * (size_t)(rowcap + 1) + (size_t)ABS_RC * d; }
+
+__device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* cm, double* mean, double& wsum, int d,
+                                                double* sh) {
+  double* coef = sh;                       // (f1, f2) per row; f2 = -1: no-op row, f2 = -2: reset (first row, wsum == 0)
+  double* chunk = sh + 2 * (size_t)nrows;  // ABS_RC x d
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // ---- phase 1: rows in order; every thread tracks wsum, thread k owns component k
+  double ws = wsum;
+  for (int r = 0; r < nrows; r++) {
+    double* x = rb + (size_t)r * (d + 1);
+    const double w = x[d];
+    if (ws > 0.0) {
+      const double f3 = w / (ws + w);
+      for (int k = tid; k < d; k += nt) {
+        const double dv = x[k] - mean[k];
+        mean[k] = mean[k] + f3 * dv;
+        x[k] = dv;
+      }
+      if (tid == 0) { coef[2 * r] = w / (ws + w - 1.0); coef[2 * r + 1] = ws / (ws + w); }
+      ws = w + ws;
+    } else if (w > 0.0) {
+      for (int k = tid; k < d; k += nt) mean[k] = x[k];
+      if (tid == 0) { coef[2 * r] = 0.0; coef[2 * r + 1] = -2.0; }
+      ws = w;
+    } else {
+      if (tid == 0) { coef[2 * r] = 0.0; coef[2 * r + 1] = -1.0; }
     }
-    for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = mean[k] + f3 * dvec[k];
-    wsum = w + wsum;
-    __syncthreads();
-  } else if (w > 0.0) {
-    for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = x[k];
-    for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = 0.0;
-    wsum = w;
-    __syncthreads();
   }
+  wsum = ws;
+  __syncthreads();
+  // ---- phase 2: tiles of the upper triangle in registers, rows streamed through shared memory
+  const int T = d * (d + 1) / 2;
+  for (int e0 = 0; e0 < T; e0 += nt * ABS_E) {
+    double v[ABS_E];
+    int ia[ABS_E], ib[ABS_E];
+#pragma unroll
+    for (int q = 0; q < ABS_E; q++) {
+      const int e = e0 + q * nt + tid;
+      int b = 0, a = 0;
+      if (e < T) {
+        b = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        while ((b + 1) * (b + 2) / 2 <= e) b++;
+        while (b * (b + 1) / 2 > e) b--;
+        a = e - b * (b + 1) / 2;
+      }
+      ia[q] = a; ib[q] = b;
+      v[q] = (e < T) ? cm[(size_t)a * d + b] : 0.0;
+    }
+    for (int r0 = 0; r0 < nrows; r0 += ABS_RC) {
+      const int nr = min(ABS_RC, nrows - r0);
+      __syncthreads();
+      for (int k = tid; k < nr * d; k += nt) chunk[k] = rb[(size_t)(r0 + k / d) * (d + 1) + (k % d)];
+      __syncthreads();
+      for (int r = 0; r < nr; r++) {
+        const double f1 = coef[2 * (r0 + r)], f2 = coef[2 * (r0 + r) + 1];
+        const double* dv = chunk + (size_t)r * d;
+        if (f2 >= 0.0) {
+#pragma unroll
+          for (int q = 0; q < ABS_E; q++) v[q] = v[q] + f1 * (f2 * (dv[ia[q]] * dv[ib[q]]) - v[q]);
+        } else if (f2 == -2.0) {
+#pragma unroll
+          for (int q = 0; q < ABS_E; q++) v[q] = 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ABS_E; q++) {
+      const int e = e0 + q * nt + tid;
+      if (e < T) {
+        cm[(size_t)ia[q] * d + ib[q]] = v[q];
+        cm[(size_t)ib[q] * d + ia[q]] = v[q];
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
 __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
-  extern __shared__ double sh[];  // d doubles
+  extern __shared__ double sh[];  // absorb_smem_doubles(rowcap, d)
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);
   const long long c = blockIdx.x;
@@ -280,7 +382,7 @@ __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   double* Rm = p.Rm + (size_t)c * p.r_stride;
   double* mean = p.mean + c * p.dp;
   double* theta = p.theta + c * p.dp;
-  double* rb = p.rowbuf + (size_t)c * p.rowcap * (d + 1);
+  double* rb = p.rowbuf + (size_t)c * (p.rowcap + 1) * (d + 1);
   double* tmp = scratch + (size_t)c * d * d;
   const int ma = cf.adaptint > 0 ? i % cf.adaptint : 1;
   const int mb = cf.badaptint > 0 ? i % cf.badaptint : 1;
@@ -306,9 +408,11 @@ __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
     }
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
-    for (int r = 0; r < nbuf; r++) cta_absorb(rb + (size_t)r * (d + 1), rb[(size_t)r * (d + 1) + d], cm, mean, wsum, d, sh);
-    cta_absorb(theta, (double)ist[Lo.i_pend * p.pitch], cm, mean, wsum, d, sh);
+    // the open row joins the logged rows with its pending weight (slot nbuf always exists: rowcap + 1 rows)
+    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+    if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
     __syncthreads();
+    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, sh);
     if (threadIdx.x == 0) {
       st[Lo.wsum * p.pitch] = wsum;
       ist[Lo.i_pend * p.pitch] = 0;
@@ -405,39 +509,51 @@ __device__ __forceinline__ bool warp_chdd(double* R, double* x, double* sv, doub
 }
 
 // y_i = sum_j R(i,j) v_j for the rows this lane owns; R column-major general (dgemv 'N', matutils.F90:161,
-// the usesvd proposal of MCMC_DRAM.F90:27)
-__device__ __forceinline__ void gen_matvec_n(const double* __restrict__ R, const double* vs, int d, int lane,
+// the usesvd proposal of MCMC_DRAM.F90:27).  U columns of loads in flight, same summation order.
+__device__ __forceinline__ void gen_matvec_n(const double* R, const double* vs, int d, int lane,
                                              double (&acc)[K2_MAXM]) {
+  constexpr int U = 8;
+  const int mm = (d + 31) >> 5;
 #pragma unroll
-  for (int m = 0; m < K2_MAXM; m++) acc[m] = 0.0;
-  for (int j = 0; j < d; j++) {
-    const double vj = vs[j];
-    const double* col = R + (size_t)j * d;
+  for (int m = 0; m < K2_MAXM; m++) {
+    acc[m] = 0.0;
+    if (m < mm) {
+      const int ic = min(lane + 32 * m, d - 1);  // clamped row: lanes past d compute a sum nobody reads
+      double a = 0.0;
+      int j = 0;
+      for (; j + U <= d; j += U) {
+        double r[U];
 #pragma unroll
-    for (int m = 0; m < K2_MAXM; m++) {
-      const int i = lane + 32 * m;
-      if (i < d) acc[m] = fma(col[i], vj, acc[m]);
+        for (int u = 0; u < U; u++) r[u] = R[(size_t)(j + u) * d + ic];
+#pragma unroll
+        for (int u = 0; u < U; u++) a = fma(r[u], vs[j + u], a);
+      }
+      for (; j < d; j++) a = fma(R[(size_t)j * d + ic], vs[j], a);
+      acc[m] = a;
     }
   }
 }
 
 template <class M, bool SMEM>
-__global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_constant__ K2Params p) {
+__global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   const int d = p.d, dp = p.dp;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const DevCfg& c = p.c;
 
   // dynamic shared memory: [per-warp vectors][model blob]
   double* vecs = reinterpret_cast<double*>(smem_raw) + (size_t)warp * K2_NVEC * dp;
   double *th = vecs, *prop = vecs + dp, *z1 = vecs + 2 * dp, *z2 = vecs + 3 * dp, *w1 = vecs + 4 * dp,
          *w2 = vecs + 5 * dp;
+  // dynamic shared memory: [per-warp vectors][per-warp resident factors (optional)][model blob (optional)]
+  double* Rs = reinterpret_cast<double*>(smem_raw) + (size_t)nwarps * K2_NVEC * dp + (size_t)warp * d * d;
   const double* data = p.blob;
   if (SMEM) {
-    unsigned char* blob_s = smem_raw + sizeof(double) * (size_t)K2_WARPS * K2_NVEC * dp;
+    unsigned char* blob_s = smem_raw + sizeof(double) * ((size_t)nwarps * K2_NVEC * dp +
+                                                        (p.r_resident ? (size_t)nwarps * d * d : 0));
     tma_stage_blob(blob_s, p.blob, p.blob_bytes, &mbar);
     data = reinterpret_cast<const double*>(blob_s);
   }
@@ -453,10 +569,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_con
     const long long cc = tile;
     double* st = p.st + cc;
     int* ist = p.ist + cc;
-    double* Rm = p.Rm + (size_t)cc * p.r_stride;
+    double* Rg = p.Rm + (size_t)cc * p.r_stride;
+    double* Rm = Rg;
     double* gth = p.theta + cc * dp;
-    double* rb = p.rowbuf + (size_t)cc * p.rowcap * (d + 1);
+    double* rb = p.rowbuf + (size_t)cc * (p.rowcap + 1) * (d + 1);
 
+    if (p.r_resident) {
+      // the factor is read once per launch instead of once per proposal, and the RAM rank-1 updates run at
+      // shared-memory latency; written back once at the end when RAM changed it
+      for (int k = lane; k < d * d; k += 32) Rs[k] = Rg[k];
+      Rm = Rs;
+    }
     for (int k = lane; k < dp; k += 32) { th[k] = gth[k]; prop[k] = gth[k]; }
     double ss1[NY], s2[NY];
 #pragma unroll
@@ -656,6 +779,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_step_kernel(const __grid_con
     }
 
     // ---- write state back
+    if (p.r_resident && c.method == MCMCB_RAM && c.doadapt) {
+      __syncwarp();
+      for (int k = lane; k < d * d; k += 32) Rg[k] = Rs[k];
+    }
     for (int k = lane; k < dp; k += 32) gth[k] = th[k];
     if (lane == 0) {
 #pragma unroll

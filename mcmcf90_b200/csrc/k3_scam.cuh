@@ -184,22 +184,22 @@ __global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i for the SVD factor modes, one CTA per chain.
 __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
-  extern __shared__ double sh[];  // 2 d doubles + d ints
+  extern __shared__ double sh[];  // d doubles + d ints (as d doubles) + absorb_smem_doubles(rowcap, d)
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);
   const long long c = blockIdx.x;
   const DevCfg& cf = p.c;
   const int d = p.d, i = p.tick_i;
-  double* dvec = sh;
-  double* sv = sh + d;
-  int* perm = reinterpret_cast<int*>(sh + 2 * d);
+  double* sv = sh;
+  int* perm = reinterpret_cast<int*>(sh + d);
+  double* dvec = sh + 2 * d;
   double* st = p.st + c;
   int* ist = p.ist + c;
   double* cm = p.cmat + (size_t)c * d * d;
   double* Rm = p.Rm + (size_t)c * p.r_stride;
   double* mean = p.mean + c * p.dp;
   double* theta = p.theta + c * p.dp;
-  double* rb = p.rowbuf + (size_t)c * p.rowcap * (d + 1);
+  double* rb = p.rowbuf + (size_t)c * (p.rowcap + 1) * (d + 1);
   double* tmpA = scratch + (size_t)c * 2 * d * d;
   double* tmpU = tmpA + (size_t)d * d;
   const int ma = cf.adaptint > 0 ? i % cf.adaptint : 1;
@@ -226,9 +226,10 @@ __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
       status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
     }
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
-    for (int r = 0; r < nbuf; r++) cta_absorb(rb + (size_t)r * (d + 1), rb[(size_t)r * (d + 1) + d], cm, mean, wsum, d, dvec);
-    cta_absorb(theta, (double)ist[Lo.i_pend * p.pitch], cm, mean, wsum, d, dvec);
+    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+    if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
     __syncthreads();
+    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, dvec);
     if (threadIdx.x == 0) {
       st[Lo.wsum * p.pitch] = wsum;
       ist[Lo.i_pend * p.pitch] = 0;
@@ -242,7 +243,7 @@ __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
 // SCAM step kernel: one warp per chain; a step = one sweep over the d components
 // (MCMC_run_scam.F90:38-88).
 template <class M, bool SMEM>
-__global__ void __launch_bounds__(K2_THREADS, 1) k3_scam_step_kernel(const __grid_constant__ K2Params p) {
+__global__ void __launch_bounds__(K2_MAX_THREADS, 1) k3_scam_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k3_scam_step_kernel(const __gri
   double *th = vecs, *prop = vecs + dp, *zs = vecs + 2 * dp, *qs = vecs + 3 * dp;
   const double* data = p.blob;
   if (SMEM) {
-    unsigned char* blob_s = smem_raw + sizeof(double) * (size_t)K2_WARPS * K2_NVEC * dp;
+    unsigned char* blob_s = smem_raw + sizeof(double) * (size_t)(blockDim.x >> 5) * K2_NVEC * dp;
     tma_stage_blob(blob_s, p.blob, p.blob_bytes, &mbar);
     data = reinterpret_cast<const double*>(blob_s);
   }
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k3_scam_step_kernel(const __gri
     const double* U = p.Rm + (size_t)cc * p.r_stride;
     double* gth = p.theta + cc * dp;
     const double* gq = p.qstd + cc * p.q_stride;
-    double* rb = p.rowbuf + (size_t)cc * p.rowcap * (d + 1);
+    double* rb = p.rowbuf + (size_t)cc * (p.rowcap + 1) * (d + 1);
 
     for (int k = lane; k < dp; k += 32) { th[k] = gth[k]; prop[k] = gth[k]; qs[k] = gq[k]; }
     double ss1[NY], s2[NY];

@@ -107,8 +107,18 @@ struct GaussN {
     const double* __restrict__ lam = c.data + 2 + dpad;
     double acc = 0.0;
     for (int i = c.lane; i < d; i += c.nlanes) {
+      // four independent partial sums would change the rounding; instead keep the reference order and
+      // unroll so that the loads of the next terms are in flight behind the FMA chain
       double w = 0.0;
-      for (int j = 0; j < d; j++) w = fma(lam[(size_t)j * d + i], theta[j] - mu[j], w);
+      int j = 0;
+      for (; j + 4 <= d; j += 4) {
+        const double l0 = lam[(size_t)j * d + i], l1 = lam[(size_t)(j + 1) * d + i], l2 = lam[(size_t)(j + 2) * d + i],
+                     l3 = lam[(size_t)(j + 3) * d + i];
+        const double d0 = theta[j] - mu[j], d1 = theta[j + 1] - mu[j + 1], d2 = theta[j + 2] - mu[j + 2],
+                     d3 = theta[j + 3] - mu[j + 3];
+        w = fma(l0, d0, w); w = fma(l1, d1, w); w = fma(l2, d2, w); w = fma(l3, d3, w);
+      }
+      for (; j < d; j++) w = fma(lam[(size_t)j * d + i], theta[j] - mu[j], w);
       acc = fma(w, theta[i] - mu[i], acc);
     }
     ss[0] = acc;

@@ -68,6 +68,8 @@ struct mcmcb_handle_s {
          *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr;
   int dp = 0, rowcap = 0, factor_mode = 0;
   long long r_stride = 0, q_stride = 0;
+  bool r_resident = false;
+  int k2_warps = 8;
   long long k2_i = 1;  // simuind shared by all chains of the handle
   // pooled adaptation + diagnostics (pool.cuh, diag.cuh)
   mcmcb_allreduce_fn ar_fn = nullptr;

@@ -51,3 +51,11 @@ if which in ("c4", "all"):
     timeit("C4 banana RAM", dict(method=mb.RAM if hasattr(mb, "RAM") else 1, nsimu=100000, updatesigma=0,
                                  alphatarget=0.234, nuparam=0.7), "banana",
            mb.models.blob_banana(d, 0.03), d, N, 100, np.eye(d), lambda q: 16 * T + 8 * (3 * d + 10))
+if which in ("c5", "all"):
+    G, J, N = 198, 10, int(os.environ.get("N_C5", 2048))
+    d = G + 2
+    rng = np.random.default_rng(5)
+    y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
+    # algorithmic HBM bytes per sweep: every component move reads one column of U (d doubles)
+    timeit("C5 hier SCAM", dict(method=mb.SCAM, nsimu=100000, adaptint=100, initcmatn=1, updatesigma=0), "hier",
+           mb.models.blob_hier(y), d, N, 20, 0.1 * np.eye(d), lambda q: 8 * (d * d + 3 * d + 10))
