@@ -36,6 +36,8 @@ struct mcmcb_ctx {
   const double* prior;      /* default Gaussian prior: mu[npar] then sig[npar]; nullptr = flat */
   int lane, nlanes;         /* this thread's rank among the lanes that share the chain */
   double exp_c1, exp_c2;    /* MCMCB_EXP_C1L, MCMCB_EXP_C2L handed through the kernel-parameter bank (see mcmcb_expmul_fast) */
+  double* scratch;          /* warp-per-chain kernels: npar doubles of shared memory private to the chain's warp
+                               (nullptr in the register kernel) */
   unsigned exp_tl;          /* shared-window byte address of this thread's column of the replicated 2^(j/256)
                                table (see mcmcb_exp; mcmcb_exp_column()); 0 = no table staged, use exp() */
 };

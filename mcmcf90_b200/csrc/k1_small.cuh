@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
   const int sub = lane / L, gl = lane % L;
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
-  ctx.exp_tl = mcmcb_exp_column(exp_tab); ctx.exp_c1 = p.exp_c1; ctx.exp_c2 = p.exp_c2;
+  ctx.exp_tl = mcmcb_exp_column(exp_tab); ctx.exp_c1 = p.exp_c1; ctx.exp_c2 = p.exp_c2; ctx.scratch = nullptr;
 
   K1State<D, NY> S;
   for (;;) {

@@ -149,33 +149,62 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
 // loads would be fused with their FMAs and issue one at a time, so out-of-range lanes of the last group
 // load a clamped (valid) column and their sums are simply never used.  Every column still accumulates its
 // rows in ascending order: results are bit-identical to the rolled reference loop.
+template <int U, bool TRI>
+__device__ __forceinline__ void tmv_load(double (&r)[U], const double* R, int d, int i, int jc) {
+#pragma unroll
+  for (int u = 0; u < U; u++) r[u] = R[(size_t)(i + u) * d + (TRI ? max(jc, i + u) : jc)];
+}
+template <int U, bool TRI>
+__device__ __forceinline__ void tmv_use(const double (&r)[U], const double* vs, int i, int j, double& acc) {
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const double t = fma(r[u], vs[i + u], acc);
+    acc = (!TRI || i + u <= j) ? t : acc;
+  }
+}
+// nb batches of U rows starting at row i, software pipelined: the loads of the next batch are issued before
+// the FMAs of the current one, so a lane keeps U..2U row loads in flight across the whole column
+template <int U, bool TRI>
+__device__ __forceinline__ void tmv_batches(const double* R, const double* vs, int d, int j, int jc, int i, int nb,
+                                            double& acc) {
+  if (nb <= 0) return;
+  double r0[U], r1[U];
+  tmv_load<U, TRI>(r0, R, d, i, jc);
+  int b = 0;
+  while (b + 2 <= nb) {
+    tmv_load<U, TRI>(r1, R, d, i + (b + 1) * U, jc);
+    tmv_use<U, TRI>(r0, vs, i + b * U, j, acc);
+    if (b + 2 < nb) tmv_load<U, TRI>(r0, R, d, i + (b + 2) * U, jc);
+    tmv_use<U, TRI>(r1, vs, i + (b + 1) * U, j, acc);
+    b += 2;
+  }
+  if (b < nb) tmv_use<U, TRI>(r0, vs, i + b * U, j, acc);
+}
+
 template <int U>
 __device__ __forceinline__ double tri_matvec_col(const double* R, const double* vs, int d, int j, int jc) {
   // j = this lane's column (may be >= d), jc = min(j, d - 1); returns sum_{i <= min(j, d-1)} R(i, jc) v_i
   const int m32 = j & ~31;                      // first column of the group = last fully rectangular row
   const int nrect = min(m32 + 1, d);            // rows 0 .. nrect-1: all 32 lanes active
+  const int iend = min(m32 + 32, d);            // rows nrect .. iend-1: the triangle, lane active while row <= column
   double acc = 0.0;
-  int i = 0;
-  for (; i + U <= nrect; i += U) {
-    double r[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) r[u] = R[(size_t)(i + u) * d + jc];
-#pragma unroll
-    for (int u = 0; u < U; u++) acc = fma(r[u], vs[i + u], acc);
-  }
-  for (; i < nrect; i++) acc = fma(R[(size_t)i * d + jc], vs[i], acc);
-  // the triangle: rows m32+1 .. m32+31 (clipped to d), lane active while row <= its column
-  const int iend = min(m32 + 32, d);
-  for (; i < iend; i++) {
-    const double r = R[(size_t)i * d + max(jc, i)];
-    const double t = fma(r, vs[i], acc);
+  const int nb = nrect / U;
+  tmv_batches<U, false>(R, vs, d, j, jc, 0, nb, acc);
+  int i = nb * U;
+  // the rows left over from the rectangle join the triangle: same arithmetic, the select is a no-op for them
+  const int nbt = (iend - i) / U;
+  tmv_batches<U, true>(R, vs, d, j, jc, i, nbt, acc);
+  for (i += nbt * U; i < iend; i++) {
+    const double t = fma(R[(size_t)i * d + max(jc, i)], vs[i], acc);
     acc = (i <= j) ? t : acc;
   }
   return acc;
 }
 
-__device__ __forceinline__ void tri_matvec_t(const double* R, const double* vs, int d, int lane,
-                                             double (&acc)[K2_MAXM]) {
+// not inlined: the pipelined loops get their own register allocation instead of competing with the step
+// kernel's long-lived state (the call happens once per proposal)
+__device__ __noinline__ void tri_matvec_t(const double* R, const double* vs, int d, int lane,
+                                          double (&acc)[K2_MAXM]) {
   const int mm = (d + 31) >> 5;
 #pragma unroll
   for (int m = 0; m < K2_MAXM; m++) {
@@ -321,48 +350,56 @@ __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* c
   }
   wsum = ws;
   __syncthreads();
-  // ---- phase 2: tiles of the upper triangle in registers, rows streamed through shared memory
-  const int T = d * (d + 1) / 2;
-  for (int e0 = 0; e0 < T; e0 += nt * ABS_E) {
-    double v[ABS_E];
-    int ia[ABS_E], ib[ABS_E];
-#pragma unroll
-    for (int q = 0; q < ABS_E; q++) {
-      const int e = e0 + q * nt + tid;
-      int b = 0, a = 0;
-      if (e < T) {
-        b = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-        while ((b + 1) * (b + 2) / 2 <= e) b++;
-        while (b * (b + 1) / 2 > e) b--;
-        a = e - b * (b + 1) / 2;
+  // ---- phase 2: the upper triangle in registers, rows streamed through shared memory.  A thread owns runs
+  // of ABS_E consecutive rows a0 .. a0+7 of one column b, so one row of the recursion costs it one dv[b] and
+  // eight consecutive dv[a] from shared memory for eight entry updates.
+  int nchunk = 0;
+  for (int b = 0; b < d; b++) nchunk += (b + ABS_E) / ABS_E;  // ceil((b + 1) / ABS_E) runs in column b
+  for (int c0 = 0; c0 < nchunk; c0 += nt) {
+    const int cidx = c0 + tid;
+    int b = 0, a0 = 0;
+    bool live = cidx < nchunk;
+    if (live) {  // run index -> (column, first row): walk the columns (d <= 256 steps, once per tick)
+      int left = cidx;
+      for (;;) {
+        const int nb = (b + ABS_E) / ABS_E;
+        if (left < nb) break;
+        left -= nb;
+        b++;
       }
-      ia[q] = a; ib[q] = b;
-      v[q] = (e < T) ? cm[(size_t)a * d + b] : 0.0;
+      a0 = left * ABS_E;
     }
+    double v[ABS_E];
+#pragma unroll
+    for (int q = 0; q < ABS_E; q++) v[q] = (live && a0 + q <= b) ? cm[(size_t)b * d + a0 + q] : 0.0;  // symmetric: (b,a) == (a,b)
     for (int r0 = 0; r0 < nrows; r0 += ABS_RC) {
       const int nr = min(ABS_RC, nrows - r0);
       __syncthreads();
       for (int k = tid; k < nr * d; k += nt) chunk[k] = rb[(size_t)(r0 + k / d) * (d + 1) + (k % d)];
       __syncthreads();
-      for (int r = 0; r < nr; r++) {
-        const double f1 = coef[2 * (r0 + r)], f2 = coef[2 * (r0 + r) + 1];
-        const double* dv = chunk + (size_t)r * d;
-        if (f2 >= 0.0) {
+      if (live) {
+        for (int r = 0; r < nr; r++) {
+          const double f1 = coef[2 * (r0 + r)], f2 = coef[2 * (r0 + r) + 1];
+          const double* dv = chunk + (size_t)r * d;
+          if (f2 >= 0.0) {
+            const double db = dv[b];
+            // rows past the diagonal (a0 + q > b) of the last run read in-bounds garbage that is never stored
 #pragma unroll
-          for (int q = 0; q < ABS_E; q++) v[q] = v[q] + f1 * (f2 * (dv[ia[q]] * dv[ib[q]]) - v[q]);
-        } else if (f2 == -2.0) {
+            for (int q = 0; q < ABS_E; q++) v[q] = v[q] + f1 * (f2 * (dv[min(a0 + q, d - 1)] * db) - v[q]);
+          } else if (f2 == -2.0) {
 #pragma unroll
-          for (int q = 0; q < ABS_E; q++) v[q] = 0.0;
+            for (int q = 0; q < ABS_E; q++) v[q] = 0.0;
+          }
         }
       }
     }
+    if (live) {
 #pragma unroll
-    for (int q = 0; q < ABS_E; q++) {
-      const int e = e0 + q * nt + tid;
-      if (e < T) {
-        cm[(size_t)ia[q] * d + ib[q]] = v[q];
-        cm[(size_t)ib[q] * d + ia[q]] = v[q];
-      }
+      for (int q = 0; q < ABS_E; q++)
+        if (a0 + q <= b) {
+          cm[(size_t)(a0 + q) * d + b] = v[q];
+          cm[(size_t)b * d + a0 + q] = v[q];
+        }
     }
   }
   __syncthreads();
@@ -475,15 +512,27 @@ __device__ __forceinline__ bool warp_chdd(double* R, double* x, double* sv, doub
   if (!(norm < 1.0)) return false;
   double alpha = sqrt(1.0 - norm * norm);
   __syncwarp();
+  // dchdd.f:157-165.  Only alpha is carried from row to row (one division and one square root on the
+  // serial path); lane 0 runs that chain and leaves (alpha_i, scale_i * nr_i) behind, then every lane forms
+  // c_i, s_i of its own rows with the reference's operations -- same values, 3 of the 5 divisions per row
+  // off the serial path.
   if (lane == 0) {
     for (int i = d - 1; i >= 0; i--) {
       const double scale = alpha + fabs(sv[i]);
       const double a = alpha / scale, b = sv[i] / scale;
       const double nr = sqrt(a * a + b * b);
-      cv[i] = a / nr;
-      sv[i] = b / nr;
+      cv[i] = alpha;  // alpha entering row i
       alpha = scale * nr;
     }
+  }
+  __syncwarp();
+  for (int i = lane; i < d; i += 32) {
+    const double al = cv[i];
+    const double scale = al + fabs(sv[i]);
+    const double a = al / scale, b = sv[i] / scale;
+    const double nr = sqrt(a * a + b * b);
+    cv[i] = a / nr;
+    sv[i] = b / nr;
   }
   __syncwarp();
   // apply: per column j, xx runs from row j down to row 0; lanes own columns
@@ -560,6 +609,7 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = lane; ctx.nlanes = 32;
   ctx.exp_tl = 0u; ctx.exp_c1 = MCMCB_EXP_C1L; ctx.exp_c2 = MCMCB_EXP_C2L;
+  ctx.scratch = vecs + 5 * dp;  // w2: free while the model runs
 
   for (;;) {
     unsigned tile = 0;

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k3_scam_step_kernel(const _
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = lane; ctx.nlanes = 32;
   ctx.exp_tl = 0u; ctx.exp_c1 = MCMCB_EXP_C1L; ctx.exp_c2 = MCMCB_EXP_C2L;
+  ctx.scratch = vecs + 5 * dp;  // w2: free while the model runs
 
   for (;;) {
     unsigned tile = 0;

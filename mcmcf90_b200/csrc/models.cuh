@@ -106,20 +106,30 @@ struct GaussN {
     const double* __restrict__ mu = c.data + 2;
     const double* __restrict__ lam = c.data + 2 + dpad;
     double acc = 0.0;
-    for (int i = c.lane; i < d; i += c.nlanes) {
-      // four independent partial sums would change the rounding; instead keep the reference order and
-      // unroll so that the loads of the next terms are in flight behind the FMA chain
-      double w = 0.0;
-      int j = 0;
-      for (; j + 4 <= d; j += 4) {
-        const double l0 = lam[(size_t)j * d + i], l1 = lam[(size_t)(j + 1) * d + i], l2 = lam[(size_t)(j + 2) * d + i],
-                     l3 = lam[(size_t)(j + 3) * d + i];
-        const double d0 = theta[j] - mu[j], d1 = theta[j + 1] - mu[j + 1], d2 = theta[j + 2] - mu[j + 2],
-                     d3 = theta[j + 3] - mu[j + 3];
-        w = fma(l0, d0, w); w = fma(l1, d1, w); w = fma(l2, d2, w); w = fma(l3, d3, w);
+    if (c.scratch != nullptr) {
+      // theta - mu once per evaluation instead of once per matrix entry (same values, same order of the sum)
+      double* df = c.scratch;
+      for (int j = c.lane; j < d; j += c.nlanes) df[j] = theta[j] - mu[j];
+      __syncwarp();
+      for (int i = c.lane; i < d; i += c.nlanes) {
+        const double* col = lam + i;
+        double w = 0.0;
+        int j = 0;
+        for (; j + 4 <= d; j += 4) {
+          const double l0 = col[0], l1 = col[d], l2 = col[2 * d], l3 = col[3 * d];
+          w = fma(l0, df[j], w); w = fma(l1, df[j + 1], w); w = fma(l2, df[j + 2], w); w = fma(l3, df[j + 3], w);
+          col += 4 * d;
+        }
+        for (; j < d; j++, col += d) w = fma(col[0], df[j], w);
+        acc = fma(w, df[i], acc);
       }
-      for (; j < d; j++) w = fma(lam[(size_t)j * d + i], theta[j] - mu[j], w);
-      acc = fma(w, theta[i] - mu[i], acc);
+      __syncwarp();
+    } else {
+      for (int i = c.lane; i < d; i += c.nlanes) {
+        double w = 0.0;
+        for (int j = 0; j < d; j++) w = fma(lam[(size_t)j * d + i], theta[j] - mu[j], w);
+        acc = fma(w, theta[i] - mu[i], acc);
+      }
     }
     ss[0] = acc;
   }
