@@ -38,74 +38,75 @@ struct mcmcb_ctx {
   double exp_c1, exp_c2;    /* MCMCB_EXP_C1L, MCMCB_EXP_C2L handed through the kernel-parameter bank (see mcmcb_expmul_fast) */
   double* scratch;          /* warp-per-chain kernels: npar doubles of shared memory private to the chain's warp
                                (nullptr in the register kernel) */
-  unsigned exp_tl;          /* shared-window byte address of this thread's column of the replicated 2^(j/256)
-                               table (see mcmcb_exp; mcmcb_exp_column()); 0 = no table staged, use exp() */
+  unsigned exp_tl;          /* shared-window byte address of the staged 2^(j/2048) table (see mcmcb_exp;
+                               mcmcb_exp_column()); 0 = no table staged, use exp() */
 };
 
 /* ---------------------------------------------------------------------------------------
  * mcmcb_exp: FP64 exp() for model code, built for the FP64 pipe of sm_100a.
- * exp(a) = 2^m * 2^(j/256) * e^u with k = round(a*256/ln2) = 256 m + j and |u| <= ln2/512, so a
- * degree-4 polynomial reaches double precision (economised: max error 2.4e-18).  2^(j/256) comes
- * from a 256-entry table that the sampling kernels stage in shared memory with every entry
- * replicated 16 times -- hardware lane l reads copy (l mod 16), so the 16 lanes of a half-warp
- * hit 16 distinct 8-byte bank pairs and the lookup is conflict-free whatever j each lane needs.
- * The fast paths are branch-free (independent calls interleave in the instruction stream).
+ * exp(a) = 2^m * 2^(j/2048) * e^u with k = round(a*2048/ln2) = 2048 m + j and |u| <= ln2/4096, so a
+ * degree-2 polynomial for (e^u - 1)/u reaches double precision (near-minimax, relative error of e^u
+ * 8.5e-18 = 0.08 ulp).  2^(j/2048) comes from a 2048-entry table (16 KB) that the sampling kernels
+ * stage in shared memory.  The fast paths are branch-free (independent calls interleave in the
+ * instruction stream).
  *
- *   mcmcb_exp_fast(a)         9 FP64 instructions  (libdevice exp(): 16)
- *   mcmcb_expmul_fast(x, ks)  8 FP64 instructions  = exp(x * s) with ks = mcmcb_expmul_scale(s)
+ *   mcmcb_exp_fast(a)         8 FP64 instructions  (libdevice exp(): 16)
+ *   mcmcb_expmul_fast(x, ks)  7 FP64 instructions  = exp(x * s) with ks = mcmcb_expmul_scale(s)
  *                             computed once per evaluation: the product, the range reduction
- *                             and the change of units to ln2/256 are one DFMA pair.
+ *                             and the change of units to ln2/2048 are one DFMA pair.
  *
  * An FP64 warp instruction occupies the scheduler's issue port for two cycles on sm_100a, so
  * the instruction COUNT of the datum loop, integer and load instructions included, is what
- * sets the speed of a model evaluation.  mcmcb_exp_ok() tells whether an
- * argument is in the fast range (|a| < 708: result normal, no overflow, not NaN).
+ * sets the speed of a model evaluation: a table 8 times larger than the earlier
+ * 256-entry one (which was replicated 16 times to be free of bank conflicts) buys one Horner step;
+ * the lookups now conflict (about 3 wavefronts per half-warp for random j), which costs shared-memory
+ * pipe cycles but no issue slots.  mcmcb_exp_ok() tells whether an argument is in the fast range
+ * (|a| < 708: result normal, no overflow, not NaN).
  * ------------------------------------------------------------------------------------- */
-#define MCMCB_EXP_TAB_N 256
-#define MCMCB_EXP_TAB_REP 16
+#define MCMCB_EXP_TAB_N 2048
+#define MCMCB_EXP_TAB_REP 1
 #define MCMCB_EXP_TAB_DOUBLES (MCMCB_EXP_TAB_N * MCMCB_EXP_TAB_REP)
+#define MCMCB_EXP_TAB_SHIFT 9 /* 2^20 / MCMCB_EXP_TAB_N: k << 9 puts m = k >> 11 at the exponent field */
 
 /* coefficients live in the constant bank so that DFMA/DMUL read them as c[][] operands instead
- * of re-materialising 64-bit immediates inside the loop */
+ * of re-materialising 64-bit immediates inside the loop (scripts/gen_exp_table.py prints them) */
 __constant__ double MCMCB_EXPC[10] = {
-    0x1.71547652b82fep+8,   /* [0] 256/ln2 */
-    -0x1.62e42fee00000p-9,  /* [1] -ln2/256, high part (21 trailing zero bits: k*hi is exact) */
-    -0x1.a39ef35793c76p-41, /* [2] -ln2/256, low part */
-    /* e^u - 1 = u (c1 + u (1/2 + u (c3 + u/24))) on |u| <= h = ln2/512: degree-5 Taylor with the u^5
-     * term Chebyshev-economised into c1, c3 (max error 2.4e-18 against 3.8e-17 for plain degree 4) */
-    0x1.5555555555555p-5,   /* [3] 1/24 */
-    0x1.555557e54fd55p-3,   /* [4] c3 = 1/6 + h^2/96 */
-    /* the same polynomial in r = u/L, L = ln2/256, r in [-1/2, 1/2] */
-    0x1.62e42fefa39b9p-9,   /* [5] c1 L */
-    0x1.ebfbdff82c58fp-19,  /* [6] L^2/2 */
-    0x1.c6b090da1e082p-29,  /* [7] c3 L^3 */
-    0x1.3b2ab6fba4e77p-39,  /* [8] L^4/24 */
-    0x1.fffffffffffb1p-1};  /* [9] c1 = 1 - h^4/384 */
+    0x1.71547652b82fep+11,  /* [0] 2048/ln2 */
+    -0x1.62e42fec00000p-12, /* [1] -ln2/2048, high part (22 trailing zero bits: k*hi is exact) */
+    -0x1.d1cf79abc9e3bp-43, /* [2] -ln2/2048, low part */
+    /* (e^u - 1)/u = a0 + a1 u + a2 u^2 on |u| <= ln2/4096, interpolated at the Chebyshev nodes */
+    0x1.5555555b7bae9p-3,   /* [3] a2 */
+    0x1.00000007afef8p-1,   /* [4] a1 */
+    /* the same polynomial in r = u/L, L = ln2/2048, r in [-1/2, 1/2] */
+    0x1.62e42fefa39efp-12,  /* [5] a0 L */
+    0x1.ebfbe006f2598p-25,  /* [6] a1 L^2 */
+    0x1.c6b08d787b3bfp-38,  /* [7] a2 L^3 */
+    0.0,                    /* [8] unused */
+    1.0};                   /* [9] a0 */
 
 /* [5] and [6] again as macros: the host writes them into the kernel parameters (mcmcb_ctx::exp_c1/c2) */
-#define MCMCB_EXP_C1L 0x1.62e42fefa39b9p-9
-#define MCMCB_EXP_C2L 0x1.ebfbdff82c58fp-19
+#define MCMCB_EXP_C1L 0x1.ebfbe006f2598p-25 /* a1 L^2 */
+#define MCMCB_EXP_C2L 0x1.c6b08d787b3bfp-38 /* a2 L^3 */
 
 #define MCMCB_EXP_MAGIC 6755399441055744.0 /* 1.5 * 2^52: rounds to integer, k in the low word */
 
-/* 2^(k/256) * (1 + s) from the reduced pieces.  Three integer instructions: mask, address, and
- * ONE multiply-add for the exponent: table entry j is stored with j*2^12 subtracted from its high
- * word, so that adding k*2^12 = m*2^20 + j*2^12 to it yields the high word of 2^m * 2^(j/256)
- * without isolating m.  `tl` is the shared-window address of the thread's own column of the
- * replicated table; the load is spelled as ld.shared so that the address stays one mask and one
- * shift-add of an opaque per-thread base. */
+/* 2^(k/2048) * (1 + s) from the reduced pieces.  Three integer instructions: mask, address, and
+ * ONE multiply-add for the exponent: table entry j is stored with j*2^9 subtracted from its high
+ * word, so that adding k*2^9 = m*2^20 + j*2^9 to it yields the high word of 2^m * 2^(j/2048)
+ * without isolating m.  `tl` is the shared-window address of the table; the load is spelled as
+ * ld.shared so that the address stays one mask and one multiply-add. */
 __device__ __forceinline__ double mcmcb_exp_assemble(int k, double s, unsigned tl) {
   double tj;
   unsigned addr;
-  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(k & (MCMCB_EXP_TAB_N - 1)), "r"(tl));  /* 8 B * 16 columns */
+  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(k & (MCMCB_EXP_TAB_N - 1)), "r"(tl));
   asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));
-  const double sc = __hiloint2double(k * 4096 + __double2hiint(tj), __double2loint(tj));
+  const double sc = __hiloint2double((k << MCMCB_EXP_TAB_SHIFT) + __double2hiint(tj), __double2loint(tj));
   return fma(sc, s, sc);
 }
-/* address of this thread's column of a table staged at smem_tab (16 columns, lane mod 16) */
+/* shared-window address of a table staged at smem_tab */
 __device__ __forceinline__ unsigned mcmcb_exp_column(const double* smem_tab) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(smem_tab) + 8u * (threadIdx.x & (MCMCB_EXP_TAB_REP - 1));
-  asm volatile("" : "+r"(a));  /* opaque: keeps the compiler from folding the lane term back into every lookup */
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem_tab);
+  asm volatile("" : "+r"(a));  /* opaque: one register base for every lookup */
   return a;
 }
 
@@ -116,12 +117,11 @@ __device__ __forceinline__ double mcmcb_exp_fast(double a, unsigned tl) {
   double r = fma(t, MCMCB_EXPC[1], a);
   r = fma(t, MCMCB_EXPC[2], r);
   double q = fma(r, MCMCB_EXPC[3], MCMCB_EXPC[4]);
-  q = fma(r, q, 0.5);
   q = fma(r, q, MCMCB_EXPC[9]);
   return mcmcb_exp_assemble(k, r * q, tl);
 }
 
-/* ks for mcmcb_expmul_fast: s * 256/ln2 */
+/* ks for mcmcb_expmul_fast: s * 2048/ln2 */
 __device__ __forceinline__ double mcmcb_expmul_scale(double s) { return s * MCMCB_EXPC[0]; }
 
 /* exp(x * s), ks = mcmcb_expmul_scale(s).  The reduced argument r = x*ks - round(x*ks) is formed
@@ -132,21 +132,22 @@ __device__ __forceinline__ double mcmcb_expmul_scale(double s) { return s * MCMC
  * Operand placement matters: measured on B200 (scripts/ubench_fp64_operands.cu) a DFMA that reads
  * three DISTINCT 64-bit registers holds the FP64 pipe for 3 cycles, one that reads at most two
  * (plus a uniform-register / constant / immediate operand, or a repeated register) for 2.  The
- * Horner steps below are (r, q, constant): the constant must not be hoisted into a vector
- * register.  ptxas 12.9 keeps at most two hoisted constants per bank in uniform registers, so
- * c1, c2 arrive through the kernel-parameter bank (c[0x0], mcmcb_ctx) and c3, c4 through the
- * __constant__ bank (c[0x3]); the first step (r, c4, c3) then reads r + one register. */
+ * Horner steps below are (r, C3, C2) and (r, q, C1): an instruction takes ONE uniform operand, so C2
+ * has to sit in a vector register and C3, C1 in uniform registers.  ptxas 12.9 does that when C2
+ * (`c1` below = MCMCB_EXP_C1L = a1 L^2) arrives through the kernel-parameter bank (c[0x0], mcmcb_ctx)
+ * and C3, C1 come from the __constant__ bank (c[0x3]); other splits put two of them in vector
+ * registers and cost a cycle per step (checked in the SASS: `DFMA R, R, UR, R` then `DFMA R, R, R, UR`). */
 __device__ __forceinline__ double mcmcb_expmul_fast(double x, double ks, unsigned tl, double c1, double c2) {
   const double t = fma(x, ks, MCMCB_EXP_MAGIC);
   const int k = __double2loint(t);
   const double r = fma(x, ks, MCMCB_EXP_MAGIC - t);
-  double q = fma(r, MCMCB_EXPC[8], MCMCB_EXPC[7]);
-  q = fma(r, q, c2);
-  q = fma(r, q, c1);
+  double q = fma(r, MCMCB_EXPC[7], c1);
+  q = fma(r, q, MCMCB_EXPC[5]);
+  (void)c2;
   return mcmcb_exp_assemble(k, r * q, tl);
 }
 __device__ __forceinline__ double mcmcb_expmul_fast(double x, double ks, unsigned tl) {
-  return mcmcb_expmul_fast(x, ks, tl, MCMCB_EXPC[5], MCMCB_EXPC[6]);
+  return mcmcb_expmul_fast(x, ks, tl, MCMCB_EXPC[6], MCMCB_EXPC[7]);
 }
 
 /* true when the fast paths are valid for argument a: |a| < 708 and a is not NaN */
@@ -158,18 +159,16 @@ __device__ __forceinline__ double mcmcb_exp(double a, const mcmcb_ctx& c) {
   return exp(a);
 }
 
-/* correctly rounded 2^(j/256) (scripts/gen_exp_table.py, mpmath at 80 digits) */
+/* correctly rounded 2^(j/2048) (scripts/gen_exp_table.py, mpmath at 80 digits) */
 __device__ static const double MCMCB_EXP2_TABLE[MCMCB_EXP_TAB_N] = {
 #include "mcmcb200_exp_table.inc"
 };
 
-/* stage the replicated table; call from every thread of the CTA, then __syncthreads() */
+/* stage the table; call from every thread of the CTA, then __syncthreads() */
 __device__ __forceinline__ void mcmcb_stage_exp_table(double* smem_tab) {
-  for (int i = threadIdx.x; i < MCMCB_EXP_TAB_DOUBLES; i += blockDim.x)
-  {
-    const int j = i / MCMCB_EXP_TAB_REP;
+  for (int j = threadIdx.x; j < MCMCB_EXP_TAB_N; j += blockDim.x) {
     const double v = MCMCB_EXP2_TABLE[j];
-    smem_tab[i] = __hiloint2double(__double2hiint(v) - j * 4096, __double2loint(v));  /* see mcmcb_exp_assemble */
+    smem_tab[j] = __hiloint2double(__double2hiint(v) - (j << MCMCB_EXP_TAB_SHIFT), __double2loint(v));  /* see mcmcb_exp_assemble */
   }
 }
 
