@@ -252,6 +252,11 @@ def run_ours(args):
                                                nsimu=MCMC_PER_STEP + 1, model="expreg", lanes_per_chain=args.lanes,
                                                **NML))
     e2e_sampler.set_data(blob)
+    # results land in pinned host buffers (caller-owned, as the C ABI prescribes)
+    outs = {"par": torch.empty((N, 2), dtype=torch.float64).pin_memory(),
+            "mean": torch.empty((N, 2), dtype=torch.float64).pin_memory(),
+            "cmat": torch.empty((N, 4), dtype=torch.float64).pin_memory(),
+            "counters": torch.empty((N, 8), dtype=torch.int64).pin_memory()}
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
@@ -259,7 +264,7 @@ def run_ours(args):
         e2e_sampler.set_data(blob)                                   # H2D model data
         e2e_sampler.set_initial(par0, CMAT0, [0.5], [NDATA])         # H2D start points (pinned) + init kernel
         e2e_sampler.run(MCMC_PER_STEP, sync=False)
-        out = [e2e_sampler.fetch(w) for w in ("par", "mean", "cmat", "counters")]  # D2H results
+        out = [e2e_sampler.fetch(w, out=t.numpy()) for w, t in outs.items()]  # D2H results
         d2h = sum(o.nbytes for o in out)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
@@ -280,8 +285,13 @@ def run_ours(args):
         # hardware FP64 instruction count per datum of the compiled ssfunction loop (see DESIGN.md;
         # DFMA counted as 2 flops) -- explains the gap between algorithmic and pipe utilisation
         hw_flop_per_datum = float(os.environ.get("MCMCB_HW_FLOP_PER_DATUM", "0") or 0)
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch (2^20 chains x 100 iterations) from the
+        # committed `ncu --set full` capture profiles/r01_ncu_k1_fullsize.txt; algorithmic state traffic is
+        # 2 x 208 B x 2^20 = 436 MB, the rest is the chains' local-memory state spilling out of L1/L2
+        traffic = 738.7e6 if (N == 1 << 20 and info["lanes_per_chain"] == 1) else None
         roof = {"bound": "fp64", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": None,
+                "frac": achieved / sustained, "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_k1_fullsize.txt)",
                 "peak_source": "in-bench DFMA microbenchmark on this GPU, sustained 2 s (burst %.2f); "
                                "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks, neither bounds this kernel" % burst,
                 "algorithmic_flops_per_chain_step": fl, "stage2_rate_q": q, "accept_rate": 1 - stay,
@@ -306,7 +316,10 @@ def run_ours(args):
                            threads_per_block=info["threads_per_block"], smem_bytes=info["smem_bytes"]),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "note": "every e2e step uploads data + start points, runs the first 100 iterations of fresh chains "
+                            "(stage-2 rate ~0.88 against ~0.71 in the steady state that `value` times) and downloads "
+                            "theta/mean/cov/counters of every chain into pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

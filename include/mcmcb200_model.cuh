@@ -64,7 +64,9 @@ struct mcmcb_ctx {
  * (|a| < 708: result normal, no overflow, not NaN).
  * ------------------------------------------------------------------------------------- */
 #define MCMCB_EXP_TAB_N 2048
-#define MCMCB_EXP_TAB_REP 1
+#ifndef MCMCB_EXP_TAB_REP
+#define MCMCB_EXP_TAB_REP 1 /* copies of every entry; lane l reads copy l mod REP (fewer bank conflicts, more shared memory) */
+#endif
 #define MCMCB_EXP_TAB_DOUBLES (MCMCB_EXP_TAB_N * MCMCB_EXP_TAB_REP)
 #define MCMCB_EXP_TAB_SHIFT 9 /* 2^20 / MCMCB_EXP_TAB_N: k << 9 puts m = k >> 11 at the exponent field */
 
@@ -98,14 +100,14 @@ __constant__ double MCMCB_EXPC[10] = {
 __device__ __forceinline__ double mcmcb_exp_assemble(int k, double s, unsigned tl) {
   double tj;
   unsigned addr;
-  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(k & (MCMCB_EXP_TAB_N - 1)), "r"(tl));
+  asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(addr) : "r"(k & (MCMCB_EXP_TAB_N - 1)), "r"(tl), "n"(8 * MCMCB_EXP_TAB_REP));
   asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));
   const double sc = __hiloint2double((k << MCMCB_EXP_TAB_SHIFT) + __double2hiint(tj), __double2loint(tj));
   return fma(sc, s, sc);
 }
 /* shared-window address of a table staged at smem_tab */
 __device__ __forceinline__ unsigned mcmcb_exp_column(const double* smem_tab) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(smem_tab);
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem_tab) + 8u * (threadIdx.x & (MCMCB_EXP_TAB_REP - 1));
   asm volatile("" : "+r"(a));  /* opaque: one register base for every lookup */
   return a;
 }
@@ -166,9 +168,10 @@ __device__ static const double MCMCB_EXP2_TABLE[MCMCB_EXP_TAB_N] = {
 
 /* stage the table; call from every thread of the CTA, then __syncthreads() */
 __device__ __forceinline__ void mcmcb_stage_exp_table(double* smem_tab) {
-  for (int j = threadIdx.x; j < MCMCB_EXP_TAB_N; j += blockDim.x) {
+  for (int i = threadIdx.x; i < MCMCB_EXP_TAB_DOUBLES; i += blockDim.x) {
+    const int j = i / MCMCB_EXP_TAB_REP;
     const double v = MCMCB_EXP2_TABLE[j];
-    smem_tab[j] = __hiloint2double(__double2hiint(v) - (j << MCMCB_EXP_TAB_SHIFT), __double2loint(v));  /* see mcmcb_exp_assemble */
+    smem_tab[i] = __hiloint2double(__double2hiint(v) - (j << MCMCB_EXP_TAB_SHIFT), __double2loint(v));  /* see mcmcb_exp_assemble */
   }
 }
 

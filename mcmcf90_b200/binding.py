@@ -187,22 +187,30 @@ class Sampler:
     def sync(self):
         self._chk(self.L.mcmcb_sync(self.h), "mcmcb_sync")
 
-    def fetch(self, what):
+    def fetch(self, what, out=None):
+        """Per-chain state, chain-major.  `out` (optional) is a C-contiguous array of the right size to
+        receive the copy -- pass a view of pinned host memory to get an asynchronous-speed transfer."""
         d, m, N = self.npar, self.nycol, self.nchains
         if what == "counters":
-            out = np.zeros((N, 8), dtype=np.int64)
+            shape, dt = (N, 8), np.int64
         else:
             width = {"par": d, "ss": m, "sspri": 1, "sigma2": m, "mean": d, "wsum": 1, "qcovstd": d,
                      "cmat": d * d, "R": d * d, "R2": d * d, "iC": d * d}[what]
-            out = np.zeros((N, width))
+            shape, dt = (N, width), np.float64
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        else:
+            if out.dtype != dt or out.size != shape[0] * shape[1] or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous %s array of %d elements" % (dt.__name__, shape[0] * shape[1]))
+            out = out.reshape(shape)
         self._chk(self.L.mcmcb_fetch(self.h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes),
                   "mcmcb_fetch(%s)" % what)
         if what in ("cmat", "R", "R2", "iC"):
             out = out.reshape(N, d, d).transpose(0, 2, 1)  # column-major -> [chain, i, j]
         return out
 
-    def counters(self):
-        c = self.fetch("counters")
+    def counters(self, out=None):
+        c = self.fetch("counters", out=out)
         return {k: c[:, i] for i, k in enumerate(COUNTER_NAMES)}
 
     def fetch_chain(self, chain):

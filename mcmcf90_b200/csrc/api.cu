@@ -59,24 +59,62 @@ static int fetch_fields(mcmcb_handle h, int f0, int nf, std::vector<double>& buf
   return 0;
 }
 
+// SoA state -> the chain-major host layouts of mcmcb_fetch, transposed on the device so that the
+// device->host copy is one contiguous transfer straight into the caller's buffer (pinned or not)
+__global__ void k1_gather_fields_kernel(const double* st, long long pitch, long long n, int f0, int width, double* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const long long c = t / width;
+  const int k = (int)(t - c * width);
+  out[t] = st[(size_t)(f0 + k) * pitch + c];
+}
+// packed upper triangle (column-packed) -> full D x D column-major per chain; sym mirrors, else zero below
+__global__ void k1_gather_tri_kernel(const double* st, long long pitch, long long n, int f0, int D, int sym, double* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * D * D) return;
+  const long long c = t / (D * D);
+  const int e = (int)(t - c * D * D), j = e / D, i = e - j * D;
+  double v = 0.0;
+  if (i <= j) v = st[(size_t)(f0 + j * (j + 1) / 2 + i) * pitch + c];
+  else if (sym) v = st[(size_t)(f0 + i * (i + 1) / 2 + j) * pitch + c];
+  out[t] = v;
+}
+__global__ void k1_gather_counters_kernel(const int* ist, long long pitch, long long n, K1Layout Lo, long long* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+#pragma unroll
+  for (int k = 0; k < 7; k++) out[c * 8 + k] = ist[(size_t)src[k] * pitch + c];
+  const unsigned lo = (unsigned)ist[(size_t)Lo.i_ndlo * pitch + c], hi = (unsigned)ist[(size_t)Lo.i_ndhi * pitch + c];
+  out[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+}
+
+static int fetch_stage(mcmcb_handle h, size_t bytes) {
+  if (h->fetch_bytes >= bytes) return 0;
+  if (h->d_fetch) cudaFree(h->d_fetch);
+  h->d_fetch = nullptr;
+  h->fetch_bytes = 0;
+  CK(cudaMalloc(&h->d_fetch, bytes));
+  h->fetch_bytes = bytes;
+  return 0;
+}
+
 static int k1_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
   const long long N = h->cfg.nchains;
-  const int D = h->npar, NY = h->nycol, T = D * (D + 1) / 2;
+  const int D = h->npar, NY = h->nycol;
   const K1Layout Lo = k1_layout(D, NY);
   std::string w(what);
-  std::vector<double> buf;
+  const int threads = 256;
   if (w == "counters") {
-    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
-    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
-    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    const size_t bytes = sizeof(long long) * 8 * (size_t)N;
+    if (out_bytes < bytes) return MCMCB_EINVAL;
+    int rc = fetch_stage(h, bytes);
+    if (rc) return rc;
+    k1_gather_counters_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->d_ist, h->pitch, N, Lo, (long long*)h->d_fetch);
+    h->launches++;
+    CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    long long* o = (long long*)out;
-    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
-    for (long long c = 0; c < N; c++) {
-      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
-      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
-      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
-    }
     return MCMCB_OK;
   }
   int f0 = -1, width = 0;
@@ -92,27 +130,22 @@ static int k1_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
   else if (w == "R2") { f0 = Lo.r2; tri = true; }
   else if (w == "iC") { f0 = Lo.ic; tri = true; }
   else return MCMCB_EINVAL;
-  double* o = (double*)out;
-  if (!tri) {
-    if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
-    int rc = fetch_fields(h, f0, width, buf);
-    if (rc) return rc;
-    for (int k = 0; k < width; k++)
-      for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
-  } else {
-    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
-    int rc = fetch_fields(h, f0, T, buf);
-    if (rc) return rc;
-    const bool sym = (w == "cmat" || w == "iC");
-    for (long long c = 0; c < N; c++)
-      for (int j = 0; j < D; j++)
-        for (int i = 0; i < D; i++) {
-          double v = 0.0;
-          if (i <= j) v = buf[(size_t)(j * (j + 1) / 2 + i) * h->pitch + c];
-          else if (sym) v = buf[(size_t)(i * (i + 1) / 2 + j) * h->pitch + c];
-          o[(size_t)c * D * D + (size_t)j * D + i] = v;  // column-major
-        }
-  }
+  const size_t per = tri ? (size_t)D * D : (size_t)width;
+  const size_t bytes = sizeof(double) * per * (size_t)N;
+  if (out_bytes < bytes) return MCMCB_EINVAL;
+  int rc = fetch_stage(h, bytes);
+  if (rc) return rc;
+  const long long total = (long long)per * N;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (tri)
+    k1_gather_tri_kernel<<<blocks, threads, 0, h->stream>>>(h->d_st, h->pitch, N, f0, D, (w == "cmat" || w == "iC") ? 1 : 0,
+                                                            (double*)h->d_fetch);
+  else
+    k1_gather_fields_kernel<<<blocks, threads, 0, h->stream>>>(h->d_st, h->pitch, N, f0, width, (double*)h->d_fetch);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return MCMCB_OK;
 }
 
@@ -751,7 +784,8 @@ static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
                   h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
-                  h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial};
+                  h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial,
+                  h->d_fetch};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& s : h->dump_slots) {
@@ -779,9 +813,9 @@ extern "C" const char* mcmcb_last_error(mcmcb_handle h) { return h ? h->err.c_st
 extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
   if (!h || !blob || n == 0) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
-  if (h->d_blob) { cudaFree(h->d_blob); h->d_blob = nullptr; }
   size_t bytes = ((n * sizeof(double) + 15) / 16) * 16;
-  CK(cudaMalloc(&h->d_blob, bytes));
+  if (h->d_blob && bytes != h->blob_bytes) { cudaFree(h->d_blob); h->d_blob = nullptr; }
+  if (!h->d_blob) CK(cudaMalloc(&h->d_blob, bytes));
   CK(cudaMemsetAsync(h->d_blob, 0, bytes, h->stream));
   CK(cudaMemcpyAsync(h->d_blob, blob, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1201,7 +1235,7 @@ extern "C" int mcmcb_dfma_peak(int device, double* tflops, double* ms_out) {
 
 // ------------------------------------------------------------------ exp self-test (accuracy evidence)
 __global__ void exp_selftest_kernel(const double* a, double sc, double* out_fast, double* out_mul, long long n) {
-  __shared__ double tab[MCMCB_EXP_TAB_DOUBLES];
+  extern __shared__ double tab[];  // MCMCB_EXP_TAB_DOUBLES
   mcmcb_stage_exp_table(tab);
   __syncthreads();
   const unsigned tl = mcmcb_exp_column(tab);
@@ -1221,7 +1255,9 @@ extern "C" int mcmcb_exp_selftest(int device, const double* a, double scale, dou
   if (e == cudaSuccess) e = cudaMalloc(&d2, 8 * n);
   if (e == cudaSuccess) e = cudaMemcpy(da, a, 8 * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    exp_selftest_kernel<<<296, 256>>>(da, scale, d1, d2, (long long)n);
+    const int tab_bytes = MCMCB_EXP_TAB_DOUBLES * sizeof(double);
+    cudaFuncSetAttribute(exp_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tab_bytes);
+    exp_selftest_kernel<<<296, 256, tab_bytes>>>(da, scale, d1, d2, (long long)n);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out_fast, d1, 8 * n, cudaMemcpyDeviceToHost);

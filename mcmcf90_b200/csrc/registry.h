@@ -80,6 +80,8 @@ struct mcmcb_handle_s {
   double *d_diag = nullptr, *d_diag_buf = nullptr, *d_diag_partial = nullptr;
   long long diag_n = 0;
   int diag_K = 0;
+  void* d_fetch = nullptr;  // device staging of mcmcb_fetch (chain-major transposition happens on the device)
+  size_t fetch_bytes = 0;
   std::vector<double> h_tmp;
   std::vector<mcmcb::DumpSlot> dump_slots;
   std::deque<int> dump_fifo;
