@@ -86,6 +86,11 @@ typedef struct mcmcb_config {
 
 typedef struct mcmcb_handle_s* mcmcb_handle;
 
+/* Load a user-model plugin (a shared library built against include/mcmcb200_plugin.cuh): its models
+ * register themselves by name -- the run-time form of the reference's link-time override of ssfunction /
+ * priorfun / checkbounds (external_inc.h:4-28).  Returns MCMCB_ENOMODEL when the library cannot be loaded. */
+int mcmcb_load_plugin(const char* path);
+
 /* namelist defaults, mcmcinit.F90:184-230 (MCMC_init_namelist) */
 int mcmcb_default_config(mcmcb_config* cfg);
 /* sanity rules + derived flags, mcmcinit.F90:235-368 (check_mcmcinit_parameters) */

@@ -17,7 +17,7 @@ EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_
            "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
            "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
            "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak", "mcmcb_exp_selftest",
-           "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset"]
+           "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset", "mcmcb_load_plugin"]
 
 # int fn(void* user, double* device_buf, size_t n, void* cuda_stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -88,6 +88,7 @@ def load_library():
     L.mcmcb_pool_fetch.argtypes = [C.c_void_p, dp, dp, dp]
     L.mcmcb_diagnostics.argtypes = [C.c_void_p, dp, dp, dp, dp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.mcmcb_diag_reset.argtypes = [C.c_void_p]
+    L.mcmcb_load_plugin.argtypes = [C.c_char_p]
     _LIB = L
     return L
 
@@ -105,6 +106,13 @@ def default_config(**kw):
             raise KeyError(k)
         setattr(c, k, v)
     return c
+
+
+def load_plugin(path):
+    """Load a user-model plugin library (include/mcmcb200_plugin.cuh); its models become available by name."""
+    rc = load_library().mcmcb_load_plugin(os.fspath(path).encode())
+    if rc:
+        raise MCMCBError("mcmcb_load_plugin(%s): %s" % (path, ERRORS.get(rc, rc)))
 
 
 def dfma_peak(device=0):

@@ -1,0 +1,631 @@
+// Kernel launchers of the sampling kernels, templated on the user model: everything a model needs to be
+// registered with the library (`register_model(K1<MyModel>::entry())`).  Included by api.cu for the built-in
+// models and by user plugins through include/mcmcb200_plugin.cuh -- the run-time analogue of the reference's
+// link-time override of ssfunction / priorfun / checkbounds (external_inc.h:4-28).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "diag.cuh"
+#include "k1_small.cuh"
+#include "k2_large.cuh"
+#include "k3_scam.cuh"
+#include "mcmcb200.h"
+#include "pool.cuh"
+#include "registry.h"
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                    \
+      return MCMCB_ECUDA;                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+namespace mcmcb {
+namespace launch {
+
+static int fetch_fields(mcmcb_handle h, int f0, int nf, std::vector<double>& buf) {
+  buf.resize((size_t)nf * h->pitch);
+  CK(cudaMemcpyAsync(buf.data(), h->d_st + (size_t)f0 * h->pitch, sizeof(double) * buf.size(), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// SoA state -> the chain-major host layouts of mcmcb_fetch, transposed on the device so that the
+// device->host copy is one contiguous transfer straight into the caller's buffer (pinned or not)
+static __global__ void k1_gather_fields_kernel(const double* st, long long pitch, long long n, int f0, int width, double* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const long long c = t / width;
+  const int k = (int)(t - c * width);
+  out[t] = st[(size_t)(f0 + k) * pitch + c];
+}
+// packed upper triangle (column-packed) -> full D x D column-major per chain; sym mirrors, else zero below
+static __global__ void k1_gather_tri_kernel(const double* st, long long pitch, long long n, int f0, int D, int sym, double* out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * D * D) return;
+  const long long c = t / (D * D);
+  const int e = (int)(t - c * D * D), j = e / D, i = e - j * D;
+  double v = 0.0;
+  if (i <= j) v = st[(size_t)(f0 + j * (j + 1) / 2 + i) * pitch + c];
+  else if (sym) v = st[(size_t)(f0 + i * (i + 1) / 2 + j) * pitch + c];
+  out[t] = v;
+}
+static __global__ void k1_gather_counters_kernel(const int* ist, long long pitch, long long n, K1Layout Lo, long long* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+#pragma unroll
+  for (int k = 0; k < 7; k++) out[c * 8 + k] = ist[(size_t)src[k] * pitch + c];
+  const unsigned lo = (unsigned)ist[(size_t)Lo.i_ndlo * pitch + c], hi = (unsigned)ist[(size_t)Lo.i_ndhi * pitch + c];
+  out[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+}
+
+static int fetch_stage(mcmcb_handle h, size_t bytes) {
+  if (h->fetch_bytes >= bytes) return 0;
+  if (h->d_fetch) cudaFree(h->d_fetch);
+  h->d_fetch = nullptr;
+  h->fetch_bytes = 0;
+  CK(cudaMalloc(&h->d_fetch, bytes));
+  h->fetch_bytes = bytes;
+  return 0;
+}
+
+static int k1_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
+  const long long N = h->cfg.nchains;
+  const int D = h->npar, NY = h->nycol;
+  const K1Layout Lo = k1_layout(D, NY);
+  std::string w(what);
+  const int threads = 256;
+  if (w == "counters") {
+    const size_t bytes = sizeof(long long) * 8 * (size_t)N;
+    if (out_bytes < bytes) return MCMCB_EINVAL;
+    int rc = fetch_stage(h, bytes);
+    if (rc) return rc;
+    k1_gather_counters_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, h->stream>>>(
+        h->d_ist, h->pitch, N, Lo, (long long*)h->d_fetch);
+    h->launches++;
+    CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCMCB_OK;
+  }
+  int f0 = -1, width = 0;
+  bool tri = false;
+  if (w == "par") { f0 = Lo.th; width = D; }
+  else if (w == "ss") { f0 = Lo.ss; width = NY; }
+  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
+  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
+  else if (w == "mean") { f0 = Lo.mean; width = D; }
+  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
+  else if (w == "cmat") { f0 = Lo.cm; tri = true; }
+  else if (w == "R") { f0 = Lo.r; tri = true; }
+  else if (w == "R2") { f0 = Lo.r2; tri = true; }
+  else if (w == "iC") { f0 = Lo.ic; tri = true; }
+  else return MCMCB_EINVAL;
+  const size_t per = tri ? (size_t)D * D : (size_t)width;
+  const size_t bytes = sizeof(double) * per * (size_t)N;
+  if (out_bytes < bytes) return MCMCB_EINVAL;
+  int rc = fetch_stage(h, bytes);
+  if (rc) return rc;
+  const long long total = (long long)per * N;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (tri)
+    k1_gather_tri_kernel<<<blocks, threads, 0, h->stream>>>(h->d_st, h->pitch, N, f0, D, (w == "cmat" || w == "iC") ? 1 : 0,
+                                                            (double*)h->d_fetch);
+  else
+    k1_gather_fields_kernel<<<blocks, threads, 0, h->stream>>>(h->d_st, h->pitch, N, f0, width, (double*)h->d_fetch);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MCMCB_OK;
+}
+
+// shared by K1 and K2: rows live in the common store, (chainind, cnt, simuind) in ist at the given fields
+static int store_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                             double* s2chain_out, int* nrows, int f_chainind, int f_cnt, int f_simuind) {
+  const int D = h->npar, NY = h->nycol, cap = h->cfg.nsimu;
+  int iv[3];
+  const int fld[3] = {f_chainind, f_cnt, f_simuind};
+  for (int k = 0; k < 3; k++)
+    CK(cudaMemcpyAsync(&iv[k], h->d_ist + (size_t)fld[k] * h->pitch + chain, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int rows = std::min(iv[0], cap), cnt = iv[1], simuind = iv[2];
+  if (nrows) *nrows = rows;
+  if (ld < rows || (s2chain_out && ld < simuind)) return MCMCB_EINVAL;
+  std::vector<double> r((size_t)rows * (D + NY)), cn((size_t)rows), s2((size_t)std::max(simuind, 1) * NY);
+  if (rows > 0) {
+    CK(cudaMemcpyAsync(r.data(), h->d_store_rows + (size_t)chain * cap * (D + NY), sizeof(double) * r.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cn.data(), h->d_store_cnt + (size_t)chain * cap, sizeof(double) * cn.size(), cudaMemcpyDeviceToHost,
+                       h->stream));
+  }
+  if (s2chain_out && simuind > 0)
+    CK(cudaMemcpyAsync(s2.data(), h->d_store_s2 + (size_t)chain * cap * NY, sizeof(double) * (size_t)simuind * NY,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (rows > 0) cn[rows - 1] = (double)cnt;  // the current row's count lives in the chain state
+  for (int i = 0; i < rows; i++) {
+    if (chain_out) {
+      for (int k = 0; k < D; k++) chain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + k];
+      chain_out[(size_t)D * ld + i] = cn[i];
+    }
+    if (sschain_out) {
+      for (int k = 0; k < NY; k++) sschain_out[(size_t)k * ld + i] = r[(size_t)i * (D + NY) + D + k];
+      sschain_out[(size_t)NY * ld + i] = cn[i];
+    }
+  }
+  if (s2chain_out)
+    for (int i = 0; i < simuind; i++)
+      for (int k = 0; k < NY; k++) s2chain_out[(size_t)k * ld + i] = s2[(size_t)i * NY + k];
+  return MCMCB_OK;
+}
+
+static int k1_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                          double* s2chain_out, int* nrows) {
+  const K1Layout Lo = k1_layout(h->npar, h->nycol);
+  return store_fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows, Lo.i_chainind, Lo.i_cnt,
+                           Lo.i_simuind);
+}
+
+
+template <class M>
+struct K1 {
+  static constexpr int D = M::NPAR, NY = M::NY, T = D * (D + 1) / 2;
+
+  static K1Params params(mcmcb_handle h, int nsteps) {
+    K1Params p{};
+    p.c = h->dc;
+    p.nchains = h->cfg.nchains;
+    p.pitch = h->pitch;
+    p.chain_offset = h->cfg.chain_offset;
+    p.seed = h->cfg.seed;
+    p.nsteps = nsteps;
+    p.st = h->d_st;
+    p.ist = h->d_ist;
+    p.par0 = h->d_par0;
+    p.cmat0 = h->d_cmat0;
+    p.sigma2_0 = h->d_sigma2;
+    p.nobs = h->d_nobs;
+    p.blob = h->d_blob;
+    p.blob_n = h->blob_n;
+    p.blob_bytes = (unsigned)h->blob_bytes;
+    p.prior = h->d_prior;
+    p.inj = h->d_inj;
+    p.inj_per_chain = h->inj_per_chain;
+    p.store_chains = h->store_chains;
+    p.store_rows = h->cfg.nsimu;
+    p.store_rows_p = h->d_store_rows;
+    p.store_cnt_p = h->d_store_cnt;
+    p.store_s2_p = h->d_store_s2;
+    p.tile_counter = h->d_tile;
+    p.exp_c1 = MCMCB_EXP_C1L;
+    p.exp_c2 = MCMCB_EXP_C2L;
+    return p;
+  }
+
+  static int alloc(mcmcb_handle h) {
+    constexpr K1Layout Lo = k1_layout(D, NY);
+    if (h->doscam || h->usesvd) return MCMCB_EUNSUPPORTED;  // SVD factor paths live in the warp-per-chain kernels
+    h->nf = Lo.nf;
+    h->inf = Lo.i_nf;
+    h->pitch = ((h->cfg.nchains + 31) / 32) * 32;
+    CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
+    CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
+    if (h->store_chains > 0) {
+      size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
+      CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (D + NY)));
+      CK(cudaMalloc(&h->d_store_cnt, sizeof(double) * rows));
+      CK(cudaMalloc(&h->d_store_s2, sizeof(double) * rows * NY));
+      CK(cudaMemsetAsync(h->d_store_rows, 0, sizeof(double) * rows * (D + NY), h->stream));
+      CK(cudaMemsetAsync(h->d_store_cnt, 0, sizeof(double) * rows, h->stream));
+      CK(cudaMemsetAsync(h->d_store_s2, 0, sizeof(double) * rows * NY, h->stream));
+    }
+    return 0;
+  }
+
+  static int init(mcmcb_handle h) {
+    K1Params p = params(h, 0);
+    int threads = 256;
+    long long blocks = (h->cfg.nchains + threads - 1) / threads;
+    k1_init_kernel<M><<<(unsigned)blocks, threads, 0, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <int L, bool SMEM>
+  static int launch_LS(mcmcb_handle h, const K1Params& p) {
+    auto kern = k1_step_kernel<M, L, SMEM>;
+    size_t smem = MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? h->blob_bytes : 0);
+    if (!h->attr_set) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
+      if (occ < 1) occ = 1;
+      h->occ = occ;
+      h->attr_set = true;
+    }
+    long long tiles = (h->cfg.nchains * L + 31) / 32;
+    long long wpb = K1_THREADS / 32;
+    long long need = (tiles + wpb - 1) / wpb;
+    long long blocks = std::min<long long>((long long)h->num_sms * h->occ, need);
+    if (blocks < 1) blocks = 1;
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
+    kern<<<(unsigned)blocks, K1_THREADS, smem, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <int L>
+  static int launch_L(mcmcb_handle h, const K1Params& p) {
+    if (h->smem_blob) return launch_LS<L, true>(h, p);
+    return launch_LS<L, false>(h, p);
+  }
+
+  static int step(mcmcb_handle h, int nsteps) {
+    K1Params p = params(h, nsteps);
+    switch (h->L) {
+      case 1: return launch_L<1>(h, p);
+      case 2: return launch_L<2>(h, p);
+      case 4: return launch_L<4>(h, p);
+      case 8: return launch_L<8>(h, p);
+      case 16: return launch_L<16>(h, p);
+      default: return launch_L<32>(h, p);
+    }
+  }
+
+  // pooled adaptation, pool.cuh
+  static int pool(mcmcb_handle h, int phase) {
+    K1Params p = params(h, 0);
+    if (phase == 3) {
+      const int threads = 256;
+      k1_pool_apply_kernel<D, NY><<<(unsigned)((h->cfg.nchains + threads - 1) / threads), threads, 0, h->stream>>>(p, h->d_pool);
+      h->launches++;
+    } else {
+      const int nv = phase == 1 ? 1 + D : D * D;
+      double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + D;
+      k1_pool_moments_kernel<D, NY><<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
+      pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  static ModelEntry entry() {
+    ModelEntry e{};
+    e.pool = &pool;
+    e.name = M::name();
+    e.kernel = 1;
+    e.npar = D;
+    e.ny = NY;
+    e.alloc = &alloc;
+    e.init = &init;
+    e.step = &step;
+    e.fetch = &k1_fetch;
+    e.fetch_chain = &k1_fetch_chain;
+    return e;
+  }
+};
+
+// ------------------------------------------------------------------ K2 launcher (large npar)
+static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
+  const long long N = h->cfg.nchains;
+  const int D = h->npar, NY = h->nycol, dp = h->dp;
+  const K2Layout Lo = k2_layout(NY);
+  std::string w(what);
+  if (w == "counters") {
+    if (out_bytes < sizeof(long long) * 8 * (size_t)N) return MCMCB_EINVAL;
+    std::vector<int> ib((size_t)Lo.i_nf * h->pitch);
+    CK(cudaMemcpyAsync(ib.data(), h->d_ist, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long* o = (long long*)out;
+    const int src[7] = {Lo.i_stayed, Lo.i_bnd, Lo.i_dracc, Lo.i_drtry, Lo.i_chainind, Lo.i_simuind, Lo.i_status};
+    for (long long c = 0; c < N; c++) {
+      for (int k = 0; k < 7; k++) o[c * 8 + k] = ib[(size_t)src[k] * h->pitch + c];
+      unsigned lo = (unsigned)ib[(size_t)Lo.i_ndlo * h->pitch + c], hi = (unsigned)ib[(size_t)Lo.i_ndhi * h->pitch + c];
+      o[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
+    }
+    return MCMCB_OK;
+  }
+  double* o = (double*)out;
+  std::vector<double> buf;
+  if (w == "par" || w == "mean" || w == "qcovstd") {
+    if (out_bytes < sizeof(double) * (size_t)D * N) return MCMCB_EINVAL;
+    buf.resize((size_t)N * dp);
+    const bool shared = (w == "qcovstd") && h->q_stride == 0;
+    CK(cudaMemcpyAsync(buf.data(), w == "par" ? h->d_theta : (w == "mean" ? h->d_mean : h->d_qstd),
+                       sizeof(double) * (shared ? (size_t)dp : buf.size()), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (shared)
+      for (long long c = 1; c < N; c++) std::copy(buf.begin(), buf.begin() + dp, buf.begin() + (size_t)c * dp);
+    for (long long c = 0; c < N; c++)
+      for (int k = 0; k < D; k++) o[(size_t)c * D + k] = buf[(size_t)c * dp + k];
+    return MCMCB_OK;
+  }
+  if (w == "R2" && h->factor_mode != FACTOR_CHOL) return MCMCB_EINVAL;
+  if (w == "cmat" || w == "R" || w == "R2") {
+    if (out_bytes < sizeof(double) * (size_t)D * D * N) return MCMCB_EINVAL;
+    buf.resize((size_t)N * D * D);
+    const bool shared = (w != "cmat") && h->r_stride == 0;  // pooled adaptation: one factor for every chain
+    CK(cudaMemcpyAsync(buf.data(), w == "cmat" ? h->d_cmat : h->d_Rm, sizeof(double) * (shared ? (size_t)D * D : buf.size()),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (shared)
+      for (long long c = 1; c < N; c++) std::copy(buf.begin(), buf.begin() + (size_t)D * D, buf.begin() + (size_t)c * D * D);
+    const double sc = (w == "R2") ? 1.0 / h->dc.drscale : 1.0;
+    for (long long c = 0; c < N; c++)
+      for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+          // cmat is symmetric; the factor is stored row-major: element (i,j) at i*D+j -> column-major output
+          double v = (w == "R" && h->factor_mode != FACTOR_CHOL) ? buf[(size_t)c * D * D + (size_t)j * D + i]  // SVD factor: column-major
+                                                                 : buf[(size_t)c * D * D + (size_t)i * D + j];
+          o[(size_t)c * D * D + (size_t)j * D + i] = (w == "cmat") ? v : v * sc;
+        }
+    return MCMCB_OK;
+  }
+  int f0 = -1, width = 0;
+  if (w == "ss") { f0 = Lo.ss; width = NY; }
+  else if (w == "sspri") { f0 = Lo.pri; width = 1; }
+  else if (w == "sigma2") { f0 = Lo.s2; width = NY; }
+  else if (w == "wsum") { f0 = Lo.wsum; width = 1; }
+  else return MCMCB_EINVAL;  // "iC" is never formed by this kernel (matrix-free DR ratio)
+  if (out_bytes < sizeof(double) * (size_t)width * N) return MCMCB_EINVAL;
+  int rc = fetch_fields(h, f0, width, buf);
+  if (rc) return rc;
+  for (int k = 0; k < width; k++)
+    for (long long c = 0; c < N; c++) o[(size_t)c * width + k] = buf[(size_t)k * h->pitch + c];
+  return MCMCB_OK;
+}
+
+static int k2_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
+                          double* s2chain_out, int* nrows) {
+  const K2Layout Lo = k2_layout(h->nycol);
+  return store_fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows, Lo.i_chainind, Lo.i_cnt,
+                           Lo.i_simuind);
+}
+
+template <class M>
+struct K2 {
+  static constexpr int NY = M::NY;
+
+  static K2Params params(mcmcb_handle h, int nsteps) {
+    K2Params p{};
+    p.c = h->dc;
+    p.nchains = h->cfg.nchains;
+    p.pitch = h->pitch;
+    p.chain_offset = h->cfg.chain_offset;
+    p.seed = h->cfg.seed;
+    p.nsteps = nsteps;
+    p.d = h->npar;
+    p.dp = h->dp;
+    p.st = h->d_st;
+    p.ist = h->d_ist;
+    p.theta = h->d_theta;
+    p.mean = h->d_mean;
+    p.Rm = h->d_Rm;
+    p.cmat = h->d_cmat;
+    p.rowbuf = h->d_rowbuf;
+    p.rowcap = h->rowcap;
+    p.par0 = h->d_par0;
+    p.cmat0 = h->d_cmat0_full;
+    p.sigma2_0 = h->d_sigma2;
+    p.nobs = h->d_nobs;
+    p.blob = h->d_blob;
+    p.blob_n = h->blob_n;
+    p.blob_bytes = (unsigned)h->blob_bytes;
+    p.prior = h->d_prior;
+    p.inj = h->d_inj;
+    p.inj_per_chain = h->inj_per_chain;
+    p.store_chains = h->store_chains;
+    p.store_rows = h->cfg.nsimu;
+    p.store_rows_p = h->d_store_rows;
+    p.store_cnt_p = h->d_store_cnt;
+    p.store_s2_p = h->d_store_s2;
+    p.tile_counter = h->d_tile;
+    p.tick_i = 0;
+    p.qstd = h->d_qstd;
+    p.factor_mode = h->factor_mode;
+    p.r_stride = h->r_stride;
+    p.q_stride = h->q_stride;
+    p.r_resident = h->r_resident ? 1 : 0;
+    return p;
+  }
+
+  static int alloc(mcmcb_handle h) {
+    static_assert(NY == 1, "the large-npar kernel supports nycol = 1");
+    const K2Layout Lo = k2_layout(NY);
+    const int d = h->npar;
+    if (d > 32 * K2_MAXM) return MCMCB_EUNSUPPORTED;
+    const long long N = h->cfg.nchains;
+    const mcmcb_config& c = h->cfg;
+    h->factor_mode = h->doscam ? FACTOR_SCAM : (h->usesvd ? FACTOR_SVD : FACTOR_CHOL);
+    // the SVD square root is a general matrix: no rank-1 Cholesky updates (RAM) on it, and the reference's
+    // second-stage ratio with usesvd inverts its upper triangle as if it were a Cholesky factor
+    // (MCMC_adapt.F90:216-219) -- not reproduced
+    if (h->factor_mode == FACTOR_SVD && (h->cfg.method == MCMCB_RAM || h->dodr)) return MCMCB_EUNSUPPORTED;
+    h->nf = Lo.nf;
+    h->inf = Lo.i_nf;
+    h->pitch = ((N + 31) / 32) * 32;
+    h->dp = ((d + 31) / 32) * 32;
+    h->rowcap = c.burnintime + 2 * std::max(c.adaptint, 1) + c.adapthist + 2;
+    if (c.method == MCMCB_RAM || !c.doadapt) h->rowcap = 1;
+    CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
+    CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
+    CK(cudaMalloc(&h->d_theta, sizeof(double) * (size_t)N * h->dp));
+    CK(cudaMalloc(&h->d_mean, sizeof(double) * (size_t)N * h->dp));
+    // pooled adaptation: every chain proposes from ONE shared factor (stride 0) -- except RAM, whose chains
+    // keep private factors between the averaging ticks
+    const bool shared_factor = c.pool_adapt && c.method != MCMCB_RAM;
+    h->r_stride = shared_factor ? 0 : (long long)d * d;
+    h->q_stride = shared_factor ? 0 : h->dp;
+    const size_t NR = shared_factor ? 1 : (size_t)N;
+    CK(cudaMalloc(&h->d_Rm, sizeof(double) * NR * d * d));
+    CK(cudaMalloc(&h->d_cmat, sizeof(double) * (size_t)N * d * d));
+    CK(cudaMalloc(&h->d_scratch, sizeof(double) * NR * d * d * (h->factor_mode == FACTOR_CHOL ? 1 : 2)));
+    CK(cudaMalloc(&h->d_qstd, sizeof(double) * NR * h->dp));
+    CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * NR * h->dp, h->stream));
+    CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * (h->rowcap + 1) * (d + 1)));
+    if (h->store_chains > 0) {
+      size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
+      CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (d + NY)));
+      CK(cudaMalloc(&h->d_store_cnt, sizeof(double) * rows));
+      CK(cudaMalloc(&h->d_store_s2, sizeof(double) * rows * NY));
+      CK(cudaMemsetAsync(h->d_store_rows, 0, sizeof(double) * rows * (d + NY), h->stream));
+      CK(cudaMemsetAsync(h->d_store_cnt, 0, sizeof(double) * rows, h->stream));
+      CK(cudaMemsetAsync(h->d_store_s2, 0, sizeof(double) * rows * NY, h->stream));
+    }
+    return 0;
+  }
+
+  static int init(mcmcb_handle h) {
+    K2Params p = params(h, 0);
+    k2_init_kernel<M><<<(unsigned)h->cfg.nchains, 128, 0, h->stream>>>(p);
+    const unsigned nfac = h->r_stride == 0 ? 1u : (unsigned)h->cfg.nchains;  // shared factor: chain 0's cmat == cmat0
+    if (h->factor_mode == FACTOR_CHOL)
+      k2_initR_kernel<<<nfac, K2_ADAPT_THREADS, 0, h->stream>>>(p, h->d_scratch);
+    else
+      k3_initR_kernel<<<nfac, K2_ADAPT_THREADS, sizeof(double) * 2 * h->npar, h->stream>>>(p, h->d_scratch,
+                                                                                            h->factor_mode);
+    h->launches += 2;
+    h->k2_i = 1;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  template <bool SMEM>
+  static int launch_step(mcmcb_handle h, const K2Params& p) {
+    auto kern = (h->factor_mode == FACTOR_SCAM) ? k3_scam_step_kernel<M, SMEM> : k2_step_kernel<M, SMEM>;
+    const int W = h->k2_warps;
+    size_t smem = sizeof(double) * (size_t)W * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0) +
+                  (h->r_resident ? sizeof(double) * (size_t)W * h->npar * h->npar : 0);
+    if (!h->attr_set) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
+      h->occ = std::max(occ, 1);
+      h->attr_set = true;
+    }
+    long long need = (h->cfg.nchains + W - 1) / W;
+    long long blocks = std::max<long long>(1, std::min<long long>((long long)h->num_sms * h->occ, need));
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
+    kern<<<(unsigned)blocks, W * 32, smem, h->stream>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  static bool is_tick(const mcmcb_config& c, long long i) {
+    if (c.method == MCMCB_RAM) return false;
+    if (!c.doadapt && !c.doburnin) return false;
+    if (c.adaptend > 0 && i > c.adaptend) return false;
+    const bool ta = c.adaptint > 0 && i % c.adaptint == 0, tb = c.badaptint > 0 && i % c.badaptint == 0;
+    return ta || tb;
+  }
+
+  static int step(mcmcb_handle h, int nsteps) {
+    const mcmcb_config& c = h->cfg;
+    // the blob shares shared memory with the per-warp vectors
+    // shared-memory plan: K2_MAX_WARPS warps per CTA (latency hiding: these kernels are issue/latency bound),
+    // the model blob beside the per-warp vectors when it fits.  RAM rewrites its factor every step, so for RAM
+    // a per-warp resident copy of the factor comes first, with as many warps as still fit.
+    const size_t d2 = sizeof(double) * (size_t)h->npar * h->npar, vec1 = sizeof(double) * (size_t)K2_NVEC * h->dp;
+    const bool ram = c.method == MCMCB_RAM && c.doadapt;
+    int W = K2_MAX_WARPS;
+    bool resident = false, smem_blob = false;
+    const char* force = getenv("MCMCB_K2_RESIDENT");  // tuning experiments only
+    if (h->factor_mode != FACTOR_SCAM && (ram || (force && force[0] == '1')) && !(force && force[0] == '0')) {
+      int w = (int)std::min<size_t>(K2_MAX_WARPS, (h->max_smem - 1024) / (vec1 + d2));
+      if (w >= 4) { resident = true; W = w; }
+    }
+    const size_t used = (size_t)W * (vec1 + (resident ? d2 : 0));
+    if (used + 1024 > h->max_smem) W = (int)std::max<size_t>(1, (h->max_smem - 1024) / vec1);
+    smem_blob = (size_t)W * (vec1 + (resident ? d2 : 0)) + h->blob_bytes + 1024 <= h->max_smem;
+    if (!smem_blob && !resident && W > 8 && (size_t)8 * vec1 + h->blob_bytes + 1024 <= h->max_smem) {
+      W = 8;  // a blob in shared memory beats the extra warps
+      smem_blob = true;
+    }
+    if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
+    int left = nsteps;
+    bool first = true;
+    while (left > 0 || first) {
+      first = false;
+      int seg = left;
+      for (int k = 1; k <= left; k++)
+        if (is_tick(c, h->k2_i + k)) { seg = k; break; }
+      K2Params p = params(h, seg);
+      int rc = smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p);
+      if (rc) return rc;
+      h->k2_i += seg;
+      left -= seg;
+      if (seg > 0 && is_tick(c, h->k2_i)) {
+        p.tick_i = (int)h->k2_i;
+        if (h->factor_mode == FACTOR_CHOL)
+          k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
+                            sizeof(double) * absorb_smem_doubles(h->rowcap, h->npar), h->stream>>>(p, h->d_scratch);
+        else
+          k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
+                            sizeof(double) * (2 * h->npar + absorb_smem_doubles(h->rowcap, h->npar)), h->stream>>>(
+              p, h->d_scratch, h->factor_mode);
+        h->launches++;
+        CK(cudaGetLastError());
+      }
+    }
+    return 0;
+  }
+
+  // pooled adaptation, pool.cuh
+  static int pool(mcmcb_handle h, int phase) {
+    K2Params p = params(h, 0);
+    const int d = h->npar;
+    if (phase == 3) {
+      k2_pool_factor_kernel<<<1, K2_ADAPT_THREADS, sizeof(double) * 3 * d, h->stream>>>(p, h->d_pool, h->d_scratch,
+                                                                                       h->d_Rpool, h->d_fail);
+      if (h->cfg.method == MCMCB_RAM)
+        k2_pool_broadcast_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(p, h->d_Rpool, h->d_fail);
+      const K2Layout Lo = k2_layout(NY);
+      pool_flag_kernel<<<h->num_sms, 256, 0, h->stream>>>(h->d_ist + (size_t)Lo.i_status * h->pitch, h->pitch,
+                                                          h->cfg.nchains, h->d_fail);
+      h->launches += 3;
+    } else {
+      const int nv = phase == 1 ? 1 + d : d * d;
+      double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + d;
+      k2_pool_moments_kernel<<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
+      pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      h->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  static ModelEntry entry() {
+    ModelEntry e{};
+    e.pool = &pool;
+    e.name = M::name();
+    e.kernel = 2;
+    e.npar = 0;
+    e.ny = NY;
+    e.alloc = &alloc;
+    e.init = &init;
+    e.step = &step;
+    e.fetch = &k2_fetch;
+    e.fetch_chain = &k2_fetch_chain;
+    return e;
+  }
+};
+
+}  // namespace launch
+}  // namespace mcmcb
