@@ -284,7 +284,8 @@ def run_ours(args):
         info = s.info()
         # hardware FP64 instruction count per datum of the compiled ssfunction loop (see DESIGN.md;
         # DFMA counted as 2 flops) -- explains the gap between algorithmic and pipe utilisation
-        hw_flop_per_datum = float(os.environ.get("MCMCB_HW_FLOP_PER_DATUM", "0") or 0)
+        # 9 FP64 instructions per datum in the SASS of the datum loop (7 DFMA + 1 DMUL + 1 DADD, profiles/r01_summary.md G)
+        hw_flop_per_datum = float(os.environ.get("MCMCB_HW_FLOP_PER_DATUM", "16") or 0)
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch (2^20 chains x 100 iterations) from the
         # committed `ncu --set full` capture profiles/r01_ncu_k1_fullsize.txt; algorithmic state traffic is
         # 2 x 208 B x 2^20 = 436 MB, the rest is the chains' local-memory state spilling out of L1/L2
@@ -302,6 +303,8 @@ def run_ours(args):
             hw = roof["datum_evals_per_s"] * hw_flop_per_datum / 1e12
             roof["achieved_hw"] = hw
             roof["frac_hw"] = hw / sustained
+            roof["hw_note"] = ("FP64 flops the compiled datum loop executes (exp = 7 FP64 instructions, counted as 1 flop in "
+                               "`achieved`): %g per datum x datum_evals_per_s" % hw_flop_per_datum)
         cores = os.cpu_count() or 1
         if world == 1 and not args.no_cpu_baseline:
             cpu_v, cpu_sample = cpu_baseline(cores)
