@@ -39,6 +39,7 @@ extern "C" {
 #define MCMCB_DRAM 0
 #define MCMCB_RAM 1
 #define MCMCB_SCAM 2
+#define MCMCB_ER 3 /* early-rejection MH, MCMC_run_er.F90:12-107 (no delayed rejection) */
 
 /* rng_mode */
 #define MCMCB_RNG_PHILOX 0   /* Philox4x32-10 keyed by (seed, global chain id) -- replaces random_number */
@@ -133,7 +134,8 @@ int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out
  *  "par" (npar) "ss" (nycol) "sspri" (1) "sigma2" (nycol) "mean" (npar) "wsum" (1)
  *  "cmat" "R" "R2" "iC" (npar*npar, column-major, upper triangle authoritative)
  *  "qcovstd" (npar)
- *  "counters" (8 x int64: stayed, bndstayed, draccepted, drtries, chainind, simuind, status, ndrawn) */
+ *  "counters" (8 x int64: stayed, bndstayed, draccepted, drtries, chainind, simuind, status, ndrawn)
+ *  "erstayed" (1 x int64: steps rejected by the prior alone in method 'er', mcmc.F90:49) */
 int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes);
 
 /* streamed dumps (MCMC_dump.F90:12-30 hook): pops the oldest completed snapshot of all

@@ -5,7 +5,7 @@ this package is the thin Python binding used by tests and bench.py.  There is no
 fallback: importing the binding without the built library raises.
 """
 from .binding import (Config, Sampler, MCMCBError, load_library, library_path, default_config, dfma_peak, exp_selftest, load_plugin,
-                      DRAM, RAM, SCAM, RNG_PHILOX, RNG_INJECTED)
+                      DRAM, RAM, SCAM, ER, RNG_PHILOX, RNG_INJECTED)
 from . import models
 
 __all__ = ["Config", "Sampler", "MCMCBError", "load_library", "library_path", "default_config", "dfma_peak", "exp_selftest", "load_plugin",

@@ -7,9 +7,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-DRAM, RAM, SCAM = 0, 1, 2
+DRAM, RAM, SCAM, ER = 0, 1, 2, 3
 RNG_PHILOX, RNG_INJECTED = 0, 1
-METHODS = {"dram": DRAM, "am": DRAM, "ram": RAM, "scam": SCAM}
+METHODS = {"dram": DRAM, "am": DRAM, "ram": RAM, "scam": SCAM, "er": ER}
 ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "EUNSUPPORTED", -4: "ENOMODEL", -5: "ENOMEM"}
 COUNTER_NAMES = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "simuind", "status", "ndrawn"]
 
@@ -201,6 +201,8 @@ class Sampler:
         d, m, N = self.npar, self.nycol, self.nchains
         if what == "counters":
             shape, dt = (N, 8), np.int64
+        elif what == "erstayed":
+            shape, dt = (N,), np.int64
         else:
             width = {"par": d, "ss": m, "sspri": 1, "sigma2": m, "mean": d, "wsum": 1, "qcovstd": d,
                      "cmat": d * d, "R": d * d, "R2": d * d, "iC": d * d}[what]

@@ -46,14 +46,8 @@ int register_model(const ModelEntry& e) {
 namespace {
 using namespace mcmcb::launch;
 
-struct BuiltinRegistrar {
-  BuiltinRegistrar() {
-    register_model(K1<ExpReg>::entry());
-    register_model(K2<GaussN>::entry());
-    register_model(K2<BananaN>::entry());
-    register_model(K2<HierN>::entry());
-  }
-} builtin_registrar;
+// the built-in models register themselves from their own translation units (builtin_*.cu), exactly like a
+// user plugin does (include/mcmcb200_plugin.cuh)
 
 const ModelEntry* find_model(const char* name, int kernel) {
   for (auto& e : registry())
@@ -143,6 +137,8 @@ extern "C" int mcmcb_check_config(mcmcb_config* c, int* dodr, int* doscam, int* 
     c->drscale = 0.0;
   }
   if (c->method == MCMCB_RAM) c->drscale = 0.0;
+  if (c->method == MCMCB_ER) c->drscale = 0.0;  // "no dr with er", MCMC_run_er.F90:24-27
+  if (c->method < MCMCB_DRAM || c->method > MCMCB_ER) return MCMCB_EINVAL;
   if (dodr) *dodr = c->drscale > 0.0;
   if (doscam) *doscam = sc;
   if (usesvd) *usesvd = c->condmax > 0.0;
@@ -158,9 +154,12 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (rc) { delete h; return rc; }
   const mcmcb_config& c = h->cfg;
   // configurations that need the stored row history of the reference (AP)
-  if (c.method != MCMCB_RAM && (c.adapthist > 1 || (c.greedy && c.doburnin)) ) { delete h; return MCMCB_EUNSUPPORTED; }
   h->model = find_model(c.model, c.kernel);
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
+  // AP windows and greedy burn-in (the configurations that walk the stored row history in the reference,
+  // MCMC_adapt.F90:83-101,116-136) are built in the register kernel only
+  if (h->model->kernel != 1 && c.method != MCMCB_RAM && ((c.adapthist > 1 && c.doadapt) || (c.greedy && c.doburnin))) { delete h; return MCMCB_EUNSUPPORTED; }
+  if (c.pool_adapt && (c.adapthist > 1 || c.method == MCMCB_ER)) { delete h; return MCMCB_EUNSUPPORTED; }
   // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
   if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }
   // pooled adaptation replaces the chains' own factor updates at the AM ticks; the burn-in scaling branch
@@ -191,7 +190,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
-                  h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
+                  h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_hist, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
                   h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
                   h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial,
                   h->d_fetch};

@@ -24,7 +24,7 @@ __device__ __forceinline__ size_t diag_f(const DiagParams& p, int field, long lo
 }
 
 // one thread per (chain, component); e = c * d + k
-__global__ void diag_update_kernel(DiagParams p) {
+static __global__ void diag_update_kernel(DiagParams p) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.nchains * p.d) return;
   const long long c = e / p.d;
@@ -58,7 +58,7 @@ __global__ void diag_update_kernel(DiagParams p) {
 // grid (B, d): component k = blockIdx.y.  phase 1: partial = [count, sum_c mean_c];
 // phase 2 (mu_k = buf[1 + k] / buf[0]): [sum_c (mean_c - mu)^2, sum_c s2_c, sum_c acov_{t,c} (t = 1..K)].
 // partial layout: [k][b][nv]
-__global__ void __launch_bounds__(POOL_THREADS) diag_reduce_kernel(DiagParams p, int phase, const double* buf,
+static __global__ void __launch_bounds__(POOL_THREADS) diag_reduce_kernel(DiagParams p, int phase, const double* buf,
                                                                   double* partial) {
   __shared__ double red[POOL_THREADS / 32];
   const int k = blockIdx.y, K = p.K;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(POOL_THREADS) diag_reduce_kernel(DiagParams p,
 }
 
 // out layout phase 1: [0] = chains, [1 + k] = sum of chain means;  phase 2: [k * (2 + K) + v]
-__global__ void diag_final_kernel(const double* partial, int nblocks, int nv, int d, int phase, double* out) {
+static __global__ void diag_final_kernel(const double* partial, int nblocks, int nv, int d, int phase, double* out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d * nv) return;
   const int k = idx / nv, v = idx - k * nv;

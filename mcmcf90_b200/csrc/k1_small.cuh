@@ -31,9 +31,9 @@ constexpr int K1_THREADS = MCMCB_K1_THREADS;
 
 // field offsets of the SoA state (doubles and ints), shared by host and device
 struct K1Layout {
-  int th, ss, pri, s2, r, r2, ic, cm, mean, wsum, spare, rama, nf;
+  int th, ss, pri, s2, r, r2, ic, cm, mean, wsum, spare, rama, gcm, gmean, gw, nf;
   int i_stayed, i_bnd, i_dracc, i_drtry, i_chainind, i_simuind, i_status, i_hasspare, i_cnt, i_pend, i_ndlo, i_ndhi,
-      i_nf;
+      i_er, i_nf;
 };
 __host__ __device__ constexpr K1Layout k1_layout(int D, int NY) {
   K1Layout l{};
@@ -51,10 +51,14 @@ __host__ __device__ constexpr K1Layout k1_layout(int D, int NY) {
   l.wsum = o; o += 1;
   l.spare = o; o += 1;
   l.rama = o; o += 1;
+  l.gcm = o; o += T;      // greedy burn-in: unit-weight covariance of every row so far (MCMC_adapt.F90:83-101)
+  l.gmean = o; o += D;
+  l.gw = o; o += 1;
   l.nf = o;
   int k = 0;
   l.i_stayed = k++; l.i_bnd = k++; l.i_dracc = k++; l.i_drtry = k++; l.i_chainind = k++; l.i_simuind = k++;
   l.i_status = k++; l.i_hasspare = k++; l.i_cnt = k++; l.i_pend = k++; l.i_ndlo = k++; l.i_ndhi = k++;
+  l.i_er = k++;  // erstayed, mcmc.F90:49
   l.i_nf = k;
   return l;
 }
@@ -82,6 +86,10 @@ struct K1Params {
   double* store_cnt_p;      // [chain][row]
   double* store_s2_p;       // [chain][step][NY]
   unsigned int* tile_counter;
+  // AP window (adapthist > 1, MCMC_adapt.F90:116-136): ring of the last hist_rows closed run-length rows,
+  // [slot][D+1][pitch] (theta then repeat count), slot = (row index - 1) mod hist_rows
+  double* hist;
+  int hist_rows;
   double exp_c1, exp_c2;    // MCMCB_EXP_C1L / C2L: see mcmcb_expmul_fast for why they travel as parameters
 };
 
@@ -338,6 +346,11 @@ __global__ void k1_init_kernel(K1Params p) {
   st[Lo.spare * p.pitch] = 0.0;
   st[Lo.rama * p.pitch] = 0.0;
 #pragma unroll
+  for (int k = 0; k < T; k++) st[(Lo.gcm + k) * p.pitch] = cm[k];
+#pragma unroll
+  for (int k = 0; k < D; k++) st[(Lo.gmean + k) * p.pitch] = p.par0[c * D + k];
+  st[Lo.gw * p.pitch] = (double)p.c.initcmatn;
+#pragma unroll
   for (int k = 0; k < Lo.i_nf; k++) ist[k * p.pitch] = 0;
   if (!ok) ist[Lo.i_status * p.pitch] = MCMCB_ST_CHOLFAIL;
 }
@@ -351,8 +364,10 @@ struct K1State {
   static constexpr int T = D * (D + 1) / 2;
   double th[D], ss1[NY], s2[NY], R[T], R2[T], iC[T], cm[T], mean[D];
   double pri1, wsum, rama;
+  double gcm[T], gmean[D], gw;              // greedy burn-in accumulators (unit row weights)
   double y1[D], z1[D], ss2[NY], pri2, a12;  // first-stage proposal kept for DR / RAM
-  int stayed, bnd, dracc, drtry, chainind, simuind, status, cnt, pend;
+  double sscrit;                            // method 'er': critical value of this proposal (MCMC_DRAM.F90:124-135)
+  int stayed, bnd, dracc, drtry, chainind, simuind, status, cnt, pend, er;
   int phase, done;
   bool valid, stored;
   long long cc;
@@ -375,6 +390,14 @@ __device__ __forceinline__ void k1_load_state(K1State<M::NPAR, M::NY>& S, const 
     S.iC[k] = st[(Lo.ic + k) * p.pitch]; S.cm[k] = st[(Lo.cm + k) * p.pitch];
   }
   S.pri1 = st[Lo.pri * p.pitch]; S.wsum = st[Lo.wsum * p.pitch]; S.rama = st[Lo.rama * p.pitch];
+  if (p.c.greedy) {
+#pragma unroll
+    for (int k = 0; k < T; k++) S.gcm[k] = st[(Lo.gcm + k) * p.pitch];
+#pragma unroll
+    for (int k = 0; k < D; k++) S.gmean[k] = st[(Lo.gmean + k) * p.pitch];
+    S.gw = st[Lo.gw * p.pitch];
+  }
+  S.er = ist[Lo.i_er * p.pitch]; S.sscrit = 0.0;
   S.stayed = ist[Lo.i_stayed * p.pitch]; S.bnd = ist[Lo.i_bnd * p.pitch]; S.dracc = ist[Lo.i_dracc * p.pitch];
   S.drtry = ist[Lo.i_drtry * p.pitch]; S.chainind = ist[Lo.i_chainind * p.pitch];
   S.simuind = ist[Lo.i_simuind * p.pitch]; S.status = ist[Lo.i_status * p.pitch];
@@ -415,6 +438,14 @@ __device__ __forceinline__ void k1_store_state(const K1State<M::NPAR, M::NY>& S,
   }
   st[Lo.pri * p.pitch] = S.pri1; st[Lo.wsum * p.pitch] = S.wsum; st[Lo.rama * p.pitch] = S.rama;
   st[Lo.spare * p.pitch] = S.g.spare;
+  if (p.c.greedy) {
+#pragma unroll
+    for (int k = 0; k < T; k++) st[(Lo.gcm + k) * p.pitch] = S.gcm[k];
+#pragma unroll
+    for (int k = 0; k < D; k++) st[(Lo.gmean + k) * p.pitch] = S.gmean[k];
+    st[Lo.gw * p.pitch] = S.gw;
+  }
+  ist[Lo.i_er * p.pitch] = S.er;
   ist[Lo.i_stayed * p.pitch] = S.stayed; ist[Lo.i_bnd * p.pitch] = S.bnd; ist[Lo.i_dracc * p.pitch] = S.dracc;
   ist[Lo.i_drtry * p.pitch] = S.drtry; ist[Lo.i_chainind * p.pitch] = S.chainind;
   ist[Lo.i_simuind * p.pitch] = S.simuind; ist[Lo.i_status * p.pitch] = S.status;
@@ -427,8 +458,8 @@ __device__ __forceinline__ void k1_store_state(const K1State<M::NPAR, M::NY>& S,
 // Next proposal of this chain (cold, divergent): theta + R'z, MCMC_DRAM.F90:20-31, with the
 // first- or second-stage factor.  Returns the bounds verdict (MCMC_DRAM.F90:37-46).
 template <class M>
-__device__ __noinline__ bool k1_prepare(K1State<M::NPAR, M::NY>* Sp, double* prop_out, const mcmcb_ctx* ctx) {
-  constexpr int D = M::NPAR;
+__device__ __noinline__ bool k1_prepare(K1State<M::NPAR, M::NY>* Sp, double* prop_out, const mcmcb_ctx* ctx, int method) {
+  constexpr int D = M::NPAR, NY = M::NY;
   K1State<M::NPAR, M::NY>& S = *Sp;
   double prop[D];
   if (S.phase < 0) {
@@ -453,7 +484,15 @@ __device__ __noinline__ bool k1_prepare(K1State<M::NPAR, M::NY>* Sp, double* pro
   }
 #pragma unroll
   for (int k = 0; k < D; k++) prop_out[k] = prop[k];
-  return M::checkbounds(prop, D, *ctx);
+  const bool inb = M::checkbounds(prop, D, *ctx);
+  if (method == MCMCB_ER && inb) {  // MCMC_sscrit, MCMC_DRAM.F90:124-135: the uniform is drawn for every in-bounds proposal
+    const double u = S.g.uniform();
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NY; k++) sum += S.ss1[k] / S.s2[k];
+    S.sscrit = -2.0 * log(u) + sum + S.pri1;
+  }
+  return inb;
 }
 
 // Accept / reject and, at the end of a step, everything MCMC_run.F90:93-105 does after it
@@ -482,6 +521,7 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
     for (int k = 0; k < NY; k++) S.ss1[k] = ssn[k];
     S.pri1 = prn;
     S.chainind = 1; S.simuind = 1; S.cnt = 1; S.pend = 1;
+    if (c.greedy && c.doburnin) absorb<D>(S.th, 1.0, S.gcm, S.gmean, S.gw);
     if (stored) {
 #pragma unroll
       for (int k = 0; k < D; k++) srow[k] = S.th[k];
@@ -491,7 +531,21 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
     S.phase = 0;
     return;
   }
-  if (S.phase == 0) {  // MCMC_run.F90:46-59
+  if (c.method == MCMCB_ER) {  // MCMC_run_er.F90:50-83
+    if (!inb) {
+      S.bnd++;
+      reject = true;
+    } else if (prn >= S.sscrit) {  // rejected by the prior alone
+      S.er++;
+      reject = true;
+    } else {
+      const double crit = S.s2[0] * (S.sscrit - prn);  // "problem here if nycol > 1", MCMC_run_er.F90:70-71
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < NY; k++) sum += ssn[k];
+      reject = sum >= crit;
+    }
+  } else if (S.phase == 0) {  // MCMC_run.F90:46-59
     if (!inb) {
       if (!c.dodr || c.method == MCMCB_RAM) S.bnd++;
 #pragma unroll
@@ -549,13 +603,19 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
   // ---------------- end of one MCMC_LOOP iteration, MCMC_run.F90:93-105
   const int i = S.simuind + 1;
   S.simuind = i;
-  const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
+  const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend) && c.adapthist <= 1;
   if (reject) {
     S.stayed++;
     S.cnt++; S.pend++;
   } else {
     if (absorbing) absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
     if (stored && S.chainind - 1 < p.store_rows) scnt[S.chainind - 1] = (double)S.cnt;
+    if (p.hist != nullptr) {  // the closing row joins the AP window ring
+      double* hr = p.hist + ((size_t)((S.chainind - 1) % p.hist_rows) * (D + 1)) * p.pitch + S.cc;
+#pragma unroll
+      for (int k = 0; k < D; k++) hr[(size_t)k * p.pitch] = S.th[k];
+      hr[(size_t)D * p.pitch] = (double)S.cnt;
+    }
 #pragma unroll
     for (int k = 0; k < D; k++) S.th[k] = prop[k];
 #pragma unroll
@@ -563,6 +623,8 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
     S.pri1 = prn;
     S.chainind++;
     S.cnt = 1; S.pend = 1;
+    // greedy burn-in: covmat over ALL rows with unit weights (MCMC_adapt.F90:88-93) == every row fed once, when it opens
+    if (c.greedy && c.doburnin && i < c.burnintime) absorb<D>(S.th, 1.0, S.gcm, S.gmean, S.gw);
   }
   if (c.updatesigma) {  // MCMC_updatesigma2, MCMC_DRAM.F90:192-206
 #pragma unroll
@@ -622,6 +684,31 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
             S.R[k] = S.R[k] * c.scalefactor;
             if (c.dodr) { S.R2[k] = S.R2[k] * c.scalefactor; S.iC[k] = S.iC[k] / c.scalefactor / c.scalefactor; }
           }
+        } else if (c.greedy) {
+          // MCMC_adapt.F90:83-102: chaincmat = covariance of rows 1..chainind with unit weights on top of
+          // (cmat0, par0, initcmatn) -- the greedy accumulators hold exactly that; lastfreq = count of the
+          // open row, lastind = chainind; then MCMC_calculate_R(chaincmat)
+          if (!calculate_R<D>(S.gcm, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
+          // What the AM branch starts from: the reference resets (chaincmat, chainmean, chainwsum) at
+          // simuind == burnintime+adaptint+adapthist (MCMC_adapt.F90:108-114) -- only if that step is a tick --
+          // and then feeds rows lastind..chainind; otherwise it carries on from the greedy covariance.
+          const int t0 = c.burnintime + c.adaptint + c.adapthist;
+          const bool will_reset = c.doadapt && ((c.adaptint > 0 && t0 % c.adaptint == 0) || (c.badaptint > 0 && t0 % c.badaptint == 0)) &&
+                                  !(c.adaptend > 0 && t0 > c.adaptend);
+          if (will_reset) {
+#pragma unroll
+            for (int k = 0; k < T; k++) S.cm[k] = p.cmat0[k];
+#pragma unroll
+            for (int k = 0; k < D; k++) S.mean[k] = p.par0[S.cc * D + k];
+            S.wsum = (double)c.initcmatn;
+          } else {
+#pragma unroll
+            for (int k = 0; k < T; k++) S.cm[k] = S.gcm[k];
+#pragma unroll
+            for (int k = 0; k < D; k++) S.mean[k] = S.gmean[k];
+            S.wsum = S.gw;
+          }
+          S.pend = 0;  // lastfreq = current count: only later repeats of the open row count
         } else {
           // lastind = chainind (MCMC_adapt.F90:102): rows before the current one never enter the
           // covariance, the current row enters with its full count (lastfreq stays 0); then
@@ -636,7 +723,55 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
           if (!calculate_R<D>(c0, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
         }
       } else if (i >= c.burnintime + c.adaptint + c.adapthist && c.doadapt) {  // MCMC_adapt.F90:105-159
-        absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
+        if (c.adapthist > 1) {
+          // AP (MCMC_adapt.F90:116-136): covariance of the last adapthist steps, batch formula of covmat
+          // (matutils.F90:312-337) over the run-length rows istart..chainind, first weight trimmed
+          const int H = p.hist_rows;
+          const double* hb = p.hist + S.cc;
+          int istart = S.chainind, histsum = S.cnt;
+          while (histsum < c.adapthist && istart > 1) {
+            istart--;
+            histsum += (int)hb[((size_t)((istart - 1) % H) * (D + 1) + D) * p.pitch];
+          }
+          const int nrow = S.chainind - istart + 1;
+          double wsum2 = 0.0, xs[D], xm[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) xs[k] = 0.0;
+          for (int r = 0; r < nrow; r++) {
+            const int row = istart + r;
+            const double* hr = hb + ((size_t)((row - 1) % H) * (D + 1)) * p.pitch;
+            double w = (row == S.chainind) ? (double)S.cnt : hr[(size_t)D * p.pitch];
+            if (r == 0) w = (double)((int)w - histsum + c.adapthist);
+            wsum2 += w;
+#pragma unroll
+            for (int k = 0; k < D; k++) xs[k] = xs[k] + ((row == S.chainind) ? S.th[k] : hr[(size_t)k * p.pitch]) * w;
+          }
+#pragma unroll
+          for (int k = 0; k < D; k++) xm[k] = xs[k] / wsum2;
+          double acc[T];
+#pragma unroll
+          for (int k = 0; k < T; k++) acc[k] = 0.0;
+          for (int r = 0; r < nrow; r++) {
+            const int row = istart + r;
+            const double* hr = hb + ((size_t)((row - 1) % H) * (D + 1)) * p.pitch;
+            double w = (row == S.chainind) ? (double)S.cnt : hr[(size_t)D * p.pitch];
+            if (r == 0) w = (double)((int)w - histsum + c.adapthist);
+            double dv[D];
+#pragma unroll
+            for (int k = 0; k < D; k++) dv[k] = ((row == S.chainind) ? S.th[k] : hr[(size_t)k * p.pitch]) - xm[k];
+#pragma unroll
+            for (int b = 0; b < D; b++)
+#pragma unroll
+              for (int a = 0; a <= b; a++) acc[pk(a, b)] = acc[pk(a, b)] + dv[b] * (dv[a] * w);  // cmat(i,j), j<=i: (x_i-m_i)*((x_j-m_j)*w)
+          }
+#pragma unroll
+          for (int k = 0; k < T; k++) S.cm[k] = acc[k] / (wsum2 - 1.0);
+#pragma unroll
+          for (int k = 0; k < D; k++) S.mean[k] = xm[k];
+          S.wsum = wsum2;
+        } else {
+          absorb<D>(S.th, (double)S.pend, S.cm, S.mean, S.wsum);
+        }
         S.pend = 0;
         // pooled adaptation: the factor comes from the covariance pooled over all chains (pool.cuh)
         if (!c.pool && !calculate_R<D>(S.cm, S.R, S.R2, S.iC, c)) S.status |= MCMCB_ST_CHOLFAIL;
@@ -647,7 +782,17 @@ __device__ __noinline__ void k1_finish(K1State<M::NPAR, M::NY>* Sp, const K1Para
   S.done++;
 }
 
-template <class M, int L, bool SMEM>
+// does the model supply the early-rejection form of its ssfunction (ssfunction_er, external_inc.h:20-24)?
+template <class M, class = void>
+struct has_ssfunction_er { static constexpr bool value = false; };
+template <class M>
+struct has_ssfunction_er<M, decltype((void)&M::ssfunction_er)> { static constexpr bool value = true; };
+
+// EREXIT: method 'er' with a model that has ssfunction_er -- every lane hands the model its critical value and
+// the warp leaves the data loop as soon as every lane's partial sum has reached it (the GPU form of the
+// reference's "stop summing once ss >= sscrit").  A rejected proposal's ss is never used, an accepted one's
+// loop ran to the end, so chains are identical with and without the early exit.
+template <class M, int L, bool SMEM, bool EREXIT = false>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_constant__ K1Params p) {
   constexpr int D = M::NPAR, NY = M::NY;
   constexpr int CPW = 32 / L;
@@ -689,11 +834,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
       const bool act = S.valid && (S.phase < 0 || S.done < p.nsteps);
       if (!__any_sync(FULL, act)) break;
       bool inb = true;
-      if (act) inb = k1_prepare<M>(&S, prop, &ctx);
+      if (act) inb = k1_prepare<M>(&S, prop, &ctx, p.c.method);
       __syncwarp();
       // ---------------- user model: the hot, warp-converged section
       double ssn[NY];
-      M::ssfunction(prop, D, NY, ctx, ssn);
+      if constexpr (EREXIT) {
+        double crit = -DBL_HUGE;  // lanes whose ss nobody reads vote "done" at once
+        if (act) {
+          if (S.phase < 0) {
+            crit = DBL_HUGE;  // initial point: the full sum is needed
+          } else if (inb) {
+            const double pr = M::priorfun(prop, D, ctx);
+            if (pr < S.sscrit) crit = S.s2[0] * (S.sscrit - pr);
+          }
+        }
+        M::ssfunction_er(prop, D, NY, ctx, crit, ssn);
+      } else {
+        M::ssfunction(prop, D, NY, ctx, ssn);
+      }
       if (L > 1) {
 #pragma unroll
         for (int k = 0; k < NY; k++) {

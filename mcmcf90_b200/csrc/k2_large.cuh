@@ -203,7 +203,7 @@ __device__ __forceinline__ double tri_matvec_col(const double* R, const double* 
 
 // not inlined: the pipelined loops get their own register allocation instead of competing with the step
 // kernel's long-lived state (the call happens once per proposal)
-__device__ __noinline__ void tri_matvec_t(const double* R, const double* vs, int d, int lane,
+static __device__ __noinline__ void tri_matvec_t(const double* R, const double* vs, int d, int lane,
                                           double (&acc)[K2_MAXM]) {
   const int mm = (d + 31) >> 5;
 #pragma unroll
@@ -295,7 +295,7 @@ __device__ __forceinline__ bool cta_calculate_R(const double* cm, double* Rm, do
 }
 
 // Initial factor, MCMC_init.F90:108-110.  One CTA per chain; tmp = that chain's slice of a scratch buffer.
-__global__ void k2_initR_kernel(K2Params p, double* scratch) {
+static __global__ void k2_initR_kernel(K2Params p, double* scratch) {
   __shared__ double red[K2_ADAPT_THREADS / 32];
   const long long c = blockIdx.x;
   const int d = p.d;
@@ -406,7 +406,7 @@ __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* c
 }
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
-__global__ void k2_adapt_kernel(K2Params p, double* scratch) {
+static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   extern __shared__ double sh[];  // absorb_smem_doubles(rowcap, d)
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);

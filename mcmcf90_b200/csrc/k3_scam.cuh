@@ -168,7 +168,7 @@ __device__ __forceinline__ int cta_calculate_R_svd(double* cm, double* Rm, doubl
 }
 
 // Initial factor (MCMC_init.F90:108-110) for the SVD modes; one CTA per chain.
-__global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
+static __global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
   extern __shared__ double sh[];  // d doubles + d ints
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);
@@ -183,7 +183,7 @@ __global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
 }
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i for the SVD factor modes, one CTA per chain.
-__global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
+static __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
   extern __shared__ double sh[];  // d doubles + d ints (as d doubles) + absorb_smem_doubles(rowcap, d)
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);

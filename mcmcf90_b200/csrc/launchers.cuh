@@ -68,6 +68,11 @@ static __global__ void k1_gather_counters_kernel(const int* ist, long long pitch
   out[c * 8 + 7] = (long long)(((unsigned long long)hi << 32) | lo);
 }
 
+static __global__ void k1_gather_int_kernel(const int* ist, long long pitch, long long n, int field, long long* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) out[c] = ist[(size_t)field * pitch + c];
+}
+
 static int fetch_stage(mcmcb_handle h, size_t bytes) {
   if (h->fetch_bytes >= bytes) return 0;
   if (h->d_fetch) cudaFree(h->d_fetch);
@@ -91,6 +96,18 @@ static int k1_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
     if (rc) return rc;
     k1_gather_counters_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, h->stream>>>(
         h->d_ist, h->pitch, N, Lo, (long long*)h->d_fetch);
+    h->launches++;
+    CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCMCB_OK;
+  }
+  if (w == "erstayed") {  // mcmc.F90:49: steps rejected by the prior alone (method 'er'), one int64 per chain
+    const size_t bytes = sizeof(long long) * (size_t)N;
+    if (out_bytes < bytes) return MCMCB_EINVAL;
+    int rc = fetch_stage(h, bytes);
+    if (rc) return rc;
+    k1_gather_int_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, h->stream>>>(h->d_ist, h->pitch, N, Lo.i_er,
+                                                                                           (long long*)h->d_fetch);
     h->launches++;
     CK(cudaMemcpyAsync(out, h->d_fetch, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -206,6 +223,8 @@ struct K1 {
     p.store_cnt_p = h->d_store_cnt;
     p.store_s2_p = h->d_store_s2;
     p.tile_counter = h->d_tile;
+    p.hist = h->d_hist;
+    p.hist_rows = h->hist_rows;
     p.exp_c1 = MCMCB_EXP_C1L;
     p.exp_c2 = MCMCB_EXP_C2L;
     return p;
@@ -219,6 +238,11 @@ struct K1 {
     h->pitch = ((h->cfg.nchains + 31) / 32) * 32;
     CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
     CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
+    if (h->cfg.method != MCMCB_RAM && h->cfg.doadapt && h->cfg.adapthist > 1) {  // AP window ring (MCMC_adapt.F90:116-136)
+      h->hist_rows = h->cfg.adapthist;
+      CK(cudaMalloc(&h->d_hist, sizeof(double) * (size_t)h->hist_rows * (D + 1) * h->pitch));
+      CK(cudaMemsetAsync(h->d_hist, 0, sizeof(double) * (size_t)h->hist_rows * (D + 1) * h->pitch, h->stream));
+    }
     if (h->store_chains > 0) {
       size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
       CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (D + NY)));
@@ -241,9 +265,9 @@ struct K1 {
     return 0;
   }
 
-  template <int L, bool SMEM>
+  template <int L, bool SMEM, bool EREXIT = false>
   static int launch_LS(mcmcb_handle h, const K1Params& p) {
-    auto kern = k1_step_kernel<M, L, SMEM>;
+    auto kern = k1_step_kernel<M, L, SMEM, EREXIT>;
     size_t smem = MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? h->blob_bytes : 0);
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -275,6 +299,10 @@ struct K1 {
 
   static int step(mcmcb_handle h, int nsteps) {
     K1Params p = params(h, nsteps);
+    if constexpr (has_ssfunction_er<M>::value) {  // method 'er', thread per chain: warp-vote early exit of the data loop
+      if (h->cfg.method == MCMCB_ER && h->L == 1)
+        return h->smem_blob ? launch_LS<1, true, true>(h, p) : launch_LS<1, false, true>(h, p);
+    }
     switch (h->L) {
       case 1: return launch_L<1>(h, p);
       case 2: return launch_L<2>(h, p);

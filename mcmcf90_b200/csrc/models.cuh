@@ -25,6 +25,17 @@ struct ExpReg {
     return mcmcb_default_priorfun(theta, len, c);
   }
   __device__ __forceinline__ static void ssfunction(const double* theta, int, int, const mcmcb_ctx& c, double* ss) {
+    ss_impl<false>(theta, c, 0.0, ss);
+  }
+  // early-rejection form (external_inc.h:20-24, ssfunction_er(theta,npar,ny,sscrit)): the sum may stop once it has
+  // reached sscrit.  Thread-per-chain only: every 128 data the warp votes, and leaves the loop when every lane's
+  // partial sum (all terms are >= 0) has reached its own critical value.
+  __device__ __forceinline__ static void ssfunction_er(const double* theta, int, int, const mcmcb_ctx& c, double sscrit,
+                                                       double* ss) {
+    ss_impl<true>(theta, c, sscrit, ss);
+  }
+  template <bool ER>
+  __device__ __forceinline__ static void ss_impl(const double* theta, const mcmcb_ctx& c, double sscrit, double* ss) {
     const int n = (int)c.data[0];
     const int npad = (n + 1) & ~1;
     const double* __restrict__ x = c.data + 2;
@@ -39,10 +50,13 @@ struct ExpReg {
     // datum decides whether every exponent is inside mcmcb_exp_fast's range
     const bool fast = tl != 0u && fabs(nt2) * c.data[1] < 700.0;
     const double ks = mcmcb_expmul_scale(nt2);
+    // the vote is a warp-wide operation: only when every lane of the warp runs the fast loop
+    const bool vote = ER && __all_sync(0xffffffffu, fast);
     if (fast) {
       if (step == 1) {
         // one lane owns the whole chain: consecutive data, 16-byte shared loads, 8 exps in flight
         for (; i + 7 < n; i += 8) {
+          if (ER && vote && (i & 127) == 0 && __all_sync(0xffffffffu, acc >= sscrit)) { i = n; break; }
           double xv[8], yv[8];
 #pragma unroll
           for (int u = 0; u < 8; u += 2) {

@@ -39,7 +39,7 @@ __device__ __forceinline__ double pool_block_sum(double v, double* red) {
 }
 
 // partial[b][v] -> out[v] = sum_b partial[b][v], b in index order
-__global__ void pool_final_kernel(const double* partial, int nblocks, int nv, double* out) {
+static __global__ void pool_final_kernel(const double* partial, int nblocks, int nv, double* out) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * nv + v];
@@ -153,7 +153,7 @@ __global__ void k1_pool_apply_kernel(K1Params p, const double* buf) {
 
 // ------------------------------------------------------------------ K2 / K3 (run-time d, per-chain full matrices)
 // CTA b owns chains b, b + gridDim.x, ...; threads run over the output entries.
-__global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2Params p, int phase, const double* buf,
+static __global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2Params p, int phase, const double* buf,
                                                                       double* partial) {
   constexpr K2Layout Lo = k2_layout(1);
   const int d = p.d;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2Params 
 
 // One CTA: pooled covariance -> factor.  Shared factor (r_stride == 0) is written in place; for RAM the
 // new factor goes to `Rpool` and k2_pool_broadcast_kernel copies it into every chain's private factor.
-__global__ void __launch_bounds__(K2_ADAPT_THREADS) k2_pool_factor_kernel(K2Params p, double* buf, double* scratch,
+static __global__ void __launch_bounds__(K2_ADAPT_THREADS) k2_pool_factor_kernel(K2Params p, double* buf, double* scratch,
                                                                            double* Rpool, int* fail) {
   extern __shared__ double sh[];  // 2 d doubles + d ints
   __shared__ double red[K2_ADAPT_THREADS / 32];
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(K2_ADAPT_THREADS) k2_pool_factor_kernel(K2Para
   if (threadIdx.x == 0) *fail = status;
 }
 
-__global__ void k2_pool_broadcast_kernel(K2Params p, const double* Rpool, const int* fail) {
+static __global__ void k2_pool_broadcast_kernel(K2Params p, const double* Rpool, const int* fail) {
   if (*fail) return;
   const size_t n = (size_t)p.d * p.d;
   const size_t total = n * (size_t)p.nchains;
@@ -238,7 +238,7 @@ __global__ void k2_pool_broadcast_kernel(K2Params p, const double* Rpool, const 
     p.Rm[(k / n) * (size_t)p.r_stride + (k % n)] = Rpool[k % n];
 }
 
-__global__ void pool_flag_kernel(int* ist_status, long long pitch, long long nchains, const int* fail) {
+static __global__ void pool_flag_kernel(int* ist_status, long long pitch, long long nchains, const int* fail) {
   const int f = *fail;
   if (!f) return;
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nchains; c += (long long)gridDim.x * blockDim.x)

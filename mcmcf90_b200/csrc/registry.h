@@ -62,6 +62,8 @@ struct mcmcb_handle_s {
   size_t blob_n = 0, blob_bytes = 0, inj_per_chain = 0;
   int store_chains = 0;
   double *d_store_rows = nullptr, *d_store_cnt = nullptr, *d_store_s2 = nullptr;
+  double* d_hist = nullptr;  // AP window ring of the register kernel (adapthist > 1)
+  int hist_rows = 0;
   unsigned* d_tile = nullptr;
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,

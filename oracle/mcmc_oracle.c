@@ -53,6 +53,7 @@ struct orc_chain {
   double chainwsum;
   double *chain, *sschain, *s2chain;
   int stayed, bndstayed, draccepted, drtries, chainind, simuind;
+  int erstayed; /* mcmc.F90:49 */
   /* saved locals of MCMC_adapt, MCMC_adapt.F90:19 */
   int istart, istartind, lastind, lastfreq, newfreq;
   orc_rng rng;
@@ -944,6 +945,75 @@ static void run_dram(orc_chain* ch, int upto) {
   free(ss2);
 }
 
+/* MCMC_DRAM.F90:124-135: critical value of -2*log(lik); one uniform is ALWAYS drawn */
+static double mcmc_sscrit(orc_chain* ch, const double* ss1, double priss1) {
+  double u = rng_uniform(&ch->rng);
+  double sum = 0.0;
+  for (int j = 0; j < ch->nycol; j++) sum = sum + ss1[j] / ch->sigma2[j];
+  return -2.0 * log(u) + sum + priss1;
+}
+
+/* MCMC_run_er.F90:12-107 -- early-rejection MH.  The user function ssfunction_er may stop summing
+ * once its partial sum reaches sscrit; the library default (ssfunction_er0.f90) evaluates the full
+ * ssfunction, which is what this restatement does.  Delayed rejection is switched off (:24-27). */
+static void run_er(orc_chain* ch, int upto) {
+  orc_cfg* c = &ch->cfg;
+  int n = ch->npar, m = ch->nycol;
+  double* oldpar = ch->oldpar;
+  double* newpar = (double*)malloc(sizeof(double) * (size_t)n);
+  double* ss1 = ch->ss1;
+  double* ss2 = (double*)malloc(sizeof(double) * (size_t)m);
+  double sspri1 = ch->sspri1, sspri2 = 0, sscrit;
+  int reject = 0;
+  c->dodr = 0; /* :24-27 */
+  if (!ch->started) {
+    memcpy(oldpar, ch->par0, sizeof(double) * (size_t)n);
+    sspri1 = model_priorfun(&ch->model, oldpar);
+    model_ss(&ch->model, oldpar, ss1);
+    savechain(ch, oldpar, ss1, reject);
+    ch->started = 1;
+    ch->next_i = 2;
+  }
+  int i;
+  for (i = ch->next_i; i <= upto; i++) {
+    ch->simuind = i;
+    propose(ch, oldpar, ch->R, newpar, NULL);
+    int inbounds = model_checkbounds(&ch->model, newpar);
+    if (!inbounds) { /* :54-57 */
+      ch->bndstayed++;
+      reject = 1;
+    } else {
+      sscrit = mcmc_sscrit(ch, ss1, sspri1);              /* :59 */
+      sspri2 = model_priorfun(&ch->model, newpar);        /* :60 */
+      if (sspri2 >= sscrit) {                             /* :62-67 */
+        reject = 1;
+        ch->erstayed++;
+      } else {
+        sscrit = ch->sigma2[0] * (sscrit - sspri2);       /* :71, "problem here if nycol > 1" */
+        model_ss(&ch->model, newpar, ss2);                /* ssfunction_er(newpar,sscrit), default = ssfunction */
+        double sum = 0.0;
+        for (int j = 0; j < m; j++) sum = sum + ss2[j];
+        reject = (sum >= sscrit) ? 1 : 0;                 /* :74-80 */
+      }
+    }
+    if (reject) {
+      ch->stayed++;
+    } else {
+      memcpy(ss1, ss2, sizeof(double) * (size_t)m);
+      sspri1 = sspri2;
+      memcpy(oldpar, newpar, sizeof(double) * (size_t)n);
+    }
+    updatesigma2(ch, ss1);
+    savechain(ch, oldpar, ss1, reject);
+    mcmc_adapt(ch, i);
+    if (ch->rng.exhausted) { ch->status |= ORC_ST_RNG_EXHAUSTED; i++; break; }
+  }
+  ch->next_i = i;
+  ch->sspri1 = sspri1;
+  free(newpar);
+  free(ss2);
+}
+
 /* MCMC_run_ram.F90:13-83, 87-101, 104-179 */
 static void run_ram(orc_chain* ch, int upto) {
   const orc_cfg* c = &ch->cfg;
@@ -1136,6 +1206,7 @@ int orc_advance(orc_chain* ch, int upto) { /* mcmc_main.F90:29-37 */
   switch (ch->cfg.method) {
     case ORC_SCAM: run_scam(ch, upto); break;
     case ORC_RAM: run_ram(ch, upto); break;
+    case ORC_ER: run_er(ch, upto); break;
     default: run_dram(ch, upto);
   }
   return ch->status;
@@ -1184,6 +1255,7 @@ const double* orc_mean_ptr(const orc_chain* ch) { return ch->chainmean; }
 const double* orc_sigma2_ptr(const orc_chain* ch) { return ch->sigma2; }
 const double* orc_par_ptr(const orc_chain* ch) { return ch->oldpar; }
 double orc_wsum(const orc_chain* ch) { return ch->chainwsum; }
+int orc_erstayed(const orc_chain* ch) { return ch->erstayed; }
 void orc_counters(const orc_chain* ch, long* o) {
   o[0] = ch->stayed; o[1] = ch->bndstayed; o[2] = ch->draccepted; o[3] = ch->drtries;
   o[4] = ch->chainind; o[5] = ch->simuind; o[6] = ch->status; o[7] = (long)ch->rng.ndrawn;

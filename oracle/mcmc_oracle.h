@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 /* method codes (mcmc_main.F90:29-37) */
-enum { ORC_DRAM = 0, ORC_RAM = 1, ORC_SCAM = 2 };
+enum { ORC_DRAM = 0, ORC_RAM = 1, ORC_SCAM = 2, ORC_ER = 3 };
 /* built-in user models (the plugin side of external_inc.h:14-28) */
 enum { ORC_MODEL_EXPREG = 0, ORC_MODEL_GAUSS = 1, ORC_MODEL_BANANA = 2, ORC_MODEL_HIER = 3 };
 /* status bits */
@@ -82,6 +82,7 @@ const double* orc_mean_ptr(const orc_chain* ch);
 const double* orc_sigma2_ptr(const orc_chain* ch);
 const double* orc_par_ptr(const orc_chain* ch);       /* last oldpar */
 double orc_wsum(const orc_chain* ch);
+int orc_erstayed(const orc_chain* ch);               /* mcmc.F90:49, steps rejected by the prior alone in method 'er' */
 /* counters: [stayed, bndstayed, draccepted, drtries, chainind, simuind, status, ndrawn_lo] */
 void orc_counters(const orc_chain* ch, long* out8);
 

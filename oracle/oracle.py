@@ -13,9 +13,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-DRAM, RAM, SCAM = 0, 1, 2
+DRAM, RAM, SCAM, ER = 0, 1, 2, 3
 MODEL_EXPREG, MODEL_GAUSS, MODEL_BANANA, MODEL_HIER = 0, 1, 2, 3
-METHODS = {"dram": DRAM, "am": DRAM, "ram": RAM, "scam": SCAM}
+METHODS = {"dram": DRAM, "am": DRAM, "ram": RAM, "scam": SCAM, "er": ER}
 
 
 class Cfg(C.Structure):
@@ -65,6 +65,7 @@ def lib():
             f.argtypes = [C.c_void_p]
         L.orc_wsum.restype = C.c_double
         L.orc_wsum.argtypes = [C.c_void_p]
+        L.orc_erstayed.argtypes = [C.c_void_p]
         L.orc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
         L.orc_default_cfg.argtypes = [C.POINTER(Cfg)]
         L.orc_check_params.argtypes = [C.POINTER(Cfg)]
@@ -207,7 +208,9 @@ class Chain:
         out = (C.c_long * 8)()
         lib().orc_counters(self.h, out)
         k = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "simuind", "status", "ndrawn"]
-        return dict(zip(k, [int(v) for v in out]))
+        r = dict(zip(k, [int(v) for v in out]))
+        r["erstayed"] = int(lib().orc_erstayed(self.h))
+        return r
 
     def results(self):
         ns, d, m = self.cfg.nsimu, self.npar, self.nycol

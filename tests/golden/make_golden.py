@@ -18,7 +18,7 @@ from oracle import oracle as O  # noqa: E402
 from tests import cases  # noqa: E402
 
 NSIMU = 301
-SEEDS = {"shipped": 1, "dram": 2, "ram": 3, "scam": 4, "scam_hier": 5}
+SEEDS = {"shipped": 1, "dram": 2, "ram": 3, "scam": 4, "scam_hier": 5, "er": 6, "ap": 7, "greedy": 8}
 HIER_Y = np.round(np.random.default_rng(99).normal(size=(4, 1)) + np.random.default_rng(98).normal(size=(4, 3)), 3)
 CASES = {
     "shipped": dict(cases.NML_SHIPPED, nsimu=NSIMU, burnintime=150, adaptint=50),
@@ -27,6 +27,11 @@ CASES = {
     "scam": dict(method="scam", nsimu=NSIMU, adaptint=50, initcmatn=1, updatesigma=1, N0=1.0, S02=0.0),
     # SCAM on the hierarchical-means model (d = 6): the case the warp-per-chain GPU kernels are compared on
     "scam_hier": dict(method="scam", nsimu=NSIMU, adaptint=50, initcmatn=1, updatesigma=0),
+    # early-rejection sampler (MCMC_run_er.F90), AP window (adapthist > 1) and greedy burn-in (MCMC_adapt.F90:83-136)
+    "er": dict(method="er", nsimu=NSIMU, adaptint=100, initcmatn=1, updatesigma=1, N0=1.0, S02=0.0),
+    "ap": dict(cases.NML_DRAM, nsimu=NSIMU, adaptint=40, adapthist=60),
+    "greedy": dict(nsimu=NSIMU, adaptint=50, burnintime=150, doburnin=1, badaptint=25, greedy=1, scalelimit=0.05,
+                   drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.0),
 }
 
 

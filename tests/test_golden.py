@@ -41,7 +41,8 @@ def test_golden_run_lengths_are_consistent():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,rtol", [("shipped", 1e-10), ("dram", 1e-10), ("ram", 1e-9), ("scam_hier", 1e-8)])
+@pytest.mark.parametrize("name,rtol", [("shipped", 1e-10), ("dram", 1e-10), ("ram", 1e-9), ("scam_hier", 1e-8),
+                                       ("er", 1e-10), ("ap", 1e-9), ("greedy", 1e-9)])
 def test_cuda_path_reproduces_golden(name, rtol):
     model_id, blob, par0, cmat0, sigma2, nobs = G.inputs(name)
     model = {O.MODEL_EXPREG: "expreg", O.MODEL_HIER: "hier"}[model_id]
