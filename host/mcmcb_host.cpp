@@ -237,7 +237,7 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
       if (ms == "dram" || ms == "am") cfg->method = MCMCB_DRAM;  // anything that is not scam/ram/er runs MCMC_run (mcmc_main.F90:29-37)
       else if (ms == "ram") cfg->method = MCMCB_RAM;
       else if (ms == "scam") cfg->method = MCMCB_SCAM;
-      else if (ms == "er") return fail(MCMCBH_EINVAL, "method = 'er' (early rejection) has no device path");
+      else if (ms == "er") cfg->method = MCMCB_ER;  // MCMC_run_er (mcmc_main.F90:31-32)
       else cfg->method = MCMCB_DRAM;
     }
     else if (k == "alphatarget") ok = parse_double(v, cfg->alphatarget);

@@ -34,7 +34,7 @@ constexpr int K2_ADAPT_THREADS = 256;
 struct K2Layout {  // scalar SoA fields
   int ss, pri, s2, wsum, spare, rama, nf;
   int i_stayed, i_bnd, i_dracc, i_drtry, i_chainind, i_simuind, i_status, i_hasspare, i_cnt, i_pend, i_ndlo, i_ndhi,
-      i_nbuf, i_nf;
+      i_nbuf, i_er, i_nf;
 };
 __host__ __device__ constexpr K2Layout k2_layout(int NY) {
   K2Layout l{};
@@ -50,6 +50,7 @@ __host__ __device__ constexpr K2Layout k2_layout(int NY) {
   l.i_stayed = k++; l.i_bnd = k++; l.i_dracc = k++; l.i_drtry = k++; l.i_chainind = k++; l.i_simuind = k++;
   l.i_status = k++; l.i_hasspare = k++; l.i_cnt = k++; l.i_pend = k++; l.i_ndlo = k++; l.i_ndhi = k++;
   l.i_nbuf = k++;
+  l.i_er = k++;  // erstayed, mcmc.F90:49
   l.i_nf = k;
   return l;
 }
@@ -639,6 +640,8 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
     int drtry = ist[Lo.i_drtry * p.pitch], chainind = ist[Lo.i_chainind * p.pitch];
     int simuind = ist[Lo.i_simuind * p.pitch], status = ist[Lo.i_status * p.pitch];
     int cnt = ist[Lo.i_cnt * p.pitch], pend = ist[Lo.i_pend * p.pitch], nbuf = ist[Lo.i_nbuf * p.pitch];
+    int erst = ist[Lo.i_er * p.pitch];
+    double sscrit = 0.0;
     Rng g;
     g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * p.pitch] << 32) | (unsigned)ist[Lo.i_ndlo * p.pitch];
     g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
@@ -677,6 +680,13 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
         }
         __syncwarp();
         inb = M::checkbounds(prop, d, ctx);
+        if (c.method == MCMCB_ER && inb) {  // MCMC_sscrit, MCMC_DRAM.F90:124-135 (every lane keeps the same stream)
+          const double u = g.uniform();
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += ss1[k] / s2[k];
+          sscrit = -2.0 * log(u) + sum + pri1;
+        }
       }
       // ---------------- user model (cooperative over the 32 lanes)
       double ssn[NY];
@@ -701,7 +711,21 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
         phase = 0;
         continue;
       }
-      if (phase == 0) {
+      if (c.method == MCMCB_ER) {  // MCMC_run_er.F90:50-83
+        if (!inb) {
+          bnd++;
+          reject = true;
+        } else if (prn >= sscrit) {
+          erst++;
+          reject = true;
+        } else {
+          const double crit = s2[0] * (sscrit - prn);
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < NY; k++) sum += ssn[k];
+          reject = sum >= crit;
+        }
+      } else if (phase == 0) {
         if (!inb) {
           if (!c.dodr || c.method == MCMCB_RAM) bnd++;
 #pragma unroll
@@ -843,6 +867,7 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
       ist[Lo.i_simuind * p.pitch] = simuind; ist[Lo.i_status * p.pitch] = status;
       ist[Lo.i_hasspare * p.pitch] = g.has_spare ? 1 : 0;
       ist[Lo.i_cnt * p.pitch] = cnt; ist[Lo.i_pend * p.pitch] = pend; ist[Lo.i_nbuf * p.pitch] = nbuf;
+      ist[Lo.i_er * p.pitch] = erst;
       ist[Lo.i_ndlo * p.pitch] = (int)(unsigned)(g.nd & 0xffffffffull);
       ist[Lo.i_ndhi * p.pitch] = (int)(unsigned)(g.nd >> 32);
     }

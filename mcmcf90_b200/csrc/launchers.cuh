@@ -367,6 +367,14 @@ static int k2_fetch(mcmcb_handle h, const char* what, void* out, size_t out_byte
     }
     return MCMCB_OK;
   }
+  if (w == "erstayed") {
+    if (out_bytes < sizeof(long long) * (size_t)N) return MCMCB_EINVAL;
+    std::vector<int> ib((size_t)N);
+    CK(cudaMemcpyAsync(ib.data(), h->d_ist + (size_t)Lo.i_er * h->pitch, sizeof(int) * ib.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (long long c = 0; c < N; c++) ((long long*)out)[c] = ib[(size_t)c];
+    return MCMCB_OK;
+  }
   double* o = (double*)out;
   std::vector<double> buf;
   if (w == "par" || w == "mean" || w == "qcovstd") {

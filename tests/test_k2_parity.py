@@ -94,6 +94,22 @@ def test_gauss_dram_injected_counts_bit_exact(d, variant):
     s.close()
 
 
+@pytest.mark.parametrize("d", [3, 40])
+def test_gauss_early_rejection_sampler(d):
+    # method 'er' (MCMC_run_er.F90:12-107) on the warp-per-chain kernel, with a Gaussian prior so that the
+    # prior-only rejections (erstayed) occur
+    mu, lam, Sig = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    nml = dict(method="er", nsimu=500, adaptint=100, initcmatn=3, updatesigma=1, N0=4.0, S02=1.0, drscale=2.0)
+    N = 4
+    u = np.random.default_rng(100 + d).random((N, (4 * d + 40) * nml["nsimu"]))
+    par0, cmat0 = np.zeros(d), np.eye(d) * 0.5
+    s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, splits=[123, 376])
+    compare(s, nml, range(N), O.MODEL_GAUSS, blob, par0, cmat0, u=u, at_tick=True)
+    assert (s.counters()["drtries"] == 0).all()
+    s.close()
+
+
 def test_c2_shape_philox():
     # BASELINE config C2 shape: d=100 correlated Gaussian, DRAM, per-chain private factor in HBM
     d = 100

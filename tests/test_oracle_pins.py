@@ -342,3 +342,85 @@ def test_batch_runner_matches_single_chain():
         r = _chain(nml, seed=42, chain_id=10 + k)
         assert np.array_equal(out["par"][k], r["par"])
         assert out["counters"][k, 0] == r["stayed"]
+
+
+# ------------------------------------------------------------------ early-rejection sampler (MCMC_run_er.F90)
+def _er_numpy(u, nsimu, par0, cmat0, sigma2, x, y):
+    """Independent numpy restatement of MCMC_run_er.F90:12-107 without adaptation and sigma2 update:
+    polar normals (mcmcrand.F90:166-190), theta + R'z, bounds theta > 0, MCMC_sscrit (one uniform for every
+    in-bounds proposal, MCMC_DRAM.F90:124-135), flat prior, reject iff ss2 >= sigma2*(sscrit - sspri2)."""
+    pos = [0]
+    saved = []
+
+    def unif():
+        pos[0] += 1
+        return u[pos[0] - 1]
+
+    def normal():
+        if saved:
+            return saved.pop()
+        while True:
+            x1, x2 = 2.0 * unif() - 1.0, 2.0 * unif() - 1.0
+            xx = x1 * x1 + x2 * x2
+            if xx < 1.0 and xx != 0.0:
+                break
+        z = np.sqrt(-2.0 * np.log(xx) / xx)
+        saved.append(z * x1)
+        return z * x2
+
+    ssf = lambda th: float(np.sum((y - th[0] * np.exp(-th[1] * x)) ** 2))
+    R = np.linalg.cholesky(cmat0).T * 2.4 / np.sqrt(2.0)
+    th, ss1 = np.array(par0, dtype=float), ssf(par0)
+    stayed = bnd = 0
+    rows = [th.copy()]
+    for _ in range(2, nsimu + 1):
+        z = np.array([normal(), normal()])
+        new = th + R.T @ z
+        if np.any(new <= 0.0):
+            bnd += 1
+            stayed += 1
+            continue
+        sscrit = -2.0 * np.log(unif()) + ss1 / sigma2
+        ss2 = ssf(new)
+        if ss2 >= sigma2 * sscrit:
+            stayed += 1
+        else:
+            th, ss1 = new, ss2
+            rows.append(th.copy())
+    return np.array(rows), stayed, bnd, pos[0]
+
+
+def test_er_loop_against_numpy_restatement():
+    nsimu = 400
+    u = np.random.default_rng(404).random(12 * nsimu)
+    cfg = O.make_cfg(method="er", nsimu=nsimu, doadapt=0, updatesigma=0, drscale=2.0)
+    ch = O.Chain(cfg, O.MODEL_EXPREG, O.blob_expreg(cases.DATA_X, cases.DATA_Y), cases.PAR0, 0.05 * cases.CMAT0,
+                 cases.SIGMA2, cases.NOBS)
+    ch.inject(u)
+    ch.run()
+    r = ch.results()
+    rows, stayed, bnd, ndrawn = _er_numpy(u, nsimu, cases.PAR0, 0.05 * cases.CMAT0, cases.SIGMA2[0], cases.DATA_X, cases.DATA_Y)
+    assert (r["stayed"], r["bndstayed"], r["ndrawn"], r["chainind"]) == (stayed, bnd, ndrawn, len(rows))
+    assert r["drtries"] == 0 and r["erstayed"] == 0          # "no dr with er"; flat prior never rejects alone
+    np.testing.assert_allclose(r["chain"][:, :2], rows, rtol=1e-12)
+    assert 0.2 < 1.0 - stayed / (nsimu - 1) < 0.9
+
+
+def test_er_is_metropolis_hastings_in_distribution():
+    # -2 log u + ss1/s2 + pri1 > ss2/s2 + pri2  <=>  u < exp(-(ss2-ss1)/(2 s2) - (pri2-pri1)/2): the ER rule is the MH
+    # rule with the uniform drawn first, so ER and plain MH chains target the same posterior at the same acceptance rate
+    blob = O.blob_expreg(cases.DATA_X, cases.DATA_Y)
+    N, nsimu = 48, 3000
+    par0 = np.tile(cases.PAR0, (N, 1))
+    prior = None
+    out = {}
+    for m in ("er", "dram"):
+        cfg = O.make_cfg(method=m, nsimu=nsimu, adaptint=200, initcmatn=5, updatesigma=0, drscale=0.0)
+        out[m] = O.run_batch(cfg, O.MODEL_EXPREG, blob, par0, cases.CMAT0, cases.SIGMA2, cases.NOBS, seed=3, nthreads=8,
+                             moments=True)
+    acc = {m: 1.0 - out[m]["counters"][:, 0].mean() / (nsimu - 1) for m in out}
+    assert abs(acc["er"] - acc["dram"]) < 0.02, acc
+    me, md = out["er"]["chain_mean"], out["dram"]["chain_mean"]
+    se = np.sqrt(me.var(0) / N + md.var(0) / N)
+    assert np.all(np.abs(me.mean(0) - md.mean(0)) < 5 * se), (me.mean(0), md.mean(0), se)
+    del prior
