@@ -23,6 +23,10 @@
 
 using namespace mcmcb;
 
+#ifndef MCMCB_K1_DEFAULT_BATCH
+#define MCMCB_K1_DEFAULT_BATCH 4
+#endif
+
 #include "launchers.cuh"
 
 
@@ -312,6 +316,14 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   }
   h->diag_n = 0;
   h->L = (h->model->kernel == 1) ? pick_lanes(h) : 32;
+  // chains per thread of the register kernel (thread-per-chain mapping): the launcher's tile plan falls back to
+  // smaller tiles when there are too few chains to fill every warp (MCMCB_K1_BATCH overrides, tuning only)
+  h->k1_batch = 1;
+  if (h->model->kernel == 1 && h->L == 1 && h->cfg.method != MCMCB_ER) {
+    int want = MCMCB_K1_DEFAULT_BATCH;
+    if (const char* e = std::getenv("MCMCB_K1_BATCH")) want = std::atoi(e);
+    h->k1_batch = (want == 2 || want == 4) ? want : 1;
+  }
   int rc = h->model->init(h);
   if (rc) return rc;
   h->initial_set = true;

@@ -90,6 +90,7 @@ struct K1Params {
   // [slot][D+1][pitch] (theta then repeat count), slot = (row index - 1) mod hist_rows
   double* hist;
   int hist_rows;
+  long long tier[3];  // tiles of 4, 2 and 1 sub-tiles, in this order along the chain range (k1_step_kernel)
   double exp_c1, exp_c2;    // MCMCB_EXP_C1L / C2L: see mcmcb_expmul_fast for why they travel as parameters
 };
 
@@ -788,18 +789,100 @@ struct has_ssfunction_er { static constexpr bool value = false; };
 template <class M>
 struct has_ssfunction_er<M, decltype((void)&M::ssfunction_er)> { static constexpr bool value = true; };
 
+// does the model evaluate several parameter vectors in one sweep over its data (ssfunction_batch<B>)?
+template <class M, class = void>
+struct has_ssfunction_batch { static constexpr bool value = false; };
+template <class M>
+struct has_ssfunction_batch<M, decltype((void)&M::template ssfunction_batch<2>)> { static constexpr bool value = true; };
+
+// One tile: NB x (32/L) consecutive chains, NB of them per thread, advanced by p.nsteps iterations.
+//
 // EREXIT: method 'er' with a model that has ssfunction_er -- every lane hands the model its critical value and
 // the warp leaves the data loop as soon as every lane's partial sum has reached it (the GPU form of the
 // reference's "stop summing once ss >= sscrit").  A rejected proposal's ss is never used, an accepted one's
 // loop ran to the end, so chains are identical with and without the early exit.
-template <class M, int L, bool SMEM, bool EREXIT = false>
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_constant__ K1Params p) {
+//
+// NB > 1 (L == 1 only): every lane runs NB independent chain state machines and hands the model NB proposals per
+// sweep (M::ssfunction_batch<NB>): one shared-memory read of a datum then serves NB chains.  The datum loop of the
+// exponential-regression model is bound by shared-memory wavefronts (broadcast data reads + conflicting table
+// lookups), so cutting the data reads per chain-datum is what this buys.  The per-chain arithmetic
+// and its order are those of NB == 1: results are bit-identical.
+template <class M, int L, bool EREXIT, int NB>
+__device__ __forceinline__ void k1_run_tile(const K1Params& p, const mcmcb_ctx& ctx, long long first, int sub, int gl) {
   constexpr int D = M::NPAR, NY = M::NY;
-  constexpr int CPW = 32 / L;
+  K1State<D, NY> S[NB];
+  double prop[NB][D];
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const long long ch = first + b * (32 / L) + sub;  // consecutive lanes, consecutive chains
+    S[b].valid = ch < p.nchains;
+    k1_load_state<M>(S[b], p, S[b].valid ? ch : p.nchains - 1);
+    S[b].stored = S[b].valid && (ch < p.store_chains) && gl == 0;
+#pragma unroll
+    for (int k = 0; k < D; k++) prop[b][k] = S[b].th[k];
+  }
+  for (;;) {
+    bool act[NB], inb[NB], any = false;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      act[b] = S[b].valid && (S[b].phase < 0 || S[b].done < p.nsteps);
+      any = any || act[b];
+      inb[b] = true;
+    }
+    if (!__any_sync(FULL, any)) break;
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+      if (act[b]) inb[b] = k1_prepare<M>(&S[b], prop[b], &ctx, p.c.method);
+    __syncwarp();
+    // ---------------- user model: the hot, warp-converged section
+    double ssn[NB][NY];
+    if constexpr (NB > 1) {
+      M::template ssfunction_batch<NB>(&prop[0][0], D, NY, ctx, &ssn[0][0]);
+    } else if constexpr (EREXIT) {
+      double crit = -DBL_HUGE;  // lanes whose ss nobody reads vote "done" at once
+      if (act[0]) {
+        if (S[0].phase < 0) {
+          crit = DBL_HUGE;  // initial point: the full sum is needed
+        } else if (inb[0]) {
+          const double pr = M::priorfun(prop[0], D, ctx);
+          if (pr < S[0].sscrit) crit = S[0].s2[0] * (S[0].sscrit - pr);
+        }
+      }
+      M::ssfunction_er(prop[0], D, NY, ctx, crit, ssn[0]);
+    } else {
+      M::ssfunction(prop[0], D, NY, ctx, ssn[0]);
+    }
+    if (L > 1) {
+#pragma unroll
+      for (int k = 0; k < NY; k++) {
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) ssn[0][k] += __shfl_xor_sync(FULL, ssn[0][k], off);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const double prn = M::priorfun(prop[b], D, ctx);
+      if (act[b]) k1_finish<M>(&S[b], &p, prop[b], ssn[b], prn, inb[b]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; b++)
+    if (S[b].valid && gl == 0) k1_store_state<M>(S[b], p);
+  __syncwarp();
+}
+
+// Persistent CTAs; every warp pulls tiles from a global counter.  The chain range is cut into three tiers of
+// tiles holding 4, 2 and 1 sub-tiles (a sub-tile = the 32/L chains one warp owns with one chain per thread), laid
+// out by the host (K1Params::tier) so that the bulk runs B chains per thread and the last round is made of smaller
+// tiles -- with 4-sub-tile tiles alone the last round would leave most warps idle for a quarter of the launch.
+template <class M, int L, bool SMEM, bool EREXIT = false, int B = 1>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_constant__ K1Params p) {
+  static_assert(B == 1 || (L == 1 && !EREXIT), "chains-per-thread batching is for the thread-per-chain mapping");
+  constexpr int SUB = 32 / L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
 
-  // dynamic shared memory: [exp2 table, 8 KB][model blob (when it fits)]
+  // dynamic shared memory: [exp2 table, 16 KB][model blob (when it fits)]
   double* exp_tab = reinterpret_cast<double*>(smem_raw);
   mcmcb_stage_exp_table(exp_tab);
   const double* data = p.blob;
@@ -816,54 +899,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
   ctx.exp_tl = mcmcb_exp_column(exp_tab); ctx.exp_c1 = p.exp_c1; ctx.exp_c2 = p.exp_c2; ctx.scratch = nullptr;
 
-  K1State<D, NY> S;
+  const long long t4 = p.tier[0], t2 = p.tier[1], t1 = p.tier[2];
   for (;;) {
     unsigned tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
     tile = __shfl_sync(FULL, tile, 0);
-    if ((long long)tile * CPW >= p.nchains) break;
-    const long long ch = (long long)tile * CPW + sub;
-    S.valid = ch < p.nchains;
-    k1_load_state<M>(S, p, S.valid ? ch : p.nchains - 1);
-    S.stored = S.valid && (ch < p.store_chains) && gl == 0;
-
-    double prop[D];
-#pragma unroll
-    for (int k = 0; k < D; k++) prop[k] = S.th[k];
-    for (;;) {
-      const bool act = S.valid && (S.phase < 0 || S.done < p.nsteps);
-      if (!__any_sync(FULL, act)) break;
-      bool inb = true;
-      if (act) inb = k1_prepare<M>(&S, prop, &ctx, p.c.method);
-      __syncwarp();
-      // ---------------- user model: the hot, warp-converged section
-      double ssn[NY];
-      if constexpr (EREXIT) {
-        double crit = -DBL_HUGE;  // lanes whose ss nobody reads vote "done" at once
-        if (act) {
-          if (S.phase < 0) {
-            crit = DBL_HUGE;  // initial point: the full sum is needed
-          } else if (inb) {
-            const double pr = M::priorfun(prop, D, ctx);
-            if (pr < S.sscrit) crit = S.s2[0] * (S.sscrit - pr);
-          }
-        }
-        M::ssfunction_er(prop, D, NY, ctx, crit, ssn);
-      } else {
-        M::ssfunction(prop, D, NY, ctx, ssn);
-      }
-      if (L > 1) {
-#pragma unroll
-        for (int k = 0; k < NY; k++) {
-#pragma unroll
-          for (int off = L / 2; off > 0; off >>= 1) ssn[k] += __shfl_xor_sync(FULL, ssn[k], off);
-        }
-      }
-      const double prn = M::priorfun(prop, D, ctx);
-      if (act) k1_finish<M>(&S, &p, prop, ssn, prn, inb);
+    const long long t = tile;
+    if (t >= t4 + t2 + t1) break;
+    if constexpr (B >= 4) {
+      if (t < t4) { k1_run_tile<M, L, EREXIT, 4>(p, ctx, t * 4 * SUB, sub, gl); continue; }
     }
-    if (S.valid && gl == 0) k1_store_state<M>(S, p);
-    __syncwarp();
+    if constexpr (B >= 2) {
+      if (t < t4 + t2) { k1_run_tile<M, L, EREXIT, 2>(p, ctx, (t4 * 4 + (t - t4) * 2) * SUB, sub, gl); continue; }
+    }
+    k1_run_tile<M, L, EREXIT, 1>(p, ctx, (t4 * 4 + t2 * 2 + (t - t4 - t2)) * SUB, sub, gl);
   }
 }
 

@@ -265,9 +265,9 @@ struct K1 {
     return 0;
   }
 
-  template <int L, bool SMEM, bool EREXIT = false>
+  template <int L, bool SMEM, bool EREXIT = false, int B = 1>
   static int launch_LS(mcmcb_handle h, const K1Params& p) {
-    auto kern = k1_step_kernel<M, L, SMEM, EREXIT>;
+    auto kern = k1_step_kernel<M, L, SMEM, EREXIT, B>;
     size_t smem = MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? h->blob_bytes : 0);
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -277,15 +277,27 @@ struct K1 {
       h->occ = occ;
       h->attr_set = true;
     }
-    long long tiles = (h->cfg.nchains * L + 31) / 32;
-    long long wpb = K1_THREADS / 32;
-    long long need = (tiles + wpb - 1) / wpb;
+    const long long subs = (h->cfg.nchains * L + 31) / 32;  // sub-tiles: the chains one warp owns with one chain per thread
+    const long long wpb = K1_THREADS / 32;
+    const long long need = (subs + wpb - 1) / wpb;
     long long blocks = std::min<long long>((long long)h->num_sms * h->occ, need);
     if (blocks < 1) blocks = 1;
     h->blocks = (int)blocks;
     h->smem = smem;
+    // tile plan: full rounds of B-sub-tile tiles while every warp still gets one, then one last round of smaller
+    // tiles sized to what is left per warp
+    K1Params q = p;
+    const long long W = blocks * wpb;
+    long long n4 = 0, n2 = 0, n1 = 0, rem = subs;
+    if (B >= 4) { n4 = (rem / (4 * W)) * W; rem -= 4 * n4; }
+    if (B >= 4 && rem > 3 * W) { n4 += (rem + 3) / 4; rem = 0; }
+    if (B >= 4 && rem > 2 * W) { n2 = W; rem -= 2 * W; }           // 2 + 1 per warp
+    else if (B >= 2 && B < 4) { n2 = (rem / (2 * W)) * W; rem -= 2 * n2; }
+    if (B >= 2 && rem > W) { n2 += (rem + 1) / 2; rem = 0; }
+    n1 = rem;
+    q.tier[0] = n4; q.tier[1] = n2; q.tier[2] = n1;
     CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
-    kern<<<(unsigned)blocks, K1_THREADS, smem, h->stream>>>(p);
+    kern<<<(unsigned)blocks, K1_THREADS, smem, h->stream>>>(q);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -302,6 +314,10 @@ struct K1 {
     if constexpr (has_ssfunction_er<M>::value) {  // method 'er', thread per chain: warp-vote early exit of the data loop
       if (h->cfg.method == MCMCB_ER && h->L == 1)
         return h->smem_blob ? launch_LS<1, true, true>(h, p) : launch_LS<1, false, true>(h, p);
+    }
+    if constexpr (has_ssfunction_batch<M>::value) {  // thread per chain, B chains per thread (k1_step_kernel)
+      if (h->L == 1 && h->k1_batch == 2) return h->smem_blob ? launch_LS<1, true, false, 2>(h, p) : launch_LS<1, false, false, 2>(h, p);
+      if (h->L == 1 && h->k1_batch == 4) return h->smem_blob ? launch_LS<1, true, false, 4>(h, p) : launch_LS<1, false, false, 4>(h, p);
     }
     switch (h->L) {
       case 1: return launch_L<1>(h, p);

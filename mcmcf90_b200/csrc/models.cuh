@@ -34,6 +34,65 @@ struct ExpReg {
                                                        double* ss) {
     ss_impl<true>(theta, c, sscrit, ss);
   }
+  // B parameter vectors (theta[b*npar + k]) in one sweep over the data, thread per chain: every datum read from
+  // shared memory serves B chains.  Per chain the operations and their order are those of ssfunction.
+  template <int B>
+  __device__ __forceinline__ static void ssfunction_batch(const double* theta, int npar, int ny, const mcmcb_ctx& c,
+                                                          double* ss) {
+    const int n = (int)c.data[0];
+    const int npad = (n + 1) & ~1;
+    const double* __restrict__ x = c.data + 2;
+    const double* __restrict__ y = c.data + 2 + npad;
+    const unsigned tl = c.exp_tl;
+    const double c1 = c.exp_c1, c2 = c.exp_c2;
+    double t1[B], ks[B], acc[B];
+    bool fast = tl != 0u && c.nlanes == 1;
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      t1[b] = theta[b * npar];
+      const double nt2 = -theta[b * npar + 1];
+      fast = fast && fabs(nt2) * c.data[1] < 700.0;
+      ks[b] = mcmcb_expmul_scale(nt2);
+      acc[b] = 0.0;
+    }
+    if (!__all_sync(0xffffffffu, fast)) {  // rare: some exponent leaves the fast range -- one chain at a time
+#pragma unroll
+      for (int b = 0; b < B; b++) ssfunction(theta + b * npar, npar, ny, c, ss + b * NY);
+      return;
+    }
+    constexpr int U = (8 / B) < 2 ? 2 : (8 / B);  // data per trip: B*U exponentials in flight
+    int i = 0;
+    for (; i + U - 1 < n; i += U) {
+      double xv[U], yv[U], e[B][U];
+#pragma unroll
+      for (int u = 0; u < U; u += 2) {
+        const double2 xx = *reinterpret_cast<const double2*>(x + i + u);
+        const double2 yy = *reinterpret_cast<const double2*>(y + i + u);
+        xv[u] = xx.x; xv[u + 1] = xx.y; yv[u] = yy.x; yv[u + 1] = yy.y;
+      }
+#pragma unroll
+      for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int u = 0; u < U; u++) e[b][u] = mcmcb_expmul_fast(xv[u], ks[b], tl, c1, c2);
+#pragma unroll
+      for (int b = 0; b < B; b++)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const double r = fma(-t1[b], e[b][u], yv[u]);
+          acc[b] = fma(r, r, acc[b]);
+        }
+    }
+    for (; i < n; i++) {
+      const double xi = x[i], yi = y[i];
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        const double r = fma(-t1[b], mcmcb_expmul_fast(xi, ks[b], tl, c1, c2), yi);
+        acc[b] = fma(r, r, acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++) ss[b * NY] = acc[b];
+  }
   template <bool ER>
   __device__ __forceinline__ static void ss_impl(const double* theta, const mcmcb_ctx& c, double sscrit, double* ss) {
     const int n = (int)c.data[0];

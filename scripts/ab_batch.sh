@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B timing of the register kernel: library variants (scratch_libs/*.so) x chains per thread (MCMCB_K1_BATCH), C3 shape
+cp mcmcf90_b200/libmcmcb200.so /tmp/keep.so
+for f in scratch_libs/*.so; do
+  cp $f mcmcf90_b200/libmcmcb200.so
+  for b in 1 2 4; do
+    echo "== $f batch=$b"; MCMCB_K1_BATCH=$b python scripts/quick_time.py 1048576 20 2>&1 | grep "N=" | tail -1 | cut -c1-140
+  done
+done
+cp /tmp/keep.so mcmcf90_b200/libmcmcb200.so
