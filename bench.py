@@ -297,7 +297,7 @@ def run_ours(args):
                                "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks, neither bounds this kernel" % burst,
                 "algorithmic_flops_per_chain_step": fl, "stage2_rate_q": q, "accept_rate": 1 - stay,
                 "datum_evals_per_s": N * MCMC_PER_STEP * (1 + q) * NDATA / (avg_launch_ms * 1e-3),
-                "kernel": "k1_step_kernel<ExpReg,L=%d,smem>" % info["lanes_per_chain"],
+                "kernel": "k1_step_kernel<ExpReg,L=%d,smem,B=%d>" % (info["lanes_per_chain"], info["chains_per_thread"]),
                 "avg_launch_ms": avg_launch_ms, "launch_ms": launch_ms}
         if hw_flop_per_datum > 0:
             hw = roof["datum_evals_per_s"] * hw_flop_per_datum / 1e12
@@ -315,7 +315,8 @@ def run_ours(args):
             "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args), lanes_per_chain=info["lanes_per_chain"], blocks=info["blocks"],
+            "config": dict(workload_config(args), lanes_per_chain=info["lanes_per_chain"],
+                           chains_per_thread=info["chains_per_thread"], blocks=info["blocks"],
                            threads_per_block=info["threads_per_block"], smem_bytes=info["smem_bytes"]),
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),

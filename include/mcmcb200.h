@@ -173,6 +173,9 @@ void* mcmcb_stream(mcmcb_handle h);              /* cudaStream_t the kernels run
 long long mcmcb_launch_count(mcmcb_handle h);    /* kernels launched so far */
 int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes_per_chain, int* kernel, int* threads_per_block,
                int* blocks, size_t* smem_bytes);
+/* chains each thread of the register kernel runs side by side (1 when it does not apply): with B chains per thread
+ * one shared-memory read of a datum serves B chains' ssfunction */
+int mcmcb_chains_per_thread(mcmcb_handle h);
 /* FP64 pipe microbenchmark: dependent-free DFMA chains on every SM; returns measured
  * TFLOP/s (2 flop per DFMA) and the elapsed milliseconds. */
 int mcmcb_dfma_peak(int device, double* tflops, double* ms);

@@ -16,7 +16,7 @@ COUNTER_NAMES = ["stayed", "bndstayed", "draccepted", "drtries", "chainind", "si
 EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_destroy", "mcmcb_last_error",
            "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
            "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
-           "mcmcb_launch_count", "mcmcb_info", "mcmcb_dfma_peak", "mcmcb_exp_selftest",
+           "mcmcb_launch_count", "mcmcb_info", "mcmcb_chains_per_thread", "mcmcb_dfma_peak", "mcmcb_exp_selftest",
            "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset", "mcmcb_load_plugin"]
 
 # int fn(void* user, double* device_buf, size_t n, void* cuda_stream)
@@ -82,6 +82,7 @@ def load_library():
     L.mcmcb_launch_count.argtypes = [C.c_void_p]
     L.mcmcb_launch_count.restype = C.c_longlong
     L.mcmcb_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_size_t)]
+    L.mcmcb_chains_per_thread.argtypes = [C.c_void_p]
     L.mcmcb_dfma_peak.argtypes = [C.c_int, dp, dp]
     L.mcmcb_exp_selftest.argtypes = [C.c_int, dp, C.c_double, dp, dp, C.c_size_t]
     L.mcmcb_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p]
@@ -292,6 +293,7 @@ class Sampler:
         k = ["npar", "nycol", "lanes_per_chain", "kernel", "threads_per_block", "blocks"]
         r = dict(zip(k, [x.value for x in v]))
         r["smem_bytes"] = sm.value
+        r["chains_per_thread"] = int(self.L.mcmcb_chains_per_thread(self.h))
         return r
 
     def close(self):

@@ -594,6 +594,8 @@ extern "C" int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double
 // ------------------------------------------------------------------ introspection
 extern "C" void* mcmcb_stream(mcmcb_handle h) { return h ? (void*)h->stream : nullptr; }
 extern "C" long long mcmcb_launch_count(mcmcb_handle h) { return h ? h->launches : 0; }
+extern "C" int mcmcb_chains_per_thread(mcmcb_handle h) { return (h && h->model && h->model->kernel == 1) ? h->k1_batch : 1; }
+
 extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int* kernel, int* tpb, int* blocks,
                           size_t* smem) {
   if (!h) return MCMCB_EINVAL;
