@@ -334,6 +334,67 @@ extern "C" int mcmcbh_write_mat4(const char* path, const char* name, const doubl
   return bad ? fail(MCMCBH_ENOFILE, std::string("Error writing to file ") + path) : MCMCBH_OK;
 }
 
+// addtomat4_mat (matfiles.F90:187-293): append columns to the (single) matrix of an existing MAT-v4 file --
+// check the header's row count, append the new columns at the end of the file, rewrite the header with the new
+// column count.  This is how the reference's 'disk' save mode streams a long chain (MCMC_aux.F90:141-160: every
+// time its buffer fills it appends transpose(chain), i.e. one COLUMN per chain row).
+extern "C" int mcmcbh_addto_mat4(const char* path, const double* x, int rows, int cols, int ld) {
+  if (!path || !x || rows < 0 || cols < 0 || ld < rows) return fail(MCMCBH_EINVAL, "bad argument");
+  FILE* fp = std::fopen(path, "r+b");
+  if (!fp) return fail(MCMCBH_ENOFILE, std::string("Error opening file ") + path);
+  int32_t hdr[5];
+  if (std::fread(hdr, sizeof hdr, 1, fp) != 1) { std::fclose(fp); return fail(MCMCBH_EPARSE, std::string("Error reading file ") + path); }
+  if (hdr[0] != 0 || hdr[3] != 0) { std::fclose(fp); return fail(MCMCBH_EPARSE, "addtomat: not a little-endian full double matrix"); }
+  if (hdr[1] > 0 && hdr[1] != rows) {  // matfiles.F90:233-243
+    std::fclose(fp);
+    return fail(MCMCBH_EINVAL, "error: xmat should have same number of rows");
+  }
+  std::fseek(fp, 0, SEEK_END);
+  for (int j = 0; j < cols; j++) std::fwrite(x + (size_t)j * ld, sizeof(double), (size_t)rows, fp);
+  hdr[1] = rows;
+  hdr[2] += cols;
+  std::fseek(fp, 0, SEEK_SET);
+  std::fwrite(hdr, sizeof hdr, 1, fp);
+  const bool bad = std::ferror(fp);
+  std::fclose(fp);
+  return bad ? fail(MCMCBH_ENOFILE, std::string("Error writing new data to ") + path) : MCMCBH_OK;
+}
+
+// write_mcmcinit_namelist (mcmcinit.F90:147-179): group &mcmc with every variable of the namelist (character
+// values delimited by apostrophes, as the reference's delim='APOSTROPHE'), followed by the batch group &mcmcb.
+// The file reads back through mcmcbh_read_namelist (and, for &mcmc, through the reference's own reader).
+extern "C" int mcmcbh_write_namelist(const char* path, const mcmcb_config* c, const mcmcbh_files* f) {
+  if (!path || !c || !f) return fail(MCMCBH_EINVAL, "null argument");
+  FILE* fp = std::fopen(path, "w");
+  if (!fp) return fail(MCMCBH_ENOFILE, std::string("ERROR: File ") + path + " not opened for writing");
+  static const char* methods[] = {"dram", "ram", "scam", "er"};
+  const char* method = (c->method >= 0 && c->method <= 3) ? methods[c->method] : "dram";
+  std::fprintf(fp, "&mcmc\n");
+  std::fprintf(fp, " nsimu = %d,\n doadapt = %d,\n doburnin = %d,\n adaptint = %d,\n adapthist = %d,\n", c->nsimu, c->doadapt,
+               c->doburnin, c->adaptint, c->adapthist);
+  std::fprintf(fp, " scalelimit = %.17g,\n scalefactor = %.17g,\n drscale = %.17g,\n badaptint = %d,\n adaptend = %d,\n",
+               c->scalelimit, c->scalefactor, c->drscale, c->badaptint, c->adaptend);
+  std::fprintf(fp, " initcmatn = %d,\n N0 = %.17g,\n S02 = %.17g,\n filepars = %d,\n burnintime = %d,\n greedy = %d,\n",
+               c->initcmatn, c->N0, c->S02, f->filepars, c->burnintime, c->greedy);
+  std::fprintf(fp, " printint = %d,\n updatesigma = %d,\n usrfunlen = %d,\n", f->printint, c->updatesigma, f->usrfunlen);
+  std::fprintf(fp, " chainfile = '%s',\n s2file = '%s',\n ssfile = '%s',\n condmax = %.17g,\n", f->chainfile, f->s2file, f->ssfile,
+               c->condmax);
+  std::fprintf(fp, " cov0file = '%s',\n covffile = '%s',\n covnfile = '%s',\n meanfile = '%s',\n nmlffile = '%s',\n", f->cov0file,
+               f->covffile, f->covnfile, f->meanfile, f->nmlffile);
+  std::fprintf(fp, " parfile = '%s',\n parffile = '%s',\n sigma2file = '%s',\n sigma2ffile = '%s',\n", f->parfile, f->parffile,
+               f->sigma2file, f->sigma2ffile);
+  std::fprintf(fp, " dumpint = %d,\n priorsfile = '%s',\n verbosity = %d,\n method = '%s',\n alphatarget = %.17g,\n nuparam = %.17g\n/\n",
+               f->dumpint, f->priorsfile, f->verbosity, method, c->alphatarget, c->nuparam);
+  std::fprintf(fp, "&mcmcb\n nchains = %lld,\n chain_offset = %lld,\n seed = %llu,\n device = %d,\n store_chains = %d,\n", c->nchains,
+               c->chain_offset, c->seed, c->device, c->store_chains);
+  std::fprintf(fp, " lanes_per_chain = %d,\n dump_stride = %d,\n kernel = %d,\n pool_adapt = %d,\n diag_stride = %d,\n diag_lags = %d,\n",
+               c->lanes_per_chain, c->dump_stride, c->kernel, c->pool_adapt, c->diag_stride, c->diag_lags);
+  std::fprintf(fp, " model = '%s',\n datafile = '%s'\n/\n", c->model, f->datafile);
+  const bool bad = std::ferror(fp);
+  std::fclose(fp);
+  return bad ? fail(MCMCBH_ENOFILE, std::string("ERROR: Error writing parameters namelist to file ") + path) : MCMCBH_OK;
+}
+
 extern "C" int mcmcbh_write_matrix(const char* path, const char* name, const double* x, int rows, int cols, int ld) {
   const size_t n = path ? std::strlen(path) : 0;
   if (n >= 4 && std::strcmp(path + n - 4, ".mat") == 0) return mcmcbh_write_mat4(path, name, x, rows, cols, ld);

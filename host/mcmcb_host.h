@@ -51,6 +51,11 @@ void mcmcbh_free(void* p);
 int mcmcbh_write_dat(const char* path, const double* x, int rows, int cols, int ld);
 /* writemat4 (matfiles.F90:66-126): MATLAB Level 1.0 (v4) MAT file, little endian doubles, column-major */
 int mcmcbh_write_mat4(const char* path, const char* name, const double* x, int rows, int cols, int ld);
+/* addtomat (matfiles.F90:187-293): append `cols` columns to the matrix of an existing MAT-v4 file and rewrite its
+ * header -- the reference's streaming ('disk') chain output, one column per chain row (MCMC_aux.F90:141-160) */
+int mcmcbh_addto_mat4(const char* path, const double* x, int rows, int cols, int ld);
+/* write_mcmcinit_namelist (mcmcinit.F90:147-179; `nmlffile`, MCMC_aux.F90:82-83): &mcmc with every variable, then &mcmcb */
+int mcmcbh_write_namelist(const char* path, const mcmcb_config* cfg, const mcmcbh_files* files);
 /* writes `.mat` by extension like MCMC_writechains (MCMC_aux.F90:25-29), else ASCII */
 int mcmcbh_write_matrix(const char* path, const char* name, const double* x, int rows, int cols, int ld);
 

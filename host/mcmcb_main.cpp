@@ -137,6 +137,8 @@ int main(int argc, char** argv) {
       HOST(mcmcbh_write_dat(in_dir(dir, files.sigma2ffile).c_str(), s2n.data(), 2, nycol, 2));
     }
   }
+  // the namelist as it was run (MCMC_aux.F90:82-83)
+  if (files.nmlffile[0]) HOST(mcmcbh_write_namelist(in_dir(dir, files.nmlffile).c_str(), &cfg, &files));
   if (cfg.diag_stride > 0) {
     std::vector<double> rhat(npar), ess(npar), pm(npar), pv(npar);
     long long ns = 0, nc = 0;

@@ -62,6 +62,8 @@ def hostlib():
     L.mcmcbh_write_mat4.argtypes = [C.c_char_p, C.c_char_p, dp, C.c_int, C.c_int, C.c_int]
     L.mcmcbh_read_namelist.argtypes = [C.c_char_p, C.POINTER(Config), C.POINTER(Files)]
     L.mcmcbh_free.argtypes = [C.c_void_p]
+    L.mcmcbh_addto_mat4.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_int]
+    L.mcmcbh_write_namelist.argtypes = [C.c_char_p, C.POINTER(Config), C.POINTER(Files)]
     return L
 
 
@@ -109,6 +111,41 @@ def test_namelist_forms_and_errors(tmp_path):
         p.write_text(bad)
         assert L.mcmcbh_read_namelist(str(p).encode(), C.byref(cfg), C.byref(fl)) == code
     assert L.mcmcbh_read_namelist(str(tmp_path / "missing.nml").encode(), C.byref(cfg), C.byref(fl)) == -1
+
+
+def test_addtomat_streams_columns(tmp_path):
+    # addtomat (matfiles.F90:187-293): the 'disk' save mode appends transpose(chain) blocks (MCMC_aux.F90:141-160)
+    L = hostlib()
+    rng = np.random.default_rng(1)
+    blocks = [np.asfortranarray(rng.normal(size=(3, n))) for n in (4, 1, 6)]
+    q = str(tmp_path / "chain.mat").encode()
+    dp = C.POINTER(C.c_double)
+    assert L.mcmcbh_write_mat4(q, b"chain", blocks[0].ctypes.data_as(dp), 3, 4, 3) == 0
+    for b in blocks[1:]:
+        assert L.mcmcbh_addto_mat4(q, b.ctypes.data_as(dp), 3, b.shape[1], 3) == 0
+    assert np.array_equal(scipy.io.loadmat(q.decode())["chain"], np.hstack(blocks))
+    bad = np.asfortranarray(rng.normal(size=(2, 2)))
+    assert L.mcmcbh_addto_mat4(q, bad.ctypes.data_as(dp), 2, 2, 2) == -3          # "xmat should have same number of rows"
+    assert L.mcmcbh_addto_mat4(str(tmp_path / "none.mat").encode(), bad.ctypes.data_as(dp), 2, 2, 2) == -1
+    assert np.array_equal(scipy.io.loadmat(q.decode())["chain"], np.hstack(blocks))  # untouched by the failed calls
+
+
+def test_namelist_write_back_round_trips(tmp_path):
+    # write_mcmcinit_namelist (mcmcinit.F90:147-179, `nmlffile`): what is written reads back identically
+    L = hostlib()
+    p = tmp_path / "in.nml"
+    p.write_text("&mcmc nsimu=777, method='er', drscale=1.5, adapthist=40, greedy=1, burnintime=30, doburnin=1, "
+                 "condmax=1d10, chainfile='c h.mat', nmlffile='final.nml', S02=0.125, covnfile='n.dat' /\n"
+                 "&mcmcb nchains=12, seed=99, model='gauss', datafile='d.dat', diag_stride=5, kernel=2 /\n")
+    a, fa, b, fb = Config(), Files(), Config(), Files()
+    assert L.mcmcbh_read_namelist(str(p).encode(), C.byref(a), C.byref(fa)) == 0, L.mcmcbh_last_error()
+    out = tmp_path / "final.nml"
+    assert L.mcmcbh_write_namelist(str(out).encode(), C.byref(a), C.byref(fa)) == 0, L.mcmcbh_last_error()
+    assert L.mcmcbh_read_namelist(str(out).encode(), C.byref(b), C.byref(fb)) == 0, L.mcmcbh_last_error()
+    assert bytes(a) == bytes(b) and bytes(fa) == bytes(fb)
+    assert (b.method, b.nsimu, b.drscale, b.condmax, fb.chainfile, fb.nmlffile) == (3, 777, 1.5, 1e10, b"c h.mat", b"final.nml")
+    text = out.read_text()
+    assert text.startswith("&mcmc") and "method = 'er'" in text and "&mcmcb" in text
 
 
 def test_dat_and_mat4_writers(tmp_path):
