@@ -11,7 +11,7 @@
  * `save`d variables (its data, testcases/mcmcrun.F90:69-86) plus the cooperative-lane
  * coordinates.
  *
- * Cooperative evaluation: `nlanes` threads share one chain.  ssfunction must return the
+ * Cooperative evaluation: `nlanes` threads share one chain (a fraction of a warp, a warp, or a group of warps).  ssfunction must return the
  * PARTIAL sum over the data items this lane owns (i = lane, lane+nlanes, ...); the kernel
  * adds the partials with warp shuffles.  Terms that do not depend on the data index must
  * be added by lane 0 only.  priorfun and checkbounds are evaluated redundantly by every
@@ -40,7 +40,17 @@ struct mcmcb_ctx {
                                (nullptr in the register kernel) */
   unsigned exp_tl;          /* shared-window byte address of the staged 2^(j/2048) table (see mcmcb_exp;
                                mcmcb_exp_column()); 0 = no table staged, use exp() */
+  int bar_id = 0, bar_threads = 0; /* nlanes > 32 (a group of warps shares the chain): the group's named barrier,
+                               used by mcmcb_sync_lanes() */
 };
+
+/* Make the `scratch` writes of every lane that shares the chain visible to all of them: __syncwarp() when the
+ * lanes are one warp (or less), the group's named barrier when several warps share the chain.  Every lane of the
+ * chain must call it (model code is warp/group-converged). */
+__device__ __forceinline__ void mcmcb_sync_lanes(const mcmcb_ctx& c) {
+  if (c.bar_threads > 32) asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(c.bar_threads) : "memory");
+  else __syncwarp();
+}
 
 /* ---------------------------------------------------------------------------------------
  * mcmcb_exp: FP64 exp() for model code, built for the FP64 pipe of sm_100a.

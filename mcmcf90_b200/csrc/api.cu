@@ -601,7 +601,7 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (!h) return MCMCB_EINVAL;
   if (npar) *npar = h->npar;
   if (nycol) *nycol = h->nycol;
-  if (lanes) *lanes = h->L;
+  if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : h->L;
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
   if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : K1_THREADS;
   if (blocks) *blocks = h->blocks;

@@ -13,6 +13,7 @@
 #include "diag.cuh"
 #include "k1_small.cuh"
 #include "k2_large.cuh"
+#include "k2g_group.cuh"
 #include "k3_scam.cuh"
 #include "mcmcb200.h"
 #include "pool.cuh"
@@ -580,6 +581,51 @@ struct K2 {
     return 0;
   }
 
+  // group-of-warps-per-chain kernel (k2g_group.cuh): DRAM/AM/ER with a Cholesky factor, npar large enough that a
+  // chain keeps several warps busy.  Returns false when it does not apply or does not fit.
+  static bool plan_group(mcmcb_handle h, int& GT, int& ngroups, bool& smem_blob) {
+    const mcmcb_config& c = h->cfg;
+    const char* force = getenv("MCMCB_K2_GROUP");  // opt-in (see the status note in k2g_group.cuh): 1 = whenever it fits
+    if (!(force && force[0] == '1')) return false;
+    if (h->factor_mode != FACTOR_CHOL || c.method == MCMCB_RAM) return false;
+    const int d = h->npar;
+    GT = std::min(256, ((d + 31) / 32) * 32);
+    if (d > GT * K2G_MAXM) return false;
+    const size_t T = (size_t)d * (d + 1) / 2, Tp = (T + 1) & ~(size_t)1;
+    const size_t per = sizeof(double) * ((size_t)K2_NVEC * h->dp + Tp + 2 * K2G_RED + 4);
+    const size_t room = h->max_smem - 1024;
+    const int cap = std::min(15, K2G_MAX_THREADS / GT);
+    int with_blob = h->blob_bytes + per <= room ? (int)std::min<size_t>(cap, (room - h->blob_bytes) / per) : 0;
+    int without = (int)std::min<size_t>(cap, room / per);
+    if (with_blob >= 1 && 2 * with_blob >= without) { ngroups = with_blob; smem_blob = true; }
+    else if (without >= 1) { ngroups = without; smem_blob = false; }
+    else return false;
+    return true;
+  }
+
+  template <bool SMEM>
+  static int launch_group(mcmcb_handle h, const K2Params& p, int GT, int ngroups) {
+    auto kern = k2g_step_kernel<M, SMEM>;
+    const int d = h->npar;
+    const size_t T = (size_t)d * (d + 1) / 2, Tp = (T + 1) & ~(size_t)1;
+    const size_t smem = sizeof(double) * (size_t)ngroups * ((size_t)K2_NVEC * h->dp + Tp + 2 * K2G_RED + 4) +
+                        (SMEM ? h->blob_bytes : 0);
+    if (!h->attr_set) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      h->occ = 1;
+      h->attr_set = true;
+    }
+    const long long need = (h->cfg.nchains + ngroups - 1) / ngroups;
+    const long long blocks = std::max<long long>(1, std::min<long long>(h->num_sms, need));
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
+    kern<<<(unsigned)blocks, GT * ngroups, smem, h->stream>>>(p, GT);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   static bool is_tick(const mcmcb_config& c, long long i) {
     if (c.method == MCMCB_RAM) return false;
     if (!c.doadapt && !c.doburnin) return false;
@@ -610,6 +656,10 @@ struct K2 {
       W = 8;  // a blob in shared memory beats the extra warps
       smem_blob = true;
     }
+    int GT = 0, ngroups = 0;
+    bool gblob = false;
+    const bool group = plan_group(h, GT, ngroups, gblob);
+    if (group) { resident = false; W = GT * ngroups / 32; h->k2_group_threads = GT; }
     if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
     int left = nsteps;
     bool first = true;
@@ -619,7 +669,8 @@ struct K2 {
       for (int k = 1; k <= left; k++)
         if (is_tick(c, h->k2_i + k)) { seg = k; break; }
       K2Params p = params(h, seg);
-      int rc = smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p);
+      int rc = group ? (gblob ? launch_group<true>(h, p, GT, ngroups) : launch_group<false>(h, p, GT, ngroups))
+                     : (smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p));
       if (rc) return rc;
       h->k2_i += seg;
       left -= seg;

@@ -183,7 +183,7 @@ struct GaussN {
       // theta - mu once per evaluation instead of once per matrix entry (same values, same order of the sum)
       double* df = c.scratch;
       for (int j = c.lane; j < d; j += c.nlanes) df[j] = theta[j] - mu[j];
-      __syncwarp();
+      mcmcb_sync_lanes(c);
       for (int i = c.lane; i < d; i += c.nlanes) {
         const double* col = lam + i;
         double w = 0.0;
@@ -196,7 +196,7 @@ struct GaussN {
         for (; j < d; j++, col += d) w = fma(col[0], df[j], w);
         acc = fma(w, df[i], acc);
       }
-      __syncwarp();
+      mcmcb_sync_lanes(c);
     } else {
       for (int i = c.lane; i < d; i += c.nlanes) {
         double w = 0.0;

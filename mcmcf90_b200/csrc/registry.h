@@ -73,6 +73,7 @@ struct mcmcb_handle_s {
   long long r_stride = 0, q_stride = 0;
   bool r_resident = false;
   int k2_warps = 8;
+  int k2_group_threads = 0;  // > 0: the group-of-warps-per-chain kernel (k2g_group.cuh) runs, this many threads per chain
   long long k2_i = 1;  // simuind shared by all chains of the handle
   // pooled adaptation + diagnostics (pool.cuh, diag.cuh)
   mcmcb_allreduce_fn ar_fn = nullptr;

@@ -110,6 +110,26 @@ def test_gauss_early_rejection_sampler(d):
     s.close()
 
 
+@pytest.mark.parametrize("d,variant", [(12, "dram"), (40, "burnin"), (100, "dram"), (70, "er")])
+def test_group_of_warps_per_chain_kernel(d, variant, monkeypatch):
+    # the opt-in kernel of csrc/k2g_group.cuh (MCMCB_K2_GROUP=1): several warps per chain, factor packed in shared
+    # memory; same parity bars as the warp-per-chain kernel
+    monkeypatch.setenv("MCMCB_K2_GROUP", "1")
+    mu, lam, Sig = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    nml = {"dram": dict(nsimu=400, adaptint=100, drscale=2.0, initcmatn=1, updatesigma=0),
+           "burnin": dict(nsimu=400, adaptint=100, burnintime=200, doburnin=1, badaptint=40, drscale=3.0,
+                          initcmatn=1, scalelimit=0.3, updatesigma=1, N0=4.0, S02=1.0),
+           "er": dict(method="er", nsimu=400, adaptint=100, initcmatn=3, updatesigma=0)}[variant]
+    N = 7
+    u = np.random.default_rng(1000 + d).random((N, (4 * d + 40) * nml["nsimu"]))
+    par0, cmat0 = np.zeros(d), np.eye(d) * (0.5 if d < 50 else 0.01)
+    s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, splits=[150, 249])
+    assert s.info()["lanes_per_chain"] == min(256, (d + 31) // 32 * 32)
+    compare(s, nml, range(N), O.MODEL_GAUSS, blob, par0, cmat0, u=u, rtol=1e-9 if d >= 70 else RTOL)
+    s.close()
+
+
 def test_c2_shape_philox():
     # BASELINE config C2 shape: d=100 correlated Gaussian, DRAM, per-chain private factor in HBM
     d = 100
