@@ -286,13 +286,18 @@ def run_ours(args):
         # DFMA counted as 2 flops) -- explains the gap between algorithmic and pipe utilisation
         # 9 FP64 instructions per datum in the SASS of the datum loop (7 DFMA + 1 DMUL + 1 DADD, profiles/r01_summary.md G)
         hw_flop_per_datum = float(os.environ.get("MCMCB_HW_FLOP_PER_DATUM", "16") or 0)
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch (2^20 chains x 100 iterations) from the
-        # committed `ncu --set full` capture profiles/r01_ncu_k1_fullsize.txt; algorithmic state traffic is
-        # 2 x 208 B x 2^20 = 436 MB, the rest is the chains' local-memory state spilling out of L1/L2
-        traffic = 738.7e6 if (N == 1 << 20 and info["lanes_per_chain"] == 1) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE steady-state bench launch (2^20 chains x 100 iterations),
+        # from `ncu --metrics dram__bytes...` on this command (profiles/r01_bench_launch_dram.txt).  The algorithmic
+        # state traffic is 2 x 212 B x 2^20 = 0.44 GB; the rest is the chains' cold state (accept/reject, adaptation,
+        # RNG position: ~450 B per chain, in local memory) cycling through L2: with 4 chains per thread the 3 x 10^5
+        # chains in flight hold 136 MB of it, more than L2 keeps, so every step re-reads and re-writes it.  That is
+        # 46 GB/s = 0.7 % of the measured HBM bandwidth on a kernel bound by the FP64 pipe and shared memory
+        # (one chain per thread: 0.74 GB per launch, 7 % slower).
+        traffic = {4: 58.5e9, 1: 738.7e6}.get(info["chains_per_thread"]) if (N == 1 << 20 and info["lanes_per_chain"] == 1) else None
         roof = {"bound": "fp64", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                 "frac": achieved / sustained, "traffic": traffic,
-                "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_k1_fullsize.txt)",
+                "traffic_unit": "bytes per launch (ncu, profiles/r01_bench_launch_dram.txt)",
+                "algorithmic_bytes_per_launch": 2.0 * 212 * N,
                 "peak_source": "in-bench DFMA microbenchmark on this GPU, sustained 2 s (burst %.2f); "
                                "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks, neither bounds this kernel" % burst,
                 "algorithmic_flops_per_chain_step": fl, "stage2_rate_q": q, "accept_rate": 1 - stay,

@@ -25,7 +25,10 @@
 
 namespace mcmcb {
 
-constexpr int K2_MAX_WARPS = 16;       // warps (= chains in flight) per CTA: 16, or 8 when the resident factor needs the room
+#ifndef MCMCB_K2_MAX_WARPS
+#define MCMCB_K2_MAX_WARPS 16
+#endif
+constexpr int K2_MAX_WARPS = MCMCB_K2_MAX_WARPS;       // warps (= chains in flight) per CTA: 16, or 8 when the resident factor needs the room
 constexpr int K2_MAX_THREADS = K2_MAX_WARPS * 32;
 constexpr int K2_MAXM = 8;             // npar <= 32 * K2_MAXM
 constexpr int K2_NVEC = 6;             // per-warp shared vectors
