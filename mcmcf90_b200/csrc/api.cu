@@ -161,8 +161,9 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   h->model = find_model(c.model, c.kernel);
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
   // AP windows and greedy burn-in (the configurations that walk the stored row history in the reference,
-  // MCMC_adapt.F90:83-101,116-136) are built in the register kernel only
-  if (h->model->kernel != 1 && c.method != MCMCB_RAM && ((c.adapthist > 1 && c.doadapt) || (c.greedy && c.doburnin))) { delete h; return MCMCB_EUNSUPPORTED; }
+  // MCMC_adapt.F90:83-101,116-136) are built for the Cholesky-factor samplers (K1, K2), not for SCAM / SVD factors
+  if (h->model->kernel != 1 && c.method != MCMCB_RAM && (h->doscam || h->usesvd) &&
+      ((c.adapthist > 1 && c.doadapt) || (c.greedy && c.doburnin))) { delete h; return MCMCB_EUNSUPPORTED; }
   if (c.pool_adapt && (c.adapthist > 1 || c.method == MCMCB_ER)) { delete h; return MCMCB_EUNSUPPORTED; }
   // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
   if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }
@@ -195,7 +196,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_hist, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
-                  h->d_cmat, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
+                  h->d_cmat, h->d_gcm, h->d_gmean, h->d_gw, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
                   h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial,
                   h->d_fetch};
   for (void* p : ptrs)

@@ -90,6 +90,9 @@ struct K2Params {
   double* qstd;    // [chain][dp]  SCAM proposal standard deviations (k3_scam.cuh)
   int factor_mode; // 0 = row-major upper Cholesky factor, 1 = column-major SVD factor (usesvd), 2 = SCAM
   long long r_stride, q_stride;  // per-chain strides of Rm / qstd: d*d / dp, or 0 when every chain shares the pooled factor
+  double* gcm;     // [chain][d*d]  greedy burn-in: unit-weight covariance of the CLOSED rows so far (MCMC_adapt.F90:83-101)
+  double* gmean;   // [chain][dp]
+  double* gw;      // [chain]
   int r_resident;  // 1: the warp keeps its chain's factor in shared memory for the whole launch (d*d doubles per warp)
 };
 
@@ -231,9 +234,11 @@ __global__ void k2_init_kernel(K2Params p) {
     double v = k < d ? p.par0[c * d + k] : 0.0;
     p.theta[c * p.dp + k] = v;
     p.mean[c * p.dp + k] = v;
+    if (p.gmean) p.gmean[c * p.dp + k] = v;
   }
   for (int k = threadIdx.x; k < d * d; k += blockDim.x) {
     p.cmat[(size_t)c * d * d + k] = p.cmat0[k];
+    if (p.gcm) p.gcm[(size_t)c * d * d + k] = p.cmat0[k];
     p.Rm[(size_t)c * p.r_stride + k] = 0.0;
   }
   if (threadIdx.x == 0) {
@@ -242,6 +247,7 @@ __global__ void k2_init_kernel(K2Params p) {
     for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * p.pitch] = 0.0; st[(Lo.s2 + k) * p.pitch] = p.sigma2_0[k]; }
     st[Lo.pri * p.pitch] = 0.0;
     st[Lo.wsum * p.pitch] = (double)p.c.initcmatn;
+    if (p.gw) p.gw[c] = (double)p.c.initcmatn;
     st[Lo.spare * p.pitch] = 0.0;
     st[Lo.rama * p.pitch] = 0.0;
     for (int k = 0; k < Lo.i_nf; k++) ist[k * p.pitch] = 0;
@@ -326,7 +332,7 @@ constexpr int ABS_RC = 8;   // dv rows per shared-memory chunk
 __host__ __device__ __forceinline__ size_t absorb_smem_doubles(int rowcap, int d) { return 2 * (size_t)(rowcap + 1) + (size_t)ABS_RC * d; }
 
 __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* cm, double* mean, double& wsum, int d,
-                                                double* sh) {
+                                                double* sh, bool unit_weights = false) {
   double* coef = sh;                       // (f1, f2) per row; f2 = -1: no-op row, f2 = -2: reset (first row, wsum == 0)
   double* chunk = sh + 2 * (size_t)nrows;  // ABS_RC x d
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -334,7 +340,7 @@ __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* c
   double ws = wsum;
   for (int r = 0; r < nrows; r++) {
     double* x = rb + (size_t)r * (d + 1);
-    const double w = x[d];
+    const double w = unit_weights ? 1.0 : x[d];
     if (ws > 0.0) {
       const double f3 = w / (ws + w);
       for (int k = tid; k < d; k += nt) {
@@ -436,6 +442,40 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       for (int k = threadIdx.x; k < d * d; k += blockDim.x) Rm[k] = Rm[k] / cf.scalefactor;
     } else if (staypc < cf.scalelimit) {
       for (int k = threadIdx.x; k < d * d; k += blockDim.x) Rm[k] = Rm[k] * cf.scalefactor;
+    } else if (cf.greedy) {
+      // MCMC_adapt.F90:83-102: chaincmat = covariance of rows 1..chainind with unit weights on top of (cmat0, par0,
+      // initcmatn).  The greedy accumulators hold the rows closed before the last greedy tick; the rows closed since
+      // are in the row buffer, and the open row joins for this tick only (it is fed again, once, when it closes).
+      double* gcm = p.gcm + (size_t)c * d * d;
+      double* gmean = p.gmean + c * p.dp;
+      double gw = p.gw[c];
+      __syncthreads();
+      cta_absorb_rows(rb, nbuf, gcm, gmean, gw, d, sh, true);
+      for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = gcm[k];
+      for (int k = threadIdx.x; k < d; k += blockDim.x) { mean[k] = gmean[k]; rb[k] = theta[k]; }
+      if (threadIdx.x == 0) rb[d] = 1.0;
+      __syncthreads();
+      wsum = gw;
+      cta_absorb_rows(rb, 1, cm, mean, wsum, d, sh, true);
+      const bool ok = cta_calculate_R(cm, Rm, tmp, d, red);
+      // what the AM branch starts from: see k1_finish (the reference resets at simuind == burnintime+adaptint+adapthist
+      // only if that step is a tick, otherwise it carries on from the greedy covariance)
+      const int t0 = cf.burnintime + cf.adaptint + cf.adapthist;
+      const bool will_reset = cf.doadapt && ((cf.adaptint > 0 && t0 % cf.adaptint == 0) || (cf.badaptint > 0 && t0 % cf.badaptint == 0)) &&
+                              !(cf.adaptend > 0 && t0 > cf.adaptend);
+      __syncthreads();
+      if (will_reset) {
+        for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = p.cmat0[k];
+        for (int k = threadIdx.x; k < d; k += blockDim.x) mean[k] = p.par0[c * d + k];
+        wsum = (double)cf.initcmatn;
+      }
+      if (threadIdx.x == 0) {
+        p.gw[c] = gw;
+        st[Lo.wsum * p.pitch] = wsum;
+        ist[Lo.i_pend * p.pitch] = 0;  // lastfreq = count of the open row
+        ist[Lo.i_nbuf * p.pitch] = 0;
+        if (!ok) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
+      }
     } else {
       // restart the accumulation at the open row with its full count; R = chol(cmat0) (see K1)
       for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = p.cmat0[k];
@@ -448,6 +488,56 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       }
       if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
     }
+  } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt && cf.adapthist > 1) {
+    // AP (MCMC_adapt.F90:116-136): covariance of the last adapthist steps by the batch formula of covmat
+    // (matutils.F90:312-337).  The row buffer holds the closed rows (theta, repeat count) still inside the window;
+    // the open row is row nbuf.  The first row's weight is trimmed so that the weights add up to adapthist.
+    __shared__ int s_first, s_hist;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+    if (threadIdx.x == 0) {
+      rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_cnt * p.pitch];
+      int first = nbuf, histsum = ist[Lo.i_cnt * p.pitch];
+      while (histsum < cf.adapthist && first > 0) { first--; histsum += (int)rb[(size_t)first * (d + 1) + d]; }
+      s_first = first; s_hist = histsum;
+    }
+    __syncthreads();
+    const int first = s_first, nrow = nbuf - first + 1;
+    const double wfirst = (double)((int)rb[(size_t)first * (d + 1) + d] - s_hist + cf.adapthist);
+    double wsum2 = 0.0;
+    for (int r = 0; r < nrow; r++) wsum2 += (r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d];
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < nrow; r++) acc = acc + rb[(size_t)(first + r) * (d + 1) + k] * ((r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d]);
+      mean[k] = acc / wsum2;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+      const int a = e / d, b = e - a * d;  // entry (a, b), b <= a computed, mirrored
+      if (b > a) continue;
+      const double ma = mean[a], mb2 = mean[b];
+      double acc = 0.0;
+      for (int r = 0; r < nrow; r++) {
+        const double* x = rb + (size_t)(first + r) * (d + 1);
+        acc = acc + (x[a] - ma) * ((x[b] - mb2) * ((r == 0) ? wfirst : x[d]));
+      }
+      const double v = acc / (wsum2 - 1.0);
+      cm[(size_t)a * d + b] = v;
+      cm[(size_t)b * d + a] = v;
+    }
+    __syncthreads();
+    // keep the closed rows that can still fall inside the next window, at the front of the buffer
+    const int keep = nbuf - first;  // closed rows first .. nbuf-1
+    if (first > 0) {
+      for (int r = 0; r < keep; r++) {
+        for (int k = threadIdx.x; k <= d; k += blockDim.x) rb[(size_t)r * (d + 1) + k] = rb[(size_t)(first + r) * (d + 1) + k];
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) {
+      st[Lo.wsum * p.pitch] = wsum2;
+      ist[Lo.i_nbuf * p.pitch] = keep;
+    }
+    if (!cf.pool && !cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
     // the open row joins the logged rows with its pending weight (slot nbuf always exists: rowcap + 1 rows)
     for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
@@ -786,7 +876,8 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
       // ---------------- end of step
       const int i = simuind + 1;
       simuind = i;
-      const bool absorbing = c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend);
+      const bool absorbing = (c.doadapt && c.method != MCMCB_RAM && !(c.adaptend > 0 && i > c.adaptend)) ||
+                             (c.greedy && c.doburnin && c.method != MCMCB_RAM && i <= c.burnintime);
       if (reject) {
         stayed++;
         cnt++; pend++;
@@ -794,7 +885,8 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_step_kernel(const __grid
         if (absorbing) {  // log the completed row and its not-yet-counted weight for the adaptation kernel
           if (nbuf < p.rowcap) {
             for (int k = lane; k < d; k += 32) rb[(size_t)nbuf * (d + 1) + k] = th[k];
-            if (lane == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)pend;
+            // AP windows weigh a row by its repeat count, the streaming recursion by what it has not yet counted
+            if (lane == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
             nbuf++;
           } else {
             status |= MCMCB_ST_STORE_FULL;

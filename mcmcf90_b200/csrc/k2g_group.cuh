@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(K2G_MAX_THREADS, 1) k2g_step_kernel(const __gr
       // ---------------- end of step, MCMC_run.F90:93-105
       const int i = simuind + 1;
       simuind = i;
-      const bool absorbing = c.doadapt && !(c.adaptend > 0 && i > c.adaptend);
+      const bool absorbing = (c.doadapt && !(c.adaptend > 0 && i > c.adaptend)) || (c.greedy && c.doburnin && i <= c.burnintime);
       if (reject) {
         stayed++;
         cnt++; pend++;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(K2G_MAX_THREADS, 1) k2g_step_kernel(const __gr
         if (absorbing) {  // log the completed row and its not-yet-counted weight for the adaptation kernel
           if (nbuf < p.rowcap) {
             for (int k = gt; k < d; k += GT) rb[(size_t)nbuf * (d + 1) + k] = th[k];
-            if (gt == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)pend;
+            if (gt == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
             nbuf++;
           } else {
             status |= MCMCB_ST_STORE_FULL;

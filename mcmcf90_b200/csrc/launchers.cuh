@@ -493,6 +493,9 @@ struct K2 {
     p.r_stride = h->r_stride;
     p.q_stride = h->q_stride;
     p.r_resident = h->r_resident ? 1 : 0;
+    p.gcm = h->d_gcm;
+    p.gmean = h->d_gmean;
+    p.gw = h->d_gw;
     return p;
   }
 
@@ -513,7 +516,8 @@ struct K2 {
     h->pitch = ((N + 31) / 32) * 32;
     h->dp = ((d + 31) / 32) * 32;
     h->rowcap = c.burnintime + 2 * std::max(c.adaptint, 1) + c.adapthist + 2;
-    if (c.method == MCMCB_RAM || !c.doadapt) h->rowcap = 1;
+    const bool greedy = c.greedy && c.doburnin && c.method != MCMCB_RAM && h->factor_mode == FACTOR_CHOL;
+    if (c.method == MCMCB_RAM || (!c.doadapt && !greedy)) h->rowcap = 1;
     CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
     CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
     CK(cudaMalloc(&h->d_theta, sizeof(double) * (size_t)N * h->dp));
@@ -530,6 +534,11 @@ struct K2 {
     CK(cudaMalloc(&h->d_qstd, sizeof(double) * NR * h->dp));
     CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * NR * h->dp, h->stream));
     CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * (h->rowcap + 1) * (d + 1)));
+    if (greedy) {  // unit-weight accumulators of the greedy burn-in (MCMC_adapt.F90:83-101)
+      CK(cudaMalloc(&h->d_gcm, sizeof(double) * (size_t)N * d * d));
+      CK(cudaMalloc(&h->d_gmean, sizeof(double) * (size_t)N * h->dp));
+      CK(cudaMalloc(&h->d_gw, sizeof(double) * (size_t)N));
+    }
     if (h->store_chains > 0) {
       size_t rows = (size_t)h->store_chains * h->cfg.nsimu;
       CK(cudaMalloc(&h->d_store_rows, sizeof(double) * rows * (d + NY)));

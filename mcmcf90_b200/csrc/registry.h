@@ -69,6 +69,7 @@ struct mcmcb_handle_s {
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
          *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr;
+  double *d_gcm = nullptr, *d_gmean = nullptr, *d_gw = nullptr;  // greedy burn-in accumulators (K2)
   int dp = 0, rowcap = 0, factor_mode = 0;
   long long r_stride = 0, q_stride = 0;
   bool r_resident = false;

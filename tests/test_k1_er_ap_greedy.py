@@ -143,11 +143,11 @@ def test_greedy_factor_right_after_a_greedy_tick():
     s.close()
 
 
-def test_large_npar_kernels_still_refuse_ap_and_greedy():
-    d = 40
-    for kw in (dict(adapthist=50), dict(greedy=1, doburnin=1, burnintime=100)):
-        cfg = mb.default_config(nchains=4, model="gauss", nsimu=100, adaptint=20, **kw)
+def test_svd_factor_samplers_refuse_ap_windows():
+    # AP windows / greedy burn-in exist for the Cholesky-factor samplers (K1, K2: tests/test_k2_parity.py), not for
+    # SCAM or condmax > 0
+    for kw in (dict(method="scam", adapthist=50), dict(condmax=1e10, adapthist=50)):
+        cfg = mb.default_config(nchains=4, model="hier", nsimu=100, adaptint=20, **kw)
         with pytest.raises(mb.MCMCBError) as e:
             mb.Sampler(cfg)
         assert "EUNSUPPORTED" in str(e.value)
-    del d

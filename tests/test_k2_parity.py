@@ -130,6 +130,35 @@ def test_group_of_warps_per_chain_kernel(d, variant, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("d,group", [(3, 0), (12, 0), (12, 1)])
+@pytest.mark.parametrize("variant", ["ap", "ap_short", "ap_burnin", "greedy", "greedy_no_reset", "greedy_only"])
+def test_ap_windows_and_greedy_burnin(d, group, variant, monkeypatch):
+    # adapthist > 1 (MCMC_adapt.F90:116-136) and greedy burn-in (:83-101) on the warp-per-chain kernel: the tick kernel
+    # works from the rows kept in the chain's row buffer
+    nml = {"ap": dict(nsimu=700, adaptint=50, adapthist=80, drscale=2.0, initcmatn=1, updatesigma=0),
+           "ap_short": dict(nsimu=700, adaptint=40, adapthist=30, drscale=0.0, initcmatn=1, updatesigma=1, N0=4.0, S02=1.0),
+           "ap_burnin": dict(nsimu=700, adaptint=50, adapthist=60, burnintime=150, doburnin=1, badaptint=30, scalelimit=0.3,
+                             drscale=2.0, initcmatn=1, updatesigma=0),
+           "greedy": dict(nsimu=700, adaptint=50, burnintime=300, doburnin=1, badaptint=25, greedy=1, scalelimit=0.05,
+                          drscale=2.0, initcmatn=3 * d, updatesigma=0),
+           "greedy_no_reset": dict(nsimu=700, adaptint=60, burnintime=280, doburnin=1, badaptint=35, greedy=1,
+                                   scalelimit=0.05, drscale=2.0, initcmatn=3 * d, updatesigma=0),
+           "greedy_only": dict(nsimu=400, doadapt=0, adaptint=50, burnintime=300, doburnin=1, badaptint=25, greedy=1,
+                               scalelimit=0.05, drscale=0.0, initcmatn=3 * d, updatesigma=0)}[variant]
+    if group:
+        monkeypatch.setenv("MCMCB_K2_GROUP", "1")  # the opt-in group-of-warps kernel logs its rows the same way
+    if variant == "ap_short" and d == 12:
+        pytest.skip("a 30-step window holds fewer than d+1 distinct rows: singular covariance, parity undefined")
+    mu, lam, Sig = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    N = 4
+    u = np.random.default_rng(7000 + d).random((N, (4 * d + 40) * nml["nsimu"]))
+    par0, cmat0 = np.zeros(d), np.eye(d) * 0.5
+    s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, splits=[333, 1, nml["nsimu"] - 1 - 334])
+    compare(s, nml, range(N), O.MODEL_GAUSS, blob, par0, cmat0, u=u, rtol=1e-9, at_tick=False)
+    s.close()
+
+
 def test_c2_shape_philox():
     # BASELINE config C2 shape: d=100 correlated Gaussian, DRAM, per-chain private factor in HBM
     d = 100
