@@ -658,6 +658,13 @@ struct K2 {
       int w = (int)std::min<size_t>(K2_MAX_WARPS, (h->max_smem - 1024) / (vec1 + d2));
       if (w >= 4) { resident = true; W = w; }
     }
+    // private Cholesky factors read from HBM/L2 for every proposal: keep the factors of the chains in flight inside
+    // L2 (about half of the 126 MB is usable from one side).  At npar = 100, 16 warps per CTA re-read 109 MB per step
+    // (L2 hit 24 %, 25 GB of DRAM reads per 200 steps); 8 warps fit (hit 97 %, 0.23 GB) and are as fast
+    // (profiles/r01_summary.md K)
+    if (!resident && h->factor_mode == FACTOR_CHOL && h->r_stride > 0 && c.method != MCMCB_RAM &&
+        (size_t)h->num_sms * W * (d2 / 2) > ((size_t)64 << 20))
+      W = std::max(8, W / 2);
     const size_t used = (size_t)W * (vec1 + (resident ? d2 : 0));
     if (used + 1024 > h->max_smem) W = (int)std::max<size_t>(1, (h->max_smem - 1024) / vec1);
     smem_blob = (size_t)W * (vec1 + (resident ? d2 : 0)) + h->blob_bytes + 1024 <= h->max_smem;
