@@ -313,7 +313,8 @@ struct K1 {
   static int step(mcmcb_handle h, int nsteps) {
     K1Params p = params(h, nsteps);
     if constexpr (has_ssfunction_er<M>::value) {  // method 'er', thread per chain: warp-vote early exit of the data loop
-      if (h->cfg.method == MCMCB_ER && h->L == 1)
+      const char* noexit = getenv("MCMCB_ER_NOEXIT");  // measurement only: method 'er' without the early exit
+      if (h->cfg.method == MCMCB_ER && h->L == 1 && !(noexit && noexit[0] == '1'))
         return h->smem_blob ? launch_LS<1, true, true>(h, p) : launch_LS<1, false, true>(h, p);
     }
     if constexpr (has_ssfunction_batch<M>::value) {  // thread per chain, B chains per thread (k1_step_kernel)
