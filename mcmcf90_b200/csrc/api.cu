@@ -320,7 +320,11 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   // chains per thread of the register kernel (thread-per-chain mapping): the launcher's tile plan falls back to
   // smaller tiles when there are too few chains to fill every warp (MCMCB_K1_BATCH overrides, tuning only)
   h->k1_batch = 1;
-  if (h->model->kernel == 1 && h->L == 1 && h->cfg.method != MCMCB_ER) {
+  {
+    const char* e = std::getenv("MCMCB_ER_EXIT");
+    h->er_exit = h->cfg.method == MCMCB_ER && e && e[0] == '1';
+  }
+  if (h->model->kernel == 1 && h->L == 1 && !h->er_exit) {
     int want = MCMCB_K1_DEFAULT_BATCH;
     if (const char* e = std::getenv("MCMCB_K1_BATCH")) want = std::atoi(e);
     h->k1_batch = (want == 2 || want == 4) ? want : 1;

@@ -312,9 +312,12 @@ struct K1 {
 
   static int step(mcmcb_handle h, int nsteps) {
     K1Params p = params(h, nsteps);
-    if constexpr (has_ssfunction_er<M>::value) {  // method 'er', thread per chain: warp-vote early exit of the data loop
-      const char* noexit = getenv("MCMCB_ER_NOEXIT");  // measurement only: method 'er' without the early exit
-      if (h->cfg.method == MCMCB_ER && h->L == 1 && !(noexit && noexit[0] == '1'))
+    if constexpr (has_ssfunction_er<M>::value) {
+      // method 'er', thread per chain, on request (MCMCB_ER_EXIT=1): the model's ssfunction_er with the warp-vote early
+      // exit of the data loop.  Not the default: a warp holds 32 independent chains and leaves the loop only when all of
+      // them are past their critical value, which measured no gain on the regression model (profiles/r01_summary.md M),
+      // while the batched kernel below is 13 % faster.  Chains are identical either way.
+      if (h->cfg.method == MCMCB_ER && h->L == 1 && h->k1_batch == 1 && h->er_exit)
         return h->smem_blob ? launch_LS<1, true, true>(h, p) : launch_LS<1, false, true>(h, p);
     }
     if constexpr (has_ssfunction_batch<M>::value) {  // thread per chain, B chains per thread (k1_step_kernel)

@@ -11,9 +11,9 @@ N, steps, ndata = 1 << 20, 50, 10000
 x, y = cases.synth_expreg(ndata)
 blob = mb.models.blob_expreg(x, y)
 par0 = cases.PAR0 * (1 + 0.01 * np.random.default_rng(0).normal(size=(N, 2)))
-for label, kw, env in (("AM (drscale=0)", dict(method="dram", drscale=0.0), "0"), ("ER, full sums", dict(method="er"), "1"),
-                       ("ER, early exit", dict(method="er"), "0")):
-    os.environ["MCMCB_ER_NOEXIT"] = env
+for label, kw, env in (("AM (drscale=0)", dict(method="dram", drscale=0.0), "0"), ("ER, batched", dict(method="er"), "0"),
+                       ("ER, early exit", dict(method="er"), "1")):
+    os.environ["MCMCB_ER_EXIT"] = env
     s = mb.Sampler(mb.default_config(nchains=N, seed=1, lanes_per_chain=1, nsimu=100000, adaptint=100, initcmatn=1,
                                      updatesigma=1, N0=1.0, S02=0.5, **kw))
     s.set_data(blob)

@@ -53,9 +53,12 @@ def test_er_prior_rejections_and_dr_switched_off():
     s.close()
 
 
-def test_er_early_exit_kernel_equals_full_sum():
+@pytest.mark.parametrize("early_exit", [0, 1])
+def test_er_early_exit_kernel_equals_full_sum(early_exit, monkeypatch):
     # thread per chain on 10^4 data in shared memory: the warp-vote early exit of ExpReg::ssfunction_er leaves
     # every chain identical to the oracle's full-sum default (ssfunction_er0.f90); resumed across launches
+    # (early_exit = 0: the default for 'er', four chains per thread through ssfunction_batch)
+    monkeypatch.setenv("MCMCB_ER_EXIT", str(early_exit))
     x, y = cases.synth_expreg(10000)
     blob = mb.models.blob_expreg(x, y)
     nml = dict(method="er", nsimu=241, adaptint=60, initcmatn=1, updatesigma=1, N0=1.0, S02=0.5)
@@ -63,7 +66,7 @@ def test_er_early_exit_kernel_equals_full_sum():
     par0 = cases.PAR0 * (1 + 0.01 * np.random.default_rng(3).normal(size=(N, 2)))
     cm0 = cases.CMAT0 * 11.0 / 10000
     s = _gpu_run(nml, N, blob, par0, seed=11, lanes=1, cmat0=cm0, nobs=[10000], splits=[100, 1, 139])
-    assert s.info()["lanes_per_chain"] == 1
+    assert s.info()["lanes_per_chain"] == 1 and s.info()["chains_per_thread"] == (1 if early_exit else 4)
     _compare(s, nml, 6, blob, par0, seed=11, cmat0=cm0, nobs=[10000], RTOL=1e-10)
     s.close()
 
