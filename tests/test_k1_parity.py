@@ -249,3 +249,28 @@ def test_full_size_properties_one_million_chains():
         assert c["stayed"][k] == r["stayed"]
         np.testing.assert_allclose(par[k], r["par"], rtol=RTOL)
     s.close()
+
+
+@pytest.mark.parametrize("N", [1, 33, 400003])
+def test_chains_per_thread_do_not_change_results(N, monkeypatch):
+    # the register kernel runs 4 chains per thread where there are enough chains (tile plan of 4-, 2- and 1-sub-tile
+    # tiles, csrc/launchers.cuh); a chain's result must not depend on how many neighbours share its thread.  400003
+    # chains: 4-sub-tile tiles plus a ragged last round.
+    nml = dict(cases.NML_DRAM, nsimu=100, adaptint=4, initcmatn=10)
+    par0 = cases.PAR0 * (1 + 0.01 * np.random.default_rng(17).normal(size=(N, 2)))
+    out = {}
+    for b in (1, 2, 4):
+        monkeypatch.setenv("MCMCB_K1_BATCH", str(b))
+        cfg = mb.default_config(nchains=N, seed=5, store_chains=0, model="expreg", lanes_per_chain=1, **nml)
+        s = mb.Sampler(cfg)
+        s.set_data(BLOB11)
+        s.set_initial(par0, cases.CMAT0, cases.SIGMA2, cases.NOBS)
+        s.run(3)
+        s.run(6)
+        assert s.info()["chains_per_thread"] == b
+        out[b] = (s.fetch("par"), s.fetch("cmat"), s.fetch("sigma2"), s.fetch("counters"))
+        s.close()
+    for b in (2, 4):
+        for x, y in zip(out[1], out[b]):
+            assert np.array_equal(x, y)
+    assert (out[1][3][:, 5] == 10).all() and (out[1][3][:, 6] == 0).all()  # simuind, status
