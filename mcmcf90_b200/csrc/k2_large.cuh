@@ -158,8 +158,16 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
 // rows in ascending order: results are bit-identical to the rolled reference loop.
 template <int U, bool TRI>
 __device__ __forceinline__ void tmv_load(double (&r)[U], const double* R, int d, int i, int jc) {
+  if (TRI) {
 #pragma unroll
-  for (int u = 0; u < U; u++) r[u] = R[(size_t)(i + u) * d + (TRI ? max(jc, i + u) : jc)];
+    for (int u = 0; u < U; u++) r[u] = R[(size_t)(i + u) * d + max(jc, i + u)];
+  } else {
+    // rectangle: one pointer for the batch, rows d apart (32-bit element offsets: one multiply-add per row instead of a
+    // 64-bit index computation)
+    const double* p = R + ((size_t)i * d + jc);
+#pragma unroll
+    for (int u = 0; u < U; u++) r[u] = p[(unsigned)(u * d)];
+  }
 }
 template <int U, bool TRI>
 __device__ __forceinline__ void tmv_use(const double (&r)[U], const double* vs, int i, int j, double& acc) {
