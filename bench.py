@@ -205,6 +205,31 @@ def other_workloads(mb, torch, dev):
                 "chains_with_error_status": bad}
 
     out = []
+    # C1 batched: the reference's own testcase (11 data) run as 2^22 chains -- the small-ndata end of the metric
+    x11 = np.arange(11.0)
+    y11 = np.array([9.33, 9.40, 8.99, 7.06, 7.13, 6.69, 4.69, 4.24, 4.77, 3.86, 4.02])
+    n1 = 1 << 22
+    s = mb.Sampler(mb.default_config(nchains=n1, seed=3, model="expreg", device=dev, nsimu=100000, adaptint=100, drscale=2.0,
+                                     initcmatn=1, updatesigma=1, N0=1.0, S02=0.0))
+    s.set_data(mb.models.blob_expreg(x11, y11))
+    s.set_initial(np.array([10.0, 0.1]), np.diag([0.2, 0.001]), [0.5], [11])
+    s.run(200)
+    st = torch.cuda.ExternalStream(s.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0 = s.counters()
+    e0.record(st)
+    s.run(200, sync=False)
+    e1.record(st)
+    s.sync()
+    c1 = s.counters()
+    ms = e0.elapsed_time(e1)
+    q1 = float((c1["drtries"] - c0["drtries"]).sum()) / (n1 * 200)
+    out.append({"workload": "C1 batched: testcases/data.dat model (11 data), DRAM+AM, 2^22 chains (k1_step_kernel, one chain per "
+                            "thread)", "npar": 2, "chains": n1, "iterations_timed": 200, "ms": ms,
+                "chain_steps_per_s": n1 * 200 / ms * 1e3, "stage2_rate_q": q1,
+                "datum_evals_per_s": n1 * 200 * (1 + q1) * 11 / ms * 1e3, "chains_per_thread": s.info()["chains_per_thread"],
+                "chains_with_error_status": int((c1["status"] != 0).sum())})
+    s.close()
     d = 100
     mu, lam = gauss_target(d)
     tri = d * (d + 1) // 2

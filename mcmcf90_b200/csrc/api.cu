@@ -325,7 +325,10 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
     h->er_exit = h->cfg.method == MCMCB_ER && e && e[0] == '1';
   }
   if (h->model->kernel == 1 && h->L == 1 && !h->er_exit) {
-    int want = MCMCB_K1_DEFAULT_BATCH;
+    // several chains per thread pay when the sweep over the model's data dominates a step (C3, 10^4 data: +7 %); with a
+    // short data loop the step is the cold routines, whose state then thrashes L1/L2 (11 data: 1.9e9 chain-steps/s
+    // with one chain per thread, 1.1e9 with four) -- the blob size is the proxy for the length of the data loop
+    int want = h->blob_n >= 2048 ? MCMCB_K1_DEFAULT_BATCH : 1;
     if (const char* e = std::getenv("MCMCB_K1_BATCH")) want = std::atoi(e);
     h->k1_batch = (want == 2 || want == 4) ? want : 1;
   }
