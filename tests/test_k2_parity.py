@@ -22,11 +22,14 @@ def gauss_target(d, rho=0.9, seed=0):
     return np.zeros(d), lam, Sig
 
 
-def run_gpu(nml, N, model, blob, par0, cmat0, u=None, seed=0, splits=None, chain_offset=0, sigma2=(1.0,), nobs=(1,)):
+def run_gpu(nml, N, model, blob, par0, cmat0, u=None, seed=0, splits=None, chain_offset=0, sigma2=(1.0,), nobs=(1,),
+            prior=None):
     cfg = mb.default_config(nchains=N, seed=seed, store_chains=-1, model=model, chain_offset=chain_offset,
                             rng_mode=mb.RNG_INJECTED if u is not None else mb.RNG_PHILOX, **nml)
     s = mb.Sampler(cfg)
     s.set_data(blob)
+    if prior is not None:
+        s.set_priors(*prior)
     s.set_initial(par0, cmat0, list(sigma2), list(nobs))
     if u is not None:
         s.inject_uniforms(u)
@@ -35,14 +38,16 @@ def run_gpu(nml, N, model, blob, par0, cmat0, u=None, seed=0, splits=None, chain
     return s
 
 
-def run_oracle(nml, k, model_id, blob, par0, cmat0, u=None, seed=0, chain_offset=0, sigma2=(1.0,), nobs=(1,)):
-    ch = O.Chain(O.make_cfg(**nml), model_id, blob, par0, cmat0, list(sigma2), list(nobs))
+def run_oracle(nml, k, model_id, blob, par0, cmat0, u=None, seed=0, chain_offset=0, sigma2=(1.0,), nobs=(1,), prior=None):
+    ch = O.Chain(O.make_cfg(**nml), model_id, blob, par0, cmat0, list(sigma2), list(nobs), prior=prior)
     if u is not None:
         ch.inject(u[k])
     else:
         ch.philox(seed, chain_offset + k)
     ch.run()
-    return ch.results()
+    r = ch.results()
+    r["erstayed"] = ch.counters()["erstayed"]
+    return r
 
 
 def compare(s, nml, ks, model_id, blob, par0, cmat0, u=None, seed=0, chain_offset=0, rtol=RTOL, sigma2=(1.0,),
@@ -156,6 +161,28 @@ def test_ap_windows_and_greedy_burnin(d, group, variant, monkeypatch):
     par0, cmat0 = np.zeros(d), np.eye(d) * 0.5
     s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, splits=[333, 1, nml["nsimu"] - 1 - 334])
     compare(s, nml, range(N), O.MODEL_GAUSS, blob, par0, cmat0, u=u, rtol=1e-9, at_tick=False)
+    s.close()
+
+
+def test_early_rejection_by_the_prior_alone():
+    # a Gaussian prior tighter than the likelihood: `sspri2 >= sscrit` fires (erstayed, MCMC_run_er.F90:62-67) and the
+    # model is then not consulted; mcmcb_fetch("erstayed") on the warp-per-chain kernel
+    d = 6
+    mu, lam, Sig = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    nml = dict(method="er", nsimu=400, adaptint=100, initcmatn=3, updatesigma=0)
+    prior = (np.full(d, 0.3), np.full(d, 0.2))
+    N = 4
+    u = np.random.default_rng(321).random((N, (4 * d + 40) * nml["nsimu"]))
+    par0, cmat0 = np.zeros(d), np.eye(d) * 0.5
+    s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, prior=prior)
+    er = s.fetch("erstayed")
+    cnt = s.counters()
+    for k in range(N):
+        r = run_oracle(nml, k, O.MODEL_GAUSS, blob, par0, cmat0, u=u, prior=prior)
+        assert (int(er[k]), int(cnt["stayed"][k]), int(cnt["ndrawn"][k])) == (r["erstayed"], r["stayed"], r["ndrawn"])
+        np.testing.assert_allclose(s.fetch("par")[k], r["par"], rtol=1e-9, atol=1e-12)
+    assert int(er.sum()) > 0
     s.close()
 
 
