@@ -18,7 +18,8 @@ from oracle import oracle as O  # noqa: E402
 from tests import cases  # noqa: E402
 
 NSIMU = 301
-SEEDS = {"shipped": 1, "dram": 2, "ram": 3, "scam": 4, "scam_hier": 5, "er": 6, "ap": 7, "greedy": 8}
+SEEDS = {"shipped": 1, "dram": 2, "ram": 3, "scam": 4, "scam_hier": 5, "er": 6, "ap": 7, "greedy": 8,
+         "gauss_dram": 9, "gauss_ram": 10, "gauss_er": 11, "gauss_ap": 12, "gauss_greedy": 13}
 HIER_Y = np.round(np.random.default_rng(99).normal(size=(4, 1)) + np.random.default_rng(98).normal(size=(4, 3)), 3)
 CASES = {
     "shipped": dict(cases.NML_SHIPPED, nsimu=NSIMU, burnintime=150, adaptint=50),
@@ -32,7 +33,23 @@ CASES = {
     "ap": dict(cases.NML_DRAM, nsimu=NSIMU, adaptint=40, adapthist=60),
     "greedy": dict(nsimu=NSIMU, adaptint=50, burnintime=150, doburnin=1, badaptint=25, greedy=1, scalelimit=0.05,
                    drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.0),
+    # the same samplers on a 6-dim correlated Gaussian target (the quadratic form of testcases/mcmcrun4.F90:47): the
+    # cases the warp-per-chain GPU kernels (run-time npar) are compared on
+    "gauss_dram": dict(nsimu=NSIMU, adaptint=50, drscale=2.0, initcmatn=1, updatesigma=0),
+    "gauss_ram": dict(method="ram", nsimu=NSIMU, updatesigma=0),
+    "gauss_er": dict(method="er", nsimu=NSIMU, adaptint=100, initcmatn=3, updatesigma=1, N0=4.0, S02=1.0),
+    "gauss_ap": dict(nsimu=NSIMU, adaptint=40, adapthist=60, drscale=2.0, initcmatn=1, updatesigma=0),
+    "gauss_greedy": dict(nsimu=NSIMU, adaptint=50, burnintime=150, doburnin=1, badaptint=25, greedy=1, scalelimit=0.05,
+                         drscale=2.0, initcmatn=18, updatesigma=0),
 }
+GAUSS_D = 6
+
+
+def gauss_target(d, rho=0.9):
+    sd = 1.0 + 9.0 * np.arange(d) / max(d - 1, 1)
+    sig = rho ** np.abs(np.subtract.outer(np.arange(d), np.arange(d))) * np.outer(sd, sd)
+    lam = np.linalg.inv(sig)
+    return np.zeros(d), 0.5 * (lam + lam.T)
 
 
 def uniforms(name):
@@ -42,6 +59,9 @@ def uniforms(name):
 
 def inputs(name):
     """(model_id, blob, par0, cmat0, sigma2, nobs) of a case."""
+    if name.startswith("gauss_"):
+        mu, lam = gauss_target(GAUSS_D)
+        return O.MODEL_GAUSS, O.blob_gauss(mu, lam), np.zeros(GAUSS_D), 0.5 * np.eye(GAUSS_D), [1.0], [1]
     if name == "scam_hier":
         d = HIER_Y.shape[0] + 2
         return O.MODEL_HIER, O.blob_hier(HIER_Y), np.full(d, 0.1), 0.1 * np.eye(d), [1.0], [1]

@@ -42,10 +42,12 @@ def test_golden_run_lengths_are_consistent():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,rtol", [("shipped", 1e-10), ("dram", 1e-10), ("ram", 1e-9), ("scam_hier", 1e-8),
-                                       ("er", 1e-10), ("ap", 1e-9), ("greedy", 1e-9)])
+                                       ("er", 1e-10), ("ap", 1e-9), ("greedy", 1e-9),
+                                       ("gauss_dram", 1e-9), ("gauss_ram", 1e-8), ("gauss_er", 1e-9), ("gauss_ap", 1e-9),
+                                       ("gauss_greedy", 1e-9)])
 def test_cuda_path_reproduces_golden(name, rtol):
     model_id, blob, par0, cmat0, sigma2, nobs = G.inputs(name)
-    model = {O.MODEL_EXPREG: "expreg", O.MODEL_HIER: "hier"}[model_id]
+    model = {O.MODEL_EXPREG: "expreg", O.MODEL_HIER: "hier", O.MODEL_GAUSS: "gauss"}[model_id]
     N = 3  # the same stream in every chain: all chains must reproduce the golden run
     cfg = mb.default_config(nchains=N, store_chains=-1, model=model, rng_mode=mb.RNG_INJECTED, **G.CASES[name])
     s = mb.Sampler(cfg)
