@@ -160,10 +160,9 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   // configurations that need the stored row history of the reference (AP)
   h->model = find_model(c.model, c.kernel);
   if (!h->model) { delete h; return MCMCB_ENOMODEL; }
-  // AP windows and greedy burn-in (the configurations that walk the stored row history in the reference,
-  // MCMC_adapt.F90:83-101,116-136) are built for the Cholesky-factor samplers (K1, K2), not for SCAM / SVD factors
-  if (h->model->kernel != 1 && c.method != MCMCB_RAM && (h->doscam || h->usesvd) &&
-      ((c.adapthist > 1 && c.doadapt) || (c.greedy && c.doburnin))) { delete h; return MCMCB_EUNSUPPORTED; }
+  // greedy burn-in (MCMC_adapt.F90:83-101) is built for the Cholesky-factor samplers (K1, K2), not with an SVD factor
+  // (condmax > 0; SCAM switches burn-in off anyway).  AP windows (:116-136) are built everywhere.
+  if (h->model->kernel != 1 && c.method != MCMCB_RAM && h->usesvd && c.greedy && c.doburnin) { delete h; return MCMCB_EUNSUPPORTED; }
   if (c.pool_adapt && (c.adapthist > 1 || c.method == MCMCB_ER)) { delete h; return MCMCB_EUNSUPPORTED; }
   // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
   if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }

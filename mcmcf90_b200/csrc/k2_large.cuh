@@ -423,6 +423,60 @@ __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* c
   __syncthreads();
 }
 
+// AP (MCMC_adapt.F90:116-136): covariance of the last adapthist steps by the batch formula of covmat
+// (matutils.F90:312-337), whole CTA.  The row buffer holds the closed rows (theta, repeat count) still inside the
+// window; the open row is appended as row nbuf.  The first row's weight is trimmed so that the weights add up to
+// adapthist.  Afterwards the closed rows that can still fall inside the next window sit at the front of the buffer.
+__device__ __forceinline__ void cta_ap_window(double* rb, int nbuf, const double* theta, double* cm, double* mean,
+                                              double* st, int* ist, long long pitch, int d, int adapthist) {
+  constexpr K2Layout Lo = k2_layout(1);
+  __shared__ int s_first, s_hist;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+  if (threadIdx.x == 0) {
+    rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_cnt * pitch];
+    int first = nbuf, histsum = ist[Lo.i_cnt * pitch];
+    while (histsum < adapthist && first > 0) { first--; histsum += (int)rb[(size_t)first * (d + 1) + d]; }
+    s_first = first; s_hist = histsum;
+  }
+  __syncthreads();
+  const int first = s_first, nrow = nbuf - first + 1;
+  const double wfirst = (double)((int)rb[(size_t)first * (d + 1) + d] - s_hist + adapthist);
+  double wsum2 = 0.0;
+  for (int r = 0; r < nrow; r++) wsum2 += (r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d];
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < nrow; r++) acc = acc + rb[(size_t)(first + r) * (d + 1) + k] * ((r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d]);
+    mean[k] = acc / wsum2;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int a = e / d, b = e - a * d;  // entry (a, b), b <= a computed, mirrored
+    if (b > a) continue;
+    const double ma = mean[a], mb2 = mean[b];
+    double acc = 0.0;
+    for (int r = 0; r < nrow; r++) {
+      const double* x = rb + (size_t)(first + r) * (d + 1);
+      acc = acc + (x[a] - ma) * ((x[b] - mb2) * ((r == 0) ? wfirst : x[d]));
+    }
+    const double v = acc / (wsum2 - 1.0);
+    cm[(size_t)a * d + b] = v;
+    cm[(size_t)b * d + a] = v;
+  }
+  __syncthreads();
+  const int keep = nbuf - first;  // closed rows first .. nbuf-1
+  if (first > 0) {
+    for (int r = 0; r < keep; r++) {
+      for (int k = threadIdx.x; k <= d; k += blockDim.x) rb[(size_t)r * (d + 1) + k] = rb[(size_t)(first + r) * (d + 1) + k];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    st[Lo.wsum * pitch] = wsum2;
+    ist[Lo.i_nbuf * pitch] = keep;
+  }
+  __syncthreads();
+}
+
 // MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
 static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   extern __shared__ double sh[];  // absorb_smem_doubles(rowcap, d)
@@ -497,54 +551,7 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       if (!cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
     }
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt && cf.adapthist > 1) {
-    // AP (MCMC_adapt.F90:116-136): covariance of the last adapthist steps by the batch formula of covmat
-    // (matutils.F90:312-337).  The row buffer holds the closed rows (theta, repeat count) still inside the window;
-    // the open row is row nbuf.  The first row's weight is trimmed so that the weights add up to adapthist.
-    __shared__ int s_first, s_hist;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
-    if (threadIdx.x == 0) {
-      rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_cnt * p.pitch];
-      int first = nbuf, histsum = ist[Lo.i_cnt * p.pitch];
-      while (histsum < cf.adapthist && first > 0) { first--; histsum += (int)rb[(size_t)first * (d + 1) + d]; }
-      s_first = first; s_hist = histsum;
-    }
-    __syncthreads();
-    const int first = s_first, nrow = nbuf - first + 1;
-    const double wfirst = (double)((int)rb[(size_t)first * (d + 1) + d] - s_hist + cf.adapthist);
-    double wsum2 = 0.0;
-    for (int r = 0; r < nrow; r++) wsum2 += (r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d];
-    for (int k = threadIdx.x; k < d; k += blockDim.x) {
-      double acc = 0.0;
-      for (int r = 0; r < nrow; r++) acc = acc + rb[(size_t)(first + r) * (d + 1) + k] * ((r == 0) ? wfirst : rb[(size_t)(first + r) * (d + 1) + d]);
-      mean[k] = acc / wsum2;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-      const int a = e / d, b = e - a * d;  // entry (a, b), b <= a computed, mirrored
-      if (b > a) continue;
-      const double ma = mean[a], mb2 = mean[b];
-      double acc = 0.0;
-      for (int r = 0; r < nrow; r++) {
-        const double* x = rb + (size_t)(first + r) * (d + 1);
-        acc = acc + (x[a] - ma) * ((x[b] - mb2) * ((r == 0) ? wfirst : x[d]));
-      }
-      const double v = acc / (wsum2 - 1.0);
-      cm[(size_t)a * d + b] = v;
-      cm[(size_t)b * d + a] = v;
-    }
-    __syncthreads();
-    // keep the closed rows that can still fall inside the next window, at the front of the buffer
-    const int keep = nbuf - first;  // closed rows first .. nbuf-1
-    if (first > 0) {
-      for (int r = 0; r < keep; r++) {
-        for (int k = threadIdx.x; k <= d; k += blockDim.x) rb[(size_t)r * (d + 1) + k] = rb[(size_t)(first + r) * (d + 1) + k];
-        __syncthreads();
-      }
-    }
-    if (threadIdx.x == 0) {
-      st[Lo.wsum * p.pitch] = wsum2;
-      ist[Lo.i_nbuf * p.pitch] = keep;
-    }
+    cta_ap_window(rb, nbuf, theta, cm, mean, st, ist, p.pitch, d, cf.adapthist);
     if (!cf.pool && !cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
     // the open row joins the logged rows with its pending weight (slot nbuf always exists: rowcap + 1 rows)

@@ -225,6 +225,9 @@ static __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
       }
       status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
     }
+  } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt && cf.adapthist > 1) {  // AP, MCMC_adapt.F90:116-136
+    cta_ap_window(rb, nbuf, theta, cm, mean, st, ist, p.pitch, d, cf.adapthist);
+    if (!cf.pool) status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
     for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
     if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k3_scam_step_kernel(const _
             if (absorbing) {
               if (nbuf < p.rowcap) {
                 for (int k = lane; k < d; k += 32) rb[(size_t)nbuf * (d + 1) + k] = th[k];
-                if (lane == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)pend;
+                if (lane == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
                 nbuf++;
               } else {
                 status |= MCMCB_ST_STORE_FULL;

@@ -148,11 +148,10 @@ def test_greedy_factor_right_after_a_greedy_tick():
     s.close()
 
 
-def test_svd_factor_samplers_refuse_ap_windows():
-    # AP windows / greedy burn-in exist for the Cholesky-factor samplers (K1, K2: tests/test_k2_parity.py), not for
-    # SCAM or condmax > 0
-    for kw in (dict(method="scam", adapthist=50), dict(condmax=1e10, adapthist=50)):
-        cfg = mb.default_config(nchains=4, model="hier", nsimu=100, adaptint=20, **kw)
-        with pytest.raises(mb.MCMCBError) as e:
-            mb.Sampler(cfg)
-        assert "EUNSUPPORTED" in str(e.value)
+def test_svd_factor_refuses_greedy_burnin():
+    # greedy burn-in exists for the Cholesky-factor samplers (K1, K2: tests/test_k2_parity.py), not with condmax > 0
+    cfg = mb.default_config(nchains=4, model="hier", nsimu=100, adaptint=20, condmax=1e10, greedy=1, doburnin=1,
+                            burnintime=50)
+    with pytest.raises(mb.MCMCBError) as e:
+        mb.Sampler(cfg)
+    assert "EUNSUPPORTED" in str(e.value)

@@ -90,6 +90,22 @@ def test_scam_gauss_injected(d, sig):
     s.close()
 
 
+@pytest.mark.parametrize("mode", ["scam", "usesvd"])
+def test_ap_window_with_svd_factors(mode):
+    # adapthist > 1 (MCMC_adapt.F90:116-136) feeding the SVD square root: SCAM, and AM with condmax > 0
+    d = 4
+    mu, lam, Sig = aniso_gauss(d, seed=11)
+    blob = mb.models.blob_gauss(mu, lam)
+    nml = dict(nsimu=640, adaptint=80, adapthist=120, initcmatn=2, updatesigma=0)
+    nml.update(dict(method="scam") if mode == "scam" else dict(condmax=1e12, drscale=0.0))
+    N = 3
+    u = np.random.default_rng(50).random((N, (4 * d + 30) * nml["nsimu"]))
+    par0, cmat0 = np.zeros(d), np.diag(np.linspace(0.2, 0.6, d))
+    s = run_gpu(nml, N, "gauss", blob, par0, cmat0, u=u, nobs=(d,), splits=[333, 306])
+    compare(s, nml, range(N), O.MODEL_GAUSS, blob, par0, cmat0, u=u, nobs=(d,), scam=(mode == "scam"))
+    s.close()
+
+
 def test_scam_hier_philox_with_bounds_free_model():
     rng = np.random.default_rng(1)
     G, J = 6, 5
