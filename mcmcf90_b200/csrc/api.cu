@@ -54,8 +54,10 @@ using namespace mcmcb::launch;
 // user plugin does (include/mcmcb200_plugin.cuh)
 
 const ModelEntry* find_model(const char* name, int kernel) {
-  for (auto& e : registry())
-    if (std::strcmp(e.name, name) == 0 && (kernel == 0 || e.kernel == kernel)) return &e;
+  // kernel == 0 (auto): a model registered for both kernel families runs on the register kernel (compile-time npar)
+  for (int want : {kernel == 0 ? 1 : kernel, kernel == 0 ? 2 : kernel})
+    for (auto& e : registry())
+      if (std::strcmp(e.name, name) == 0 && e.kernel == want) return &e;
   return nullptr;
 }
 
@@ -164,8 +166,13 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   // (condmax > 0; SCAM switches burn-in off anyway).  AP windows (:116-136) are built everywhere.
   if (h->model->kernel != 1 && c.method != MCMCB_RAM && h->usesvd && c.greedy && c.doburnin) { delete h; return MCMCB_EUNSUPPORTED; }
   if (c.pool_adapt && (c.adapthist > 1 || c.method == MCMCB_ER)) { delete h; return MCMCB_EUNSUPPORTED; }
-  // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only
-  if (h->model->kernel == 1 && (h->doscam || h->usesvd)) { delete h; return MCMCB_EUNSUPPORTED; }
+  // SVD factor paths (SCAM, condmax > 0) live in the warp-per-chain kernels only: take the model's registration for
+  // those kernels when it has one (the built-in "expreg" does)
+  if (h->model->kernel == 1 && (h->doscam || h->usesvd)) {
+    const ModelEntry* alt = c.kernel == 0 ? find_model(c.model, 2) : nullptr;
+    if (!alt) { delete h; return MCMCB_EUNSUPPORTED; }
+    h->model = alt;
+  }
   // pooled adaptation replaces the chains' own factor updates at the AM ticks; the burn-in scaling branch
   // (per-chain acceptance driven) and the usesvd DR combination stay per chain and are not pooled
   if (c.pool_adapt && (c.doburnin || !c.doadapt || c.adaptint <= 0)) { delete h; return MCMCB_EUNSUPPORTED; }

@@ -163,6 +163,36 @@ struct ExpReg {
 // Run-time-npar models for the warp-per-chain kernel (NPAR = 0): theta lives in shared memory,
 // the 32 lanes of the warp split the work and the kernel adds their partial sums.
 
+// The exponential-decay regression again, for the warp-per-chain kernels (run-time npar = 2): the samplers that
+// need an SVD factor (method='scam', condmax > 0) live there, and the reference's shipped testcase must be runnable
+// with them.  Same blob as ExpReg; the lanes stride over the data.
+struct ExpRegN {
+  static constexpr int NPAR = 0;
+  static constexpr int NY = 1;
+  static const char* name() { return "expreg"; }
+  __device__ __forceinline__ static bool checkbounds(const double* theta, int npar, const mcmcb_ctx&) {
+    bool ok = true;
+    for (int i = 0; i < npar; i++) ok = ok && !(theta[i] <= 0.0);
+    return ok;
+  }
+  __device__ __forceinline__ static double priorfun(const double* theta, int len, const mcmcb_ctx& c) {
+    return mcmcb_default_priorfun(theta, len, c);
+  }
+  __device__ __forceinline__ static void ssfunction(const double* theta, int, int, const mcmcb_ctx& c, double* ss) {
+    const int n = (int)c.data[0];
+    const int npad = (n + 1) & ~1;
+    const double* __restrict__ x = c.data + 2;
+    const double* __restrict__ y = c.data + 2 + npad;
+    const double t1 = theta[0], nt2 = -theta[1];
+    double acc = 0.0;
+    for (int i = c.lane; i < n; i += c.nlanes) {
+      const double r = fma(-t1, exp(nt2 * x[i]), y[i]);
+      acc = fma(r, r, acc);
+    }
+    ss[0] = acc;
+  }
+};
+
 // Gaussian target ss = (theta-mu)' Lam (theta-mu) (testcases/mcmcrun4.F90:47); BASELINE config C2.
 // blob: [d, 0, mu[dpad], Lam[d*d]]; Lam must be symmetric (row i is read as column i).
 struct GaussN {

@@ -41,7 +41,7 @@ def test_golden_run_lengths_are_consistent():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,rtol", [("shipped", 1e-10), ("dram", 1e-10), ("ram", 1e-9), ("scam_hier", 1e-8),
+@pytest.mark.parametrize("name,rtol", [("shipped", 1e-10), ("dram", 1e-10), ("ram", 1e-9), ("scam", 1e-8), ("scam_hier", 1e-8),
                                        ("er", 1e-10), ("ap", 1e-9), ("greedy", 1e-9),
                                        ("gauss_dram", 1e-9), ("gauss_ram", 1e-8), ("gauss_er", 1e-9), ("gauss_ap", 1e-9),
                                        ("gauss_greedy", 1e-9)])

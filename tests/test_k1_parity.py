@@ -195,7 +195,8 @@ def test_injected_stream_exhaustion_is_flagged():
 
 def test_unsupported_configurations_fail_loudly():
     # (AP windows and greedy burn-in are built in this kernel: tests/test_k1_er_ap_greedy.py)
-    for kw in (dict(condmax=1e10), dict(method="scam"), dict(adapthist=50, pool_adapt=1)):
+    # (SVD factors -- method='scam', condmax > 0 -- run on the warp-per-chain kernels; forcing the register kernel fails)
+    for kw in (dict(condmax=1e10, kernel=1), dict(method="scam", kernel=1), dict(adapthist=50, pool_adapt=1)):
         with pytest.raises(mb.MCMCBError):
             mb.Sampler(mb.default_config(nsimu=10, nchains=2, **kw))
     with pytest.raises(mb.MCMCBError):
