@@ -205,3 +205,29 @@ def test_driver_executable_writes_the_reference_files(tmp_path, variant):
             np.testing.assert_allclose(np.loadtxt(os.path.join(d, "mcmcsigma2f.dat")), [ref["s2chain"][-1, 0], 11.0], rtol=1e-9)
             assert np.loadtxt(os.path.join(d, "mcmccovf.dat")).shape == (2, 2)
             assert np.loadtxt(os.path.join(d, "mcmcmean.dat")).shape == (2,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["er", "scam"])
+def test_driver_runs_the_other_samplers_of_the_testcase(tmp_path, method):
+    # method = 'er' / 'scam' in mcmcinit.nml (mcmc_main.F90:29-37) through the driver executable, plus the namelist
+    # write-back (nmlffile, MCMC_aux.F90:82-83)
+    d = str(tmp_path)
+    nml = NML_SHIPPED.replace("method = 'dram'", "method = '%s'\n nmlffile = 'final.nml'" % method) \
+                     .replace("burnintime  = 1000", "burnintime  = 0").replace("doburnin    = 1", "doburnin    = 0") \
+                     .replace("adaptint    = 200", "adaptint    = 100\n initcmatn = 2").replace("nsimu       = 1000", "nsimu       = 400")
+    write_testcase(d, nml, "&mcmcb nchains = 2, seed = 7, store_chains = 1 /\n")
+    r = subprocess.run([os.path.join(HOST, "mcmcb_main"), d], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kw = dict(method=method, nsimu=400, doadapt=1, adaptint=100, initcmatn=2, burnintime=0, doburnin=0, drscale=0.0,
+              updatesigma=1, N0=1.0, S02=0.0)
+    ch = O.Chain(O.make_cfg(**kw), O.MODEL_EXPREG, O.blob_expreg(cases.DATA_X, cases.DATA_Y), cases.PAR0, cases.CMAT0,
+                 cases.SIGMA2, cases.NOBS)
+    ch.philox(7, 0)
+    ch.run()
+    ref = ch.results()
+    chain = np.loadtxt(os.path.join(d, "chain.dat"), ndmin=2)
+    assert chain.shape == ref["chain"].shape and np.array_equal(chain[:, -1], ref["chain"][:, -1])
+    np.testing.assert_allclose(chain[:, :-1], ref["chain"][:, :-1], rtol=1e-8)
+    text = open(os.path.join(d, "final.nml")).read()
+    assert "method = '%s'" % method in text and "nsimu = 400" in text
