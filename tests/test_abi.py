@@ -65,3 +65,16 @@ def test_check_config_mirrors_reference_rules(kw):
 def test_check_config_rejects_bad_scalelimit():
     c = mb.default_config(scalelimit=0.7)
     assert mb.load_library().mcmcb_check_config(C.byref(c), None, None, None) == -1
+
+
+def test_check_config_early_rejection_and_bad_method():
+    # "no dr with er" (MCMC_run_er.F90:24-27): the reference switches delayed rejection off when MCMC_run_er starts;
+    # here check_config does it.  An unknown method code is an error (the reference falls back to MCMC_run for unknown
+    # method *strings*, which the namelist reader of host/ reproduces before this call).
+    c = mb.default_config(method="er", drscale=2.0)
+    dodr = C.c_int(7)
+    assert mb.load_library().mcmcb_check_config(C.byref(c), C.byref(dodr), None, None) == 0
+    assert (c.method, c.drscale, dodr.value) == (mb.ER, 0.0, 0)
+    c = mb.default_config()
+    c.method = 9
+    assert mb.load_library().mcmcb_check_config(C.byref(c), None, None, None) == -1
