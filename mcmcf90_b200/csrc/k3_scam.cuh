@@ -329,6 +329,12 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k3_scam_step_kernel(const _
         const double delta = zs[0] * qs[j];
         const double* col = U + (size_t)j * d;
         for (int k = lane; k < d; k += 32) prop[k] = fma(col[k], delta, th[k]);
+        {
+          // the next component's column (the first one again after the last): requested now, it arrives while the model
+          // is evaluated -- the read above was the kernel's largest stall (profiles/r01_summary.md P)
+          const double* nxt = U + (size_t)((j + 1 < d) ? j + 1 : 0) * d;
+          for (int k = lane * 16; k < d; k += 32 * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + k));
+        }
         __syncwarp();
         bool reject;
         double ssn[NY], prn = 0.0;
