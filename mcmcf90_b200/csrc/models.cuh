@@ -264,7 +264,8 @@ struct BananaN {
 };
 
 // Hierarchical normal means: params (theta_1..G, mu, log tau), y_gj ~ N(theta_g, 1),
-// theta_g ~ N(mu, tau^2), weak hyperpriors mu ~ N(0,10^2), log tau ~ N(0,2^2).   blob: [G, J, y[G*J]]
+// theta_g ~ N(mu, tau^2), weak hyperpriors mu ~ N(0,10^2), log tau ~ N(0,2^2).   blob: [G, J, y[J][G]] -- observation
+// j of every group contiguous, so that lanes (one group each) read consecutive shared-memory addresses
 struct HierN {
   static constexpr int NPAR = 0;
   static constexpr int NY = 1;
@@ -282,7 +283,7 @@ struct HierN {
     for (int g = c.lane; g < G; g += c.nlanes) {
       const double tg = theta[g];
       double a = 0.0;
-      for (int j = 0; j < J; j++) { const double r = y[(size_t)g * J + j] - tg; a = fma(r, r, a); }
+      for (int j = 0; j < J; j++) { const double r = y[(size_t)j * G + g] - tg; a = fma(r, r, a); }
       const double dm = tg - mu;
       acc += a + dm * dm * itau2;
     }

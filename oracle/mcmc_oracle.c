@@ -498,7 +498,7 @@ int orc_symeig(int n, const double* Ain, double* U, double* s) {
  *  EXPREG: [n, 0, x[npad], y[npad]], npad = n rounded up to even
  *  GAUSS : [d, 0, mu[dpad], Lam[d*d] row-major]
  *  BANANA: [d, b]
- *  HIER  : [G, J, y[G*J] group-major]    params (theta_1..G, mu, log tau)           */
+ *  HIER  : [G, J, y[J][G] observation-major] params (theta_1..G, mu, log tau)         */
 static void model_ss(const orc_model* m, const double* theta, double* ss) {
   const double* b = m->blob;
   switch (m->id) {
@@ -543,7 +543,7 @@ static void model_ss(const orc_model* m, const double* theta, double* ss) {
       for (int g = 0; g < G; g++) {
         double a = 0.0;
         for (int j = 0; j < J; j++) {
-          double r = y[(size_t)g * J + j] - theta[g];
+          double r = y[(size_t)j * G + g] - theta[g]; /* blob: y[J][G] */
           a = a + r * r;
         }
         double dm = theta[g] - mu;

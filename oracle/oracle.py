@@ -146,7 +146,7 @@ def blob_hier(y):
     G, J = y.shape
     b = np.zeros(2 + G * J)
     b[0], b[1] = G, J
-    b[2:] = y.reshape(-1)
+    b[2:] = y.T.reshape(-1)  # y[j][g]: observation j of every group contiguous
     return b
 
 
