@@ -450,15 +450,18 @@ extern "C" int mcmcbh_model_blob(const char* model, const char* datapath, double
   int rc = mcmcbh_load_dat(datapath, &m, &r, &c);
   if (rc) return rc;
   if (c < 2) { std::free(m); return fail(MCMCBH_EPARSE, "data file needs two columns (x, y)"); }
-  // [n, max|x|, x[npad], y[npad]] (csrc/models.cuh ExpReg)
+  // [n, +-max|x| (negative when some x < 0), x[npad], y[npad]] (csrc/models.cuh ExpReg)
   const int npad = (r + 1) & ~1;
   double* b = (double*)std::calloc(2 + 2 * (size_t)npad, sizeof(double));
   b[0] = r;
+  bool anyneg = false;
   for (int i = 0; i < r; i++) {
     b[2 + i] = m[(size_t)i * c];
     b[2 + npad + i] = m[(size_t)i * c + 1];
     b[1] = std::max(b[1], std::fabs(m[(size_t)i * c]));
+    anyneg = anyneg || m[(size_t)i * c] < 0.0;
   }
+  if (anyneg) b[1] = -b[1];
   std::free(m);
   *blob = b;
   *n = 2 + 2 * (size_t)npad;

@@ -42,6 +42,9 @@ struct mcmcb_ctx {
                                mcmcb_exp_column()); 0 = no table staged, use exp() */
   int bar_id = 0, bar_threads = 0; /* nlanes > 32 (a group of warps shares the chain): the group's named barrier,
                                used by mcmcb_sync_lanes() */
+  unsigned exp_td = 0;      /* shared-window byte address of entry k = 0 of the DIRECT table 2^(k/2048), k = -(exp_dn-1)..0
+                               (see mcmcb_expmul_direct); 0 = not staged */
+  int exp_dn = 0;           /* entries of the direct table */
 };
 
 /* Make the `scratch` writes of every lane that shares the chain visible to all of them: __syncwarp() when the
@@ -163,6 +166,41 @@ __device__ __forceinline__ double mcmcb_expmul_fast(double x, double ks, unsigne
   return mcmcb_expmul_fast(x, ks, tl, MCMCB_EXPC[6], MCMCB_EXPC[7]);
 }
 
+/* exp(x * s) for arguments known to lie in [-(dn-2) ln2/2048, 0]: the DIRECT table holds 2^(k/2048) itself for
+ * every k the argument range can produce (k = -(dn-1)..0), so the lookup needs neither the mask that isolates j nor the
+ * integer multiply-add that inserts the exponent m -- two non-FP64 instructions (address, load) instead of four in a
+ * loop whose cost is 2 x (FP64 instructions) + (other instructions) issue cycles.  2^m * 2^(j/2048) is an
+ * exact scaling of the correctly rounded table entry, so the result is bit-identical to mcmcb_expmul_fast's.  `td` is the
+ * shared-window address of entry k = 0; entries of negative k sit below it.
+ * MCMCB_EXP_DIRECT_SPLIT: the entry's high and low words live in two 4-byte tables (low words dn*4 bytes above the
+ * high words): a warp's lookups then alias only when two k differ by a multiple of 32 (8-byte entries: 16). */
+__device__ __forceinline__ double mcmcb_expmul_direct(double x, double ks, unsigned td, double c1, int dn) {
+  const double t = fma(x, ks, MCMCB_EXP_MAGIC);
+  const int k = __double2loint(t);
+  const double r = fma(x, ks, MCMCB_EXP_MAGIC - t);
+  double q = fma(r, MCMCB_EXPC[7], c1);
+  q = fma(r, q, MCMCB_EXPC[5]);
+  unsigned addr;
+#ifdef MCMCB_EXP_DIRECT_SPLIT
+  int hi, lo;
+  asm("mad.lo.s32 %0, %1, 4, %2;" : "=r"(addr) : "r"(k), "r"(td));
+  asm("ld.shared.b32 %0, [%1];" : "=r"(hi) : "r"(addr));
+  asm("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(addr + 4u * (unsigned)dn));
+  const double sc = __hiloint2double(hi, lo);
+#else
+  double sc;
+  (void)dn;
+  asm("mad.lo.s32 %0, %1, 8, %2;" : "=r"(addr) : "r"(k), "r"(td));
+  asm("ld.shared.f64 %0, [%1];" : "=d"(sc) : "r"(addr));
+#endif
+  return fma(sc, r * q, sc);
+}
+/* does exp(x*s) for every |x| <= xmax of one sign stay inside a direct table of dn entries?  (s*x <= 0 is the
+ * caller's to guarantee; two entries of slack for the rounding of k) */
+__device__ __forceinline__ bool mcmcb_exp_direct_ok(double s, double xmax, int dn) {
+  return fabs(s) * xmax * MCMCB_EXPC[0] < (double)(dn - 2);
+}
+
 /* true when the fast paths are valid for argument a: |a| < 708 and a is not NaN */
 __device__ __forceinline__ bool mcmcb_exp_ok(double a) {
   return (unsigned)(__double2hiint(a) & 0x7fffffff) < 0x40862000u;
@@ -184,6 +222,32 @@ __device__ __forceinline__ void mcmcb_stage_exp_table(double* smem_tab) {
     const double v = MCMCB_EXP2_TABLE[j];
     smem_tab[i] = __hiloint2double(__double2hiint(v) - (j << MCMCB_EXP_TAB_SHIFT), __double2loint(v));  /* see mcmcb_exp_assemble */
   }
+}
+
+/* stage the direct table 2^(k/2048), k = -(dn-1)..0, at smem_direct (entry e holds k = e-(dn-1)); call from every
+ * thread of the CTA, then __syncthreads().  Returns nothing; mcmcb_exp_direct_base() gives the address of entry k = 0. */
+__device__ __forceinline__ void mcmcb_stage_exp_direct(double* smem_direct, int dn) {
+  for (int e = threadIdx.x; e < dn; e += blockDim.x) {
+    const int k = e - (dn - 1);
+    const int j = k & (MCMCB_EXP_TAB_N - 1), m = k >> 11;  /* k = 2048 m + j, m <= 0 */
+    const double v = MCMCB_EXP2_TABLE[j];
+    const int hi = __double2hiint(v) + m * (1 << 20), lo = __double2loint(v);
+#ifdef MCMCB_EXP_DIRECT_SPLIT
+    reinterpret_cast<int*>(smem_direct)[e] = hi;
+    reinterpret_cast<int*>(smem_direct)[dn + e] = lo;
+#else
+    smem_direct[e] = __hiloint2double(hi, lo);
+#endif
+  }
+}
+__device__ __forceinline__ unsigned mcmcb_exp_direct_base(const double* smem_direct, int dn) {
+#ifdef MCMCB_EXP_DIRECT_SPLIT
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem_direct) + 4u * (unsigned)(dn - 1);
+#else
+  unsigned a = (unsigned)__cvta_generic_to_shared(smem_direct) + 8u * (unsigned)(dn - 1);
+#endif
+  asm volatile("" : "+r"(a));
+  return a;
 }
 
 /* default prior, priorfun.f90:97-100: sum(((theta-mu)/sig)**2, mask = sig>0) */

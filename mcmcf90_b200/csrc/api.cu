@@ -326,6 +326,7 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   // chains per thread of the register kernel (thread-per-chain mapping): the launcher's tile plan falls back to
   // smaller tiles when there are too few chains to fill every warp (MCMCB_K1_BATCH overrides, tuning only)
   h->k1_batch = 1;
+  if (const char* e = std::getenv("MCMCB_EXP_DIRECT")) h->k1_exp_direct = e[0] != '0';  // tuning experiments only
   {
     const char* e = std::getenv("MCMCB_ER_EXIT");
     h->er_exit = h->cfg.method == MCMCB_ER && e && e[0] == '1';

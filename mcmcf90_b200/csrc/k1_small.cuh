@@ -92,6 +92,7 @@ struct K1Params {
   int hist_rows;
   long long tier[3];  // tiles of 4, 2 and 1 sub-tiles, in this order along the chain range (k1_step_kernel)
   double exp_c1, exp_c2;    // MCMCB_EXP_C1L / C2L: see mcmcb_expmul_fast for why they travel as parameters
+  int exp_dn;               // entries of the direct exp table staged behind the blob (0 = none), mcmcb_expmul_direct
 };
 
 __host__ __device__ constexpr int pk(int i, int j) { return j * (j + 1) / 2 + i; }  // i <= j
@@ -882,22 +883,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
 
-  // dynamic shared memory: [exp2 table, 16 KB][model blob (when it fits)]
+  // dynamic shared memory: [exp2 table, 16 KB][model blob (when it fits)][direct exp table, exp_dn entries]
   double* exp_tab = reinterpret_cast<double*>(smem_raw);
   mcmcb_stage_exp_table(exp_tab);
+  double* exp_direct = reinterpret_cast<double*>(smem_raw + MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? p.blob_bytes : 0u));
+  if (p.exp_dn > 0) mcmcb_stage_exp_direct(exp_direct, p.exp_dn);
   const double* data = p.blob;
   if (SMEM) {
     unsigned char* blob_s = smem_raw + MCMCB_EXP_TAB_DOUBLES * sizeof(double);
     tma_stage_blob(blob_s, p.blob, p.blob_bytes, &mbar);  // contains a __syncthreads()
     data = reinterpret_cast<const double*>(blob_s);
-  } else {
-    __syncthreads();
   }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, gl = lane % L;
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = gl; ctx.nlanes = L;
   ctx.exp_tl = mcmcb_exp_column(exp_tab); ctx.exp_c1 = p.exp_c1; ctx.exp_c2 = p.exp_c2; ctx.scratch = nullptr;
+  ctx.exp_dn = p.exp_dn;
+  ctx.exp_td = p.exp_dn > 0 ? mcmcb_exp_direct_base(exp_direct, p.exp_dn) : 0u;
 
   const long long t4 = p.tier[0], t2 = p.tier[1], t1 = p.tier[2];
   for (;;) {

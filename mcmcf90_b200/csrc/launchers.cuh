@@ -270,6 +270,14 @@ struct K1 {
   static int launch_LS(mcmcb_handle h, const K1Params& p) {
     auto kern = k1_step_kernel<M, L, SMEM, EREXIT, B>;
     size_t smem = MCMCB_EXP_TAB_DOUBLES * sizeof(double) + (SMEM ? h->blob_bytes : 0);
+    // the shared memory left over holds the direct exp table (mcmcb_expmul_direct): up to 8192 entries = arguments down
+    // to -2.77; models whose arguments leave its range use the masked 2048-entry table
+    int exp_dn = 0;
+    if (h->k1_exp_direct && smem + 2048 < h->max_smem) {
+      exp_dn = (int)std::min<size_t>(8192, (h->max_smem - 1024 - smem) / sizeof(double)) & ~255;
+      if (exp_dn < 2048) exp_dn = 0;
+    }
+    smem += sizeof(double) * (size_t)exp_dn;
     if (!h->attr_set) {
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
@@ -288,6 +296,7 @@ struct K1 {
     // tile plan: full rounds of B-sub-tile tiles while every warp still gets one, then one last round of smaller
     // tiles sized to what is left per warp
     K1Params q = p;
+    q.exp_dn = exp_dn;
     const long long W = blocks * wpb;
     long long n4 = 0, n2 = 0, n1 = 0, rem = subs;
     if (B >= 4) { n4 = (rem / (4 * W)) * W; rem -= 4 * n4; }

@@ -34,32 +34,21 @@ struct ExpReg {
                                                        double* ss) {
     ss_impl<true>(theta, c, sscrit, ss);
   }
-  // B parameter vectors (theta[b*npar + k]) in one sweep over the data, thread per chain: every datum read from
-  // shared memory serves B chains.  Per chain the operations and their order are those of ssfunction.
-  template <int B>
-  __device__ __forceinline__ static void ssfunction_batch(const double* theta, int npar, int ny, const mcmcb_ctx& c,
-                                                          double* ss) {
+  // one exponential of the data loop: through the direct table (mcmcb_expmul_direct) when the evaluation's whole
+  // argument range fits it, else through the masked 2048-entry table -- bit-identical results either way
+  template <bool DIRECT>
+  __device__ __forceinline__ static double ex(double x, double ks, const mcmcb_ctx& c, double c1, double c2) {
+    if constexpr (DIRECT) return mcmcb_expmul_direct(x, ks, c.exp_td, c1, c.exp_dn);
+    else return mcmcb_expmul_fast(x, ks, c.exp_tl, c1, c2);
+  }
+  template <int B, bool DIRECT>
+  __device__ __forceinline__ static void batch_loop(const double (&t1)[B], const double (&ks)[B], const mcmcb_ctx& c,
+                                                    double (&acc)[B]) {
     const int n = (int)c.data[0];
     const int npad = (n + 1) & ~1;
     const double* __restrict__ x = c.data + 2;
     const double* __restrict__ y = c.data + 2 + npad;
-    const unsigned tl = c.exp_tl;
     const double c1 = c.exp_c1, c2 = c.exp_c2;
-    double t1[B], ks[B], acc[B];
-    bool fast = tl != 0u && c.nlanes == 1;
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-      t1[b] = theta[b * npar];
-      const double nt2 = -theta[b * npar + 1];
-      fast = fast && fabs(nt2) * c.data[1] < 700.0;
-      ks[b] = mcmcb_expmul_scale(nt2);
-      acc[b] = 0.0;
-    }
-    if (!__all_sync(0xffffffffu, fast)) {  // rare: some exponent leaves the fast range -- one chain at a time
-#pragma unroll
-      for (int b = 0; b < B; b++) ssfunction(theta + b * npar, npar, ny, c, ss + b * NY);
-      return;
-    }
     constexpr int U = (8 / B) < 2 ? 2 : (8 / B);  // data per trip: B*U exponentials in flight
     int i = 0;
     for (; i + U - 1 < n; i += U) {
@@ -73,7 +62,7 @@ struct ExpReg {
 #pragma unroll
       for (int b = 0; b < B; b++)
 #pragma unroll
-        for (int u = 0; u < U; u++) e[b][u] = mcmcb_expmul_fast(xv[u], ks[b], tl, c1, c2);
+        for (int u = 0; u < U; u++) e[b][u] = ex<DIRECT>(xv[u], ks[b], c, c1, c2);
 #pragma unroll
       for (int b = 0; b < B; b++)
 #pragma unroll
@@ -86,10 +75,37 @@ struct ExpReg {
       const double xi = x[i], yi = y[i];
 #pragma unroll
       for (int b = 0; b < B; b++) {
-        const double r = fma(-t1[b], mcmcb_expmul_fast(xi, ks[b], tl, c1, c2), yi);
+        const double r = fma(-t1[b], ex<DIRECT>(xi, ks[b], c, c1, c2), yi);
         acc[b] = fma(r, r, acc[b]);
       }
     }
+  }
+  // B parameter vectors (theta[b*npar + k]) in one sweep over the data, thread per chain: every datum read from
+  // shared memory serves B chains.  Per chain the operations and their order are those of ssfunction.
+  template <int B>
+  __device__ __forceinline__ static void ssfunction_batch(const double* theta, int npar, int ny, const mcmcb_ctx& c,
+                                                          double* ss) {
+    const unsigned tl = c.exp_tl;
+    const double xmax = fabs(c.data[1]);
+    double t1[B], ks[B], acc[B];
+    bool fast = tl != 0u && c.nlanes == 1;
+    bool direct = c.exp_td != 0u && !(c.data[1] < 0.0);  // blob[1] < 0: some x is negative (blob_expreg)
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      t1[b] = theta[b * npar];
+      const double nt2 = -theta[b * npar + 1];
+      fast = fast && fabs(nt2) * xmax < 700.0;
+      direct = direct && nt2 <= 0.0 && mcmcb_exp_direct_ok(nt2, xmax, c.exp_dn);
+      ks[b] = mcmcb_expmul_scale(nt2);
+      acc[b] = 0.0;
+    }
+    if (!__all_sync(0xffffffffu, fast)) {  // rare: some exponent leaves the fast range -- one chain at a time
+#pragma unroll
+      for (int b = 0; b < B; b++) ssfunction(theta + b * npar, npar, ny, c, ss + b * NY);
+      return;
+    }
+    if (__all_sync(0xffffffffu, direct)) batch_loop<B, true>(t1, ks, c, acc);
+    else batch_loop<B, false>(t1, ks, c, acc);
 #pragma unroll
     for (int b = 0; b < B; b++) ss[b * NY] = acc[b];
   }
@@ -100,19 +116,27 @@ struct ExpReg {
     const double* __restrict__ x = c.data + 2;
     const double* __restrict__ y = c.data + 2 + npad;
     const double t1 = theta[0], nt2 = -theta[1];
-    const unsigned tl = c.exp_tl;  // this thread's column of the replicated 2^(j/256) table
+    const unsigned tl = c.exp_tl;  // shared-window address of the staged 2^(j/2048) table
     const double c1 = c.exp_c1, c2 = c.exp_c2;
     double acc = 0.0;
     int i = c.lane;
     const int step = c.nlanes;
-    // blob[1] = max|x| (set by blob_expreg): one range test per evaluation instead of one per
+    // blob[1] = +-max|x| (set by blob_expreg): one range test per evaluation instead of one per
     // datum decides whether every exponent is inside mcmcb_exp_fast's range
-    const bool fast = tl != 0u && fabs(nt2) * c.data[1] < 700.0;
+    const double xmax = fabs(c.data[1]);
+    const bool fast = tl != 0u && fabs(nt2) * xmax < 700.0;
     const double ks = mcmcb_expmul_scale(nt2);
     // the vote is a warp-wide operation: only when every lane of the warp runs the fast loop
     const bool vote = ER && __all_sync(0xffffffffu, fast);
     if (fast) {
       if (step == 1) {
+        const bool direct = c.exp_td != 0u && !(c.data[1] < 0.0) && nt2 <= 0.0 && mcmcb_exp_direct_ok(nt2, xmax, c.exp_dn);
+        if (!ER && __all_sync(0xffffffffu, direct)) {
+          double t1a[1] = {t1}, ksa[1] = {ks}, acca[1] = {0.0};
+          batch_loop<1, true>(t1a, ksa, c, acca);  // the same operations in the same order as the loop below
+          ss[0] = acca[0];
+          return;
+        }
         // one lane owns the whole chain: consecutive data, 16-byte shared loads, 8 exps in flight
         for (; i + 7 < n; i += 8) {
           if (ER && vote && (i & 127) == 0 && __all_sync(0xffffffffu, acc >= sscrit)) { i = n; break; }

@@ -65,6 +65,7 @@ struct mcmcb_handle_s {
   double* d_hist = nullptr;  // AP window ring of the register kernel (adapthist > 1)
   int hist_rows = 0;
   bool er_exit = false;  // method 'er': run the early-exit kernel (MCMCB_ER_EXIT=1)
+  bool k1_exp_direct = true;  // stage the direct exp table in the shared memory left over (MCMCB_EXP_DIRECT=0: off)
   int k1_batch = 1;  // chains per thread of the register kernel (thread-per-chain mapping only)
   unsigned* d_tile = nullptr;
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]

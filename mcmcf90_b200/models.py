@@ -5,14 +5,16 @@ import numpy as np
 
 
 def blob_expreg(x, y):
-    """[n, max|x|, x[npad], y[npad]] for y = theta1*exp(-theta2*x) (testcases/mcmcrun.F90:104)."""
+    """[n, +-max|x| (negative when some x < 0), x[npad], y[npad]] for y = theta1*exp(-theta2*x) (testcases/mcmcrun.F90:104)."""
     x = np.asarray(x, dtype=np.float64).ravel()
     y = np.asarray(y, dtype=np.float64).ravel()
     n = x.size
     npad = (n + 1) & ~1
     b = np.zeros(2 + 2 * npad)
     b[0] = n
-    b[1] = np.abs(x).max() if n else 0.0  # lets the device model range-check once per evaluation
+    # +-max|x|, negative when some x is negative: lets the device model range-check once per evaluation and know
+    # the sign of its exponents (mcmcb_expmul_direct)
+    b[1] = (np.abs(x).max() if n else 0.0) * (-1.0 if n and x.min() < 0.0 else 1.0)
     b[2:2 + n] = x
     b[2 + npad:2 + npad + n] = y
     return b

@@ -119,7 +119,9 @@ def blob_expreg(x, y):
     npad = (n + 1) & ~1
     b = np.zeros(2 + 2 * npad)
     b[0] = n
-    b[1] = np.abs(x).max() if n else 0.0  # lets the device model range-check once per evaluation
+    # +-max|x|, negative when some x is negative: lets the device model range-check once per evaluation and know
+    # the sign of its exponents (mcmcb_expmul_direct)
+    b[1] = (np.abs(x).max() if n else 0.0) * (-1.0 if n and x.min() < 0.0 else 1.0)
     b[2:2 + n] = x
     b[2 + npad:2 + npad + n] = y
     return b
