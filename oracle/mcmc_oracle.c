@@ -2,8 +2,13 @@
  * mcmc_oracle.c -- CPU restatement of mcmcf90's sampling hot path (see mcmc_oracle.h).
  *
  * TEST INFRASTRUCTURE ONLY -- never linked into the product library.
- * PARITY UNPINNED (no Fortran compiler here, no golden vectors in the reference);
- * pinned by analytic known answers, scipy LAPACK cross-checks and identities.
+ * PARITY: NOT pinned to a run of the Fortran reference (no Fortran compiler here or on the GPU box --
+ * profiles/r02_probe_fortran.txt -- and the reference ships no expected outputs).  Pinned instead by
+ * (1) an independent second restatement of the Fortran (oracle/restate_np.py, real BLAS/LAPACK through scipy):
+ * identical chain indices / counters / draws consumed and values to 1e-9 on every sampler
+ * (tests/test_ref_parity.py), (2) the reference's one binary fixture testcases/data.mat, (3) analytic known
+ * answers, scipy LAPACK cross-checks and identities (tests/test_oracle_pins.py).  oracle/Makefile.ref builds the
+ * reference itself against the injected stream wherever gfortran exists.
  *
  * All citations are file:line into /root/reference.  Arrays are column-major with
  * 1-based Fortran indices mapped through the IDX macro so that loops read like the

@@ -5,10 +5,12 @@
  * this file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs use it, and only as the checker / reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (Fortran 90 + F77) cannot be compiled in this image
- * (no Fortran compiler) and ships no golden vectors, known-answer tests or expected
- * outputs.  This restatement follows the reference line by line
- * (citations are file:line into /root/reference) and is pinned only by (a) analytic
+ * PARITY NOT PINNED TO A RUN OF THE REFERENCE: the reference (Fortran 90 + F77) cannot be compiled in this image
+ * or on the GPU box (no Fortran compiler; profiles/r02_probe_fortran.txt) and ships no golden vectors,
+ * known-answer tests or expected outputs.  This restatement follows the reference line by
+ * line (citations are file:line into /root/reference) and is pinned by (0) an independent second restatement
+ * of the Fortran, oracle/restate_np.py (numpy + real BLAS/LAPACK), which must reproduce its chain indices, counters
+ * and draw counts exactly and its values to 1e-9 on every sampler (tests/test_ref_parity.py); (a) analytic
  * known answers for the shipped testcase, (b) scipy's LAPACK/BLAS (the same third-party
  * routines the reference links: dpotrf, dpotri, dtrmv, dsymv, dgemv, drotg, dnrm2),
  * (c) mathematical identities (R'R == C +/- xx' for dchud/dchdd, distribution moments

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  Never imported by mcmcf90_b200/.
-PARITY UNPINNED -- see the header of mcmc_oracle.h.
+Parity status (not pinned to a run of the Fortran; pinned by oracle/restate_np.py) -- see the header of mcmc_oracle.h.
 """
 import ctypes as C
 import os
