@@ -1,21 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- chain-steps/s of the batched adaptive-MH hot path on the BASELINE config C3.
+"""bench.py -- chain-steps/s of the batched adaptive-MH hot path on the BASELINE configurations.
 
-Workload (BASELINE.json configs[2], the config the whole-box target is quoted on; SURVEY.md
-8d): 2^20 independent DRAM+AM chains PER GPU (weak scaling) on the exponential-regression
-model y = th1*exp(-th2*x) with ndata = 10^4 observations staged in shared memory,
-drscale=2, adaptint=100, initcmatn=1, sigma2 Gibbs update on.  One bench "step" = one pass
-of the hot path = ONE kernel launch advancing every chain by 100 MCMC iterations
-(one adaptation interval).  Data are synthetic (seeded); FP64 throughout.
+  python bench.py --gpus N --steps K --warmup W [--workload c3|c2|c4|c5|c1] [--scaling weak|strong]
+  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference (oracle/)
 
-  python bench.py --gpus N --steps K --warmup W            # this framework
-  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference
+Default workload = BASELINE.json configs[2] ("C3", the config the whole-box target is quoted on):
+2^20 independent DRAM+AM chains PER GPU (weak scaling) on the exponential-regression model with ndata = 10^4
+observations staged in shared memory, drscale=2, adaptint=100, initcmatn=1, sigma2 Gibbs update on.  One bench "step"
+= one pass of the hot path over every chain = `mcmcb_run(h, iters)` with iters = one adaptation interval (C3: ONE
+kernel launch advancing every chain by 100 MCMC iterations).  The other workloads are the remaining BASELINE
+configurations at their stated sizes:
+  c2  4096 DRAM chains, 100-dim correlated Gaussian            (k2_step_kernel + k2_adapt_kernel)
+  c4  65536 RAM chains, 50-dim banana, POOLED shape matrix: one allreduce pair per 100 steps inside the timed region
+  c5  262144 SCAM chains, 200-parameter hierarchical model, POOLED rotation (one allreduce pair per 100 sweeps)
+  c1  the reference's own testcase (11 data) batched as 2^22 chains
+--scaling weak: the stated chain count per GPU; strong: the stated count in total, sharded over the GPUs.
+Data are synthetic (seeded); FP64 throughout.
 
-`value`  : device-timed (CUDA events on the kernel's stream, max over ranks), state resident in HBM.
-`e2e`    : same metric through the C ABI with HOST buffers: per step H2D of every chain's start
-           point (pinned), the kernel, D2H of theta/mean/cov/counters.
+`value`  : device-timed (CUDA events on the kernels' stream, max over ranks), state resident in HBM.
+`e2e`    : the same metric through the C ABI with HOST buffers: every step uploads every chain's start point
+           (pinned) and the proposal covariance, runs the same number of iterations and downloads theta / mean /
+           covariance / counters of every chain into pinned host buffers.  The start state is the steady state of the
+           device-timed chains (their last points and their mean adapted covariance), so the work mix (stage-2 rate)
+           is the one `value` times.
+`roofline.traffic` and the hardware FP64 count come from the committed ncu capture profiles/r02_ncu_<workload>.json
+(scripts/ncu_profile.py), which records the hash of the CUDA sources it was taken from: a capture of other sources is
+reported as stale and its numbers are NOT used.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -27,33 +41,142 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-NDATA = 10000
-MCMC_PER_STEP = 100
-NML = dict(adaptint=100, drscale=2.0, initcmatn=1, doburnin=0, burnintime=0, updatesigma=1, N0=1.0, S02=0.5)
 SEED = 2024
-PAR0 = np.array([10.0, 0.1])
-CMAT0 = np.diag([0.2, 0.001]) * (11.0 / NDATA)
 
 
-def synth_data():
-    rng = np.random.default_rng(SEED)
-    x = 10.0 * np.arange(NDATA) / (NDATA - 1)
-    y = 10.0 * np.exp(-0.1 * x) + rng.normal(0.0, np.sqrt(0.5), NDATA)
-    return x, y
+def source_hash():
+    """Identity of the CUDA sources the library is built from (profiles are keyed by it)."""
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "mcmcf90_b200", "csrc", "*.cu*")) +
+                   glob.glob(os.path.join(ROOT, "mcmcf90_b200", "csrc", "*.h")) +
+                   glob.glob(os.path.join(ROOT, "include", "*")))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
-def start_points(n, offset):
-    """par0 = (10, 0.1) with 1% jitter per chain, keyed by the global chain id block."""
-    rng = np.random.default_rng([SEED, offset])
-    return PAR0 * (1.0 + 0.01 * rng.standard_normal((n, 2)))
+def load_profile(workload):
+    """Committed ncu capture of this workload's dominant kernel, or (None, reason)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_%s.json" % workload)
+    if not os.path.exists(p):
+        return None, "no capture committed (%s)" % os.path.relpath(p, ROOT)
+    d = json.load(open(p))
+    if d.get("source_hash") != source_hash():
+        return None, "STALE capture: taken from sources %s, library sources are %s -- re-run scripts/ncu_profile.py" % (
+            d.get("source_hash"), source_hash())
+    return d, os.path.relpath(p, ROOT)
 
 
-def flops_per_chain_step(q, rows_per_step, d=2, n=NDATA, adaptint=100):
-    """Algorithmic FP64 flops of one DRAM/AM chain-step (exp counted as 1)."""
-    f_prop, f_ss, f_q1, f_alpha = d * (d + 1), 6 * n, 4 * d * d + 6 * d, 12
-    f_adapt = 5 * d * d * rows_per_step * adaptint + d ** 3 / 3 + 2 * d ** 3 / 3
-    return (1 + q) * (f_prop + f_ss + 3 * d) + q * f_q1 + (1 + q) * f_alpha + f_adapt / adaptint
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 7700.0 * 0.85}, "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE configuration as concrete synthetic inputs."""
+
+    def __init__(self, name):
+        self.name = name
+        getattr(self, "_" + name)()
+
+    def _c3(self):
+        n = 10000
+        rng = np.random.default_rng(SEED)
+        x = 10.0 * np.arange(n) / (n - 1)
+        y = 10.0 * np.exp(-0.1 * x) + rng.normal(0.0, np.sqrt(0.5), n)
+        self.desc = "C3: DRAM+AM chains on exp-regression, ndata=%d in shared memory" % n
+        self.model, self.oracle_model, self.blob_args = "expreg", "MODEL_EXPREG", ("blob_expreg", (x, y))
+        self.d, self.ndata, self.chains, self.iters = 2, n, 1 << 20, 100
+        self.nml = dict(adaptint=100, drscale=2.0, initcmatn=1, doburnin=0, burnintime=0, updatesigma=1, N0=1.0, S02=0.5)
+        self.cmat0, self.sigma2, self.nobs = np.diag([0.2, 0.001]) * (11.0 / n), [0.5], [n]
+        self.par0 = lambda nn, off: np.array([10.0, 0.1]) * (1.0 + 0.01 * np.random.default_rng([SEED, off]).standard_normal((nn, 2)))
+        self.pool, self.bound = 0, "fp64"
+        self.kernel = "k1_step_kernel"
+
+    def _c1(self):
+        x = np.arange(11.0)
+        y = np.array([9.33, 9.40, 8.99, 7.06, 7.13, 6.69, 4.69, 4.24, 4.77, 3.86, 4.02])
+        self.desc = "C1 batched: testcases/data.dat model (11 data), DRAM+AM"
+        self.model, self.oracle_model, self.blob_args = "expreg", "MODEL_EXPREG", ("blob_expreg", (x, y))
+        self.d, self.ndata, self.chains, self.iters = 2, 11, 1 << 22, 100
+        self.nml = dict(adaptint=100, drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.0)
+        self.cmat0, self.sigma2, self.nobs = np.diag([0.2, 0.001]), [0.5], [11]
+        self.par0 = lambda nn, off: np.tile([10.0, 0.1], (nn, 1))
+        self.pool, self.bound = 0, "fp64"
+        self.kernel = "k1_step_kernel"
+
+    def _c2(self):
+        d, rho = 100, 0.9
+        sd = 1.0 + 9.0 * np.arange(d) / (d - 1)
+        sig = rho ** np.abs(np.subtract.outer(np.arange(d), np.arange(d))) * np.outer(sd, sd)
+        lam = np.linalg.inv(sig)
+        self.desc = "C2: DRAM chains on a 100-dim correlated Gaussian target (private Cholesky factor per chain)"
+        self.model, self.oracle_model, self.blob_args = "gauss", "MODEL_GAUSS", ("blob_gauss", (np.zeros(d), 0.5 * (lam + lam.T)))
+        self.d, self.ndata, self.chains, self.iters = d, 0, 4096, 200
+        self.nml = dict(adaptint=200, drscale=2.0, initcmatn=1, updatesigma=0)
+        self.cmat0, self.sigma2, self.nobs = 0.01 * np.eye(d), [1.0], [1]
+        self.par0 = lambda nn, off: np.zeros((nn, d))
+        self.pool, self.bound = 0, "hbm"
+        self.kernel = "k2_step_kernel"
+
+    def _c4(self):
+        d = 50
+        self.desc = "C4: RAM chains on the 50-dim banana target, shape matrices pooled (averaged over ALL chains) every 100 steps"
+        self.model, self.oracle_model, self.blob_args = "banana", "MODEL_BANANA", ("blob_banana", (d, 0.03))
+        self.d, self.ndata, self.chains, self.iters = d, 0, 65536, 100
+        self.nml = dict(method="ram", adaptint=100, updatesigma=0, alphatarget=0.234, nuparam=0.7)
+        self.cmat0, self.sigma2, self.nobs = np.eye(d), [1.0], [1]
+        self.par0 = lambda nn, off: np.zeros((nn, d))
+        self.pool, self.bound = 1, "hbm"
+        self.kernel = "k2_step_kernel"
+
+    def _c5(self):
+        groups, per = 198, 10
+        rng = np.random.default_rng(5)
+        y = rng.normal(size=(groups, 1)) + rng.normal(size=(groups, per))
+        d = groups + 2
+        self.desc = ("C5: SCAM chains on the 200-parameter hierarchical model (1980 observations), ONE pooled rotation for all "
+                     "chains rebuilt every 100 sweeps; one step = a sweep over the 200 components")
+        self.model, self.oracle_model, self.blob_args = "hier", "MODEL_HIER", ("blob_hier", (y,))
+        self.d, self.ndata, self.chains, self.iters = d, groups * per, 262144, 100
+        self.nml = dict(method="scam", adaptint=100, initcmatn=1, updatesigma=0)
+        self.cmat0, self.sigma2, self.nobs = 0.1 * np.eye(d), [1.0], [1]
+        self.par0 = lambda nn, off: np.zeros((nn, d))
+        self.pool, self.bound = 1, "fp64"
+        self.kernel = "k3_scam_step_kernel"
+
+    def blob(self, mod):
+        return getattr(mod, self.blob_args[0])(*self.blob_args[1])
+
+    # ---- algorithmic work per chain-step, SURVEY.md 8d
+    def flops_per_step(self, q, rows_per_step):
+        d, n = self.d, self.ndata
+        if self.name in ("c3", "c1"):
+            f_prop, f_ss, f_q1, f_alpha = d * (d + 1), 6 * n, 4 * d * d + 6 * d, 12
+            f_adapt = 5 * d * d * rows_per_step * self.nml["adaptint"] + d ** 3 / 3 + 2 * d ** 3 / 3
+            return (1 + q) * (f_prop + f_ss + 3 * d) + q * f_q1 + (1 + q) * f_alpha + f_adapt / self.nml["adaptint"]
+        if self.name == "c5":  # SCAM, minimal form: d component moves, each one full ssfunction
+            return d * (2 * d + (6 * n + 5 * d) + 12)
+        return None
+
+    def hbm_bytes_per_step(self, q):
+        d = self.d
+        tri = d * (d + 1) // 2
+        if self.name == "c2":
+            return 8 * (tri * (1 + q) + 3 * d + 10)       # the factor is read once per proposal (1+q per step)
+        if self.name == "c4":
+            return 16 * tri + 8 * (3 * d + 10)             # RAM: the factor is read and rewritten every step
+        return None
+
+    def units_note(self):
+        return {"c3": "F_step = (1+q)(d(d+1)+6n+3d) + q(4d^2+6d) + 12(1+q) + F_adapt/adaptint, exp counted as 1 flop",
+                "c1": "as c3 with n = 11", "c5": "F_step = d (2d + 6n + 5d + 12), one sweep over d components",
+                "c2": "bytes/step = 8 (d(d+1)/2 (1+q) + 3d + 10): private factor read once per proposal",
+                "c4": "bytes/step = 16 d(d+1)/2 + 8 (3d + 10): private factor read and rewritten every step"}[self.name]
 
 
 class ClockSampler:
@@ -103,169 +226,100 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-# --------------------------------------------------------------------------- reference arm
-def cpu_baseline(cores, target_seconds=15.0, chains_per_core=4):
-    """The oracle (C restatement of the reference, 'port') timed on the host cores: one chain
-    per thread at a time (the reference is one chain per process)."""
+def workload_config(W, args, chains_per_gpu, scaling):
+    return {"workload": W.desc, "chains_per_gpu": int(chains_per_gpu), "mcmc_iterations_per_step": int(W.iters), "npar": W.d,
+            "namelist": W.nml, "rng": "philox4x32-10", "scaling_mode": scaling,
+            "parallelism": ("chains sharded over GPUs; pooled adaptation: 2 NCCL allreduces per %d iterations" % W.nml["adaptint"])
+            if W.pool else "chains sharded over GPUs, no collective",
+            "l2": "per-chain state exceeds L2 (no flush needed)" if W.name != "c2" else
+                  "4096 private 40 KB factors = 164 MB exceed L2; 3-step warm-up"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_rate(W, cores, nch, nsimu, native):
     from oracle import oracle as O
-    x, y = synth_data()
-    blob = O.blob_expreg(x, y)
+    O.use_native(native)
+    cfg = O.make_cfg(nsimu=nsimu, **W.nml)
+    out = O.run_batch(cfg, getattr(O, W.oracle_model), W.blob(O), W.par0(nch, 0), W.cmat0, W.sigma2, W.nobs, seed=SEED,
+                      chain0=0, nthreads=cores)
+    return nch * (nsimu - 1) / max(out["seconds"], 1e-9), out["seconds"]
+
+
+def cpu_baseline(W, cores, target_seconds=12.0, chains_per_core=4):
+    """The oracle (C restatement of the reference, 'port') timed on the host cores: one chain per thread at a time
+    (the reference is one chain per process).  Two builds: the reference's own flags (-O2, no -march,
+    linux64.mk:38) and -O3 -march=native; the faster one is the reported value."""
     nch = cores * chains_per_core
-
-    def run(nsimu):
-        cfg = O.make_cfg(nsimu=nsimu, **NML)
-        out = O.run_batch(cfg, O.MODEL_EXPREG, blob, start_points(nch, 0), CMAT0, [0.5], [NDATA], seed=SEED,
-                          chain0=0, nthreads=cores)
-        return out["seconds"]
-
-    t = run(51)  # calibration
-    rate = nch * 50 / max(t, 1e-6)
-    nsimu = int(max(101, min(200000, target_seconds * rate / nch))) + 1
-    sec = run(nsimu)
-    return nch * (nsimu - 1) / sec, "%d chains x %d MCMC steps of C3 (ndata=%d), %d threads, %.1f s" % (
-        nch, nsimu - 1, NDATA, cores, sec)
+    res = {}
+    for native in (False, True):
+        rate, _ = oracle_rate(W, cores, nch, 21, native)  # calibration
+        nsimu = int(max(41, min(200000, 0.5 * target_seconds * rate / nch))) + 1
+        rate, sec = oracle_rate(W, cores, nch, nsimu, native)
+        res[native] = (rate, "%d chains x %d MCMC steps of %s, %d threads, %.1f s" % (nch, nsimu - 1, W.name.upper(), cores, sec))
+    best = max(res, key=lambda k: res[k][0])
+    return {"value": res[best][0], "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": res[best][1],
+            "flags": "-O3 -march=native" if best else "-O2 -ffp-contract=off (reference flags, linux64.mk:38)",
+            "value_reference_flags": res[False][0], "value_march_native": res[True][0],
+            "note": ("C restatement of the reference (oracle/); no Fortran compiler on this box; pooled workloads: the CPU "
+                     "chains adapt on their own (the reference has no pooling)") if W.pool else
+                    "C restatement of the reference (oracle/); no Fortran compiler on this box"}
 
 
 def run_reference(args):
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_env()
     if rank != 0:
         return 0
-    from oracle import oracle as O
+    W = Workload(args.workload)
     cores = os.cpu_count() or 1
-    x, y = synth_data()
-    blob = O.blob_expreg(x, y)
-    nch, msteps = 8 * cores, 500  # bounded sample of one C3 step per bench step
-    cfg = O.make_cfg(nsimu=msteps + 1, **NML)
-    par0 = start_points(nch, 0)
+    from oracle import oracle as O
+    O.use_native(True)
+    nch = 8 * cores
+    rate, _ = oracle_rate(W, cores, nch, 11, True)
+    msteps = int(max(10, min(5000, 8.0 * rate / nch)))  # ~8 s per bench step
+    cfg = O.make_cfg(nsimu=msteps + 1, **W.nml)
+    par0, blob = W.par0(nch, 0), W.blob(O)
     times = []
     for it in range(args.warmup + args.steps):
-        out = O.run_batch(cfg, O.MODEL_EXPREG, blob, par0, CMAT0, [0.5], [NDATA], seed=SEED + it, chain0=0,
+        out = O.run_batch(cfg, getattr(O, W.oracle_model), blob, par0, W.cmat0, W.sigma2, W.nobs, seed=SEED + it, chain0=0,
                           nthreads=cores)
         if it >= args.warmup:
             times.append(out["seconds"])
     total = sum(times)
     value = nch * msteps * args.steps / total
-    sample = "%d chains x %d MCMC steps per step on %d host threads (bounded sample of the 2^20-chain step)" % (
-        nch, msteps, cores)
+    sample = "%d chains x %d MCMC steps per step on %d host threads (bounded sample of the %d-chain step)" % (
+        nch, msteps, cores, W.chains)
     line = {
         "impl": "reference", "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(W, args, W.chains, args.scaling),
+        "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "flags": "-O3 -march=native"},
         "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C restatement of the reference (oracle/): the Fortran reference cannot be built here (no Fortran compiler)",
+        "note": "C restatement of the reference (oracle/): the Fortran reference cannot be built here or on the GPU box "
+                "(no Fortran compiler, profiles/r02_probe_fortran.txt)",
     }
     print(json.dumps(line))
     return 0
 
 
-def other_workloads(mb, torch, dev):
-    """Short device-timed runs of the other BASELINE configurations' shapes (C2, C4, C5: the large-npar kernels) on this
-    GPU.  Not part of the headline metric: reported beside it so that every configuration has a measured number in
-    the bench record.  Algorithmic HBM bytes per step as in SURVEY.md 8d (private factor per chain)."""
-    def gauss_target(d, rho=0.9):
-        sd = 1.0 + 9.0 * np.arange(d) / max(d - 1, 1)
-        sig = rho ** np.abs(np.subtract.outer(np.arange(d), np.arange(d))) * np.outer(sd, sd)
-        lam = np.linalg.inv(sig)
-        return np.zeros(d), 0.5 * (lam + lam.T)
-
-    def timeit(label, cfg_kw, model, blob, d, n, steps, cmat0, bytes_per_step):
-        s = mb.Sampler(mb.default_config(nchains=n, seed=12345, model=model, device=dev, **cfg_kw))
-        s.set_data(blob)
-        s.set_initial(np.zeros(d), cmat0, [1.0], [1])
-        s.run(steps)  # warm-up incl. the initial evaluation
-        st = torch.cuda.ExternalStream(s.stream, device=dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        best = None
-        for _ in range(3):
-            c0 = s.counters()
-            e0.record(st)
-            s.run(steps, sync=False)
-            e1.record(st)
-            s.sync()
-            ms = e0.elapsed_time(e1)
-            c1 = s.counters()
-            if best is None or ms < best[0]:
-                best = (ms, float((c1["drtries"] - c0["drtries"]).sum()) / (n * steps), int((c1["status"] != 0).sum()))
-        info = s.info()
-        s.close()
-        ms, q, bad = best
-        rate = n * steps / ms * 1e3
-        return {"workload": label, "npar": d, "chains": n, "iterations_timed": steps, "ms": ms, "chain_steps_per_s": rate,
-                "stage2_rate_q": q, "algorithmic_hbm_bytes_per_step": bytes_per_step(q),
-                "algorithmic_GBps": rate * bytes_per_step(q) / 1e9, "threads_per_chain": info["lanes_per_chain"],
-                "chains_with_error_status": bad}
-
-    out = []
-    # C1 batched: the reference's own testcase (11 data) run as 2^22 chains -- the small-ndata end of the metric
-    x11 = np.arange(11.0)
-    y11 = np.array([9.33, 9.40, 8.99, 7.06, 7.13, 6.69, 4.69, 4.24, 4.77, 3.86, 4.02])
-    n1 = 1 << 22
-    s = mb.Sampler(mb.default_config(nchains=n1, seed=3, model="expreg", device=dev, nsimu=100000, adaptint=100, drscale=2.0,
-                                     initcmatn=1, updatesigma=1, N0=1.0, S02=0.0))
-    s.set_data(mb.models.blob_expreg(x11, y11))
-    s.set_initial(np.array([10.0, 0.1]), np.diag([0.2, 0.001]), [0.5], [11])
-    s.run(200)
-    st = torch.cuda.ExternalStream(s.stream, device=dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0 = s.counters()
-    e0.record(st)
-    s.run(200, sync=False)
-    e1.record(st)
-    s.sync()
-    c1 = s.counters()
-    ms = e0.elapsed_time(e1)
-    q1 = float((c1["drtries"] - c0["drtries"]).sum()) / (n1 * 200)
-    out.append({"workload": "C1 batched: testcases/data.dat model (11 data), DRAM+AM, 2^22 chains (k1_step_kernel, one chain per "
-                            "thread)", "npar": 2, "chains": n1, "iterations_timed": 200, "ms": ms,
-                "chain_steps_per_s": n1 * 200 / ms * 1e3, "stage2_rate_q": q1,
-                "datum_evals_per_s": n1 * 200 * (1 + q1) * 11 / ms * 1e3, "chains_per_thread": s.info()["chains_per_thread"],
-                "chains_with_error_status": int((c1["status"] != 0).sum())})
-    s.close()
-    d = 100
-    mu, lam = gauss_target(d)
-    tri = d * (d + 1) // 2
-    out.append(timeit("C2: 4096 DRAM chains, 100-dim correlated Gaussian (k2_step_kernel + k2_adapt_kernel at the tick)",
-                      dict(nsimu=100000, adaptint=200, drscale=2.0, initcmatn=1, updatesigma=0), "gauss",
-                      mb.models.blob_gauss(mu, lam), d, 4096, 200, 0.01 * np.eye(d),
-                      lambda q: 8 * (tri * (1 + q) + 3 * d + 10)))
-    d = 50
-    tri = d * (d + 1) // 2
-    out.append(timeit("C4: 65536 RAM chains, 50-dim banana (k2_step_kernel, per-chain factor; pooling off)",
-                      dict(method=mb.RAM, nsimu=100000, updatesigma=0, alphatarget=0.234, nuparam=0.7), "banana",
-                      mb.models.blob_banana(d, 0.03), d, 65536, 100, np.eye(d), lambda q: 16 * tri + 8 * (3 * d + 10)))
-    groups, per = 198, 10
-    d = groups + 2
-    rng = np.random.default_rng(5)
-    y = rng.normal(size=(groups, 1)) + rng.normal(size=(groups, per))
-    out.append(timeit("C5 shape at 2048 chains: SCAM, 200-param hierarchical model (k3_scam_step_kernel; one step = a sweep "
-                      "over the 200 components; per-chain 320 KB rotation)",
-                      dict(method=mb.SCAM, nsimu=100000, adaptint=100, initcmatn=1, updatesigma=0), "hier",
-                      mb.models.blob_hier(y), d, 2048, 20, 0.1 * np.eye(d), lambda q: 8 * (d * d + 3 * d + 10)))
-    return out
-
-
-def workload_config(args):
-    return {"workload": "C3: DRAM+AM chains on exp-regression, ndata=%d in shared memory" % NDATA,
-            "chains_per_gpu": args.chains, "mcmc_iterations_per_step": MCMC_PER_STEP, "npar": 2,
-            "namelist": NML, "rng": "philox4x32-10", "parallelism": "chains sharded over GPUs, no collective",
-            "l2": "per-chain state (~220 MB/GPU) exceeds L2; no flush needed"}
-
-
-# --------------------------------------------------------------------------- this framework
+# ------------------------------------------------------------------------------------------------ this framework
 def run_ours(args):
     import torch
     import mcmcf90_b200 as mb
+    from mcmcf90_b200 import parallel
 
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_env()
+    W = Workload(args.workload)
+    if args.iters:
+        W.iters = args.iters
+    single_process = world == 1 and args.gpus > 1  # one handle drives all GPUs of the box (mcmcb_config.ngpus)
+    G = args.gpus if single_process else 1
+    ngpus_total = world * G
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -274,26 +328,39 @@ def run_ours(args):
         dist = None
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
-    N = args.chains
+    if args.chains:
+        per_gpu = args.chains
+    elif args.scaling == "strong":
+        per_gpu = W.chains // ngpus_total
+    else:
+        per_gpu = W.chains
+    N = per_gpu * G                   # chains of this process
     offset = rank * N
-    x, y = synth_data()
-    blob = mb.models.blob_expreg(x, y)
-    nsimu = 1 + MCMC_PER_STEP * (2 * (args.warmup + args.steps) + 8)
-    cfg = mb.default_config(nchains=N, chain_offset=offset, seed=SEED, device=dev, nsimu=nsimu, model="expreg",
-                            lanes_per_chain=args.lanes, **NML)
+    blob = W.blob(mb.models)
+    nsimu = 1 + W.iters * (2 * (args.warmup + args.steps) + 8)
+    extra = dict(dump_stride=args.dump_stride) if args.dump_stride else {}
+    cfg = mb.default_config(nchains=N, chain_offset=offset, seed=SEED, device=dev, nsimu=nsimu, model=W.model,
+                            lanes_per_chain=args.lanes, pool_adapt=W.pool, ngpus=G, **W.nml, **extra)
     s = mb.Sampler(cfg)
     s.set_data(blob)
-    par0_pinned = torch.empty((N, 2), dtype=torch.float64).pin_memory()
+    par0_pinned = torch.empty((N, W.d), dtype=torch.float64).pin_memory()
     par0 = par0_pinned.numpy()
-    par0[:] = start_points(N, offset)
-    s.set_initial(par0, CMAT0, [0.5], [NDATA])
-    stream = torch.cuda.ExternalStream(s.stream, device=dev)
+    par0[:] = W.par0(N, offset)
+    s.set_initial(par0, W.cmat0, W.sigma2, W.nobs)
+    nccl_world = False
+    if world > 1 and W.pool:
+        nccl_world = parallel.attach(s)
+    streams = [torch.cuda.ExternalStream(s.stream_of(k), device=dev + k) for k in range(G)]
+
+    def sync_all():
+        for k in range(G):
+            torch.cuda.synchronize(dev + k)
 
     def barrier():
-        torch.cuda.synchronize(dev)
+        sync_all()
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize(dev)
+        sync_all()
 
     # FP64 pipe peak, measured on this GPU: burst (best 22 ms run) and sustained (2 s of back-to-back runs)
     burst = mb.dfma_peak(dev)[0]
@@ -302,133 +369,192 @@ def run_ours(args):
         sus.append(mb.dfma_peak(dev)[0])
     sustained = float(np.mean(sus[len(sus) // 2:]))
 
+    dumped = 0
+
+    def drain():  # a consumer of the streamed dumps: pops whatever is complete (host-side transposition included)
+        nonlocal dumped
+        while args.dump_stride and s.dump_pop_ex() is not None:
+            dumped += 1
+
     for _ in range(args.warmup):
-        s.run(MCMC_PER_STEP, sync=False)
+        s.run(W.iters, sync=False)
+        drain()
     s.sync()
+    drain()
     c0 = s.counters()
-    l0 = s.launches
+    l0, n0 = s.launches, s.nccl_calls
     clocks = ClockSampler(dev)
     barrier()
     clocks.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_all0.record(stream)
+
+    def ev():
+        return [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+
+    def rec(es):  # one event per device of the handle, each on that device's kernel stream
+        for k in range(G):
+            with torch.cuda.device(dev + k):
+                es[k].record(streams[k])
+
+    evs = [(ev(), ev()) for _ in range(args.steps)]
+    e_all0, e_all1 = ev(), ev()
+    rec(e_all0)
     for a, b in evs:
-        a.record(stream)
-        s.run(MCMC_PER_STEP, sync=False)
-        b.record(stream)
-    e_all1.record(stream)
+        rec(a)
+        s.run(W.iters, sync=False)
+        rec(b)
+        drain()
+    rec(e_all1)
     s.sync()
     barrier()
     clk = clocks.stop()
-    total_ms = e_all0.elapsed_time(e_all1)
-    launch_ms = [a.elapsed_time(b) for a, b in evs]
+    drain()
+    total_ms = max(e_all0[k].elapsed_time(e_all1[k]) for k in range(G))
+    launch_ms = [max(a[k].elapsed_time(b[k]) for k in range(G)) for a, b in evs]
     launches = s.launches - l0
+    nccl_calls = s.nccl_calls - n0
     c1 = s.counters()
-    done_steps = MCMC_PER_STEP * args.steps
+    done_steps = W.iters * args.steps
     q = float((c1["drtries"] - c0["drtries"]).sum()) / (N * done_steps)
     rows = float((c1["chainind"] - c0["chainind"]).sum()) / (N * done_steps)
     stay = float((c1["stayed"] - c0["stayed"]).sum()) / (N * done_steps)
     status_bad = int((c1["status"] != 0).sum())
 
-    # ---- end to end through the C ABI with host buffers
-    h2d = par0.nbytes + blob.nbytes + CMAT0.nbytes + 8 + 4
-    d2h = 0
-    e2e_sampler = mb.Sampler(mb.default_config(nchains=N, chain_offset=offset, seed=SEED + 1, device=dev,
-                                               nsimu=MCMC_PER_STEP + 1, model="expreg", lanes_per_chain=args.lanes,
-                                               **NML))
-    e2e_sampler.set_data(blob)
-    # results land in pinned host buffers (caller-owned, as the C ABI prescribes)
-    outs = {"par": torch.empty((N, 2), dtype=torch.float64).pin_memory(),
-            "mean": torch.empty((N, 2), dtype=torch.float64).pin_memory(),
-            "cmat": torch.empty((N, 4), dtype=torch.float64).pin_memory(),
-            "counters": torch.empty((N, 8), dtype=torch.int64).pin_memory()}
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for it in range(e2e_steps):
-        e2e_sampler.set_data(blob)                                   # H2D model data
-        e2e_sampler.set_initial(par0, CMAT0, [0.5], [NDATA])         # H2D start points (pinned) + init kernel
-        e2e_sampler.run(MCMC_PER_STEP, sync=False)
-        out = [e2e_sampler.fetch(w, out=t.numpy()) for w, t in outs.items()]  # D2H results
-        d2h = sum(o.nbytes for o in out)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    e2e_sampler.close()
+    # ---- end to end through the C ABI with host buffers, from the steady state of the chains above
+    e2e = None
+    if not args.no_e2e:
+        d = W.d
+        theta_end = s.fetch("par")
+        if W.nml.get("method") == "ram":
+            cov = W.cmat0  # RAM has no running covariance: the continuation starts from the initial shape
+        elif W.pool:
+            cov = s.pool_fetch()[2]  # the pooled covariance of the last tick
+        else:
+            cm = s.fetch("cmat")
+            good = c1["status"] == 0
+            cov = cm[good].mean(axis=0) if good.any() else W.cmat0
+        cov = np.triu(cov) + np.triu(cov, 1).T
+        s.close()
+        s = None
+        e2e_sampler = mb.Sampler(mb.default_config(nchains=N, chain_offset=offset, seed=SEED + 1, device=dev, nsimu=W.iters + 1,
+                                                   model=W.model, lanes_per_chain=args.lanes, pool_adapt=W.pool, ngpus=G, **W.nml))
+        if world > 1 and W.pool:
+            parallel.attach(e2e_sampler)
+        par0[:] = theta_end
+        outs = {"par": torch.empty((N, d), dtype=torch.float64).pin_memory(),
+                "mean": torch.empty((N, d), dtype=torch.float64).pin_memory(),
+                "counters": torch.empty((N, 8), dtype=torch.int64).pin_memory()}
+        if d <= 8:  # per-chain covariance of the small models; the large-npar workloads return the pooled one
+            outs["cmat"] = torch.empty((N, d * d), dtype=torch.float64).pin_memory()
+        h2d = par0.nbytes + blob.nbytes + cov.nbytes + 8 * len(W.sigma2) + 4 * len(W.nobs)
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_sampler.set_data(blob)
+        e2e_sampler.set_initial(par0, cov, W.sigma2, W.nobs)  # allocation + first touch outside the timed region
+        e2e_sampler.run(1)
+        ce0 = None
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for it in range(e2e_steps):
+            e2e_sampler.set_data(blob)                                   # H2D model data
+            e2e_sampler.set_initial(par0, cov, W.sigma2, W.nobs)         # H2D start points (pinned) + init kernel
+            e2e_sampler.run(W.iters, sync=False)
+            out = [e2e_sampler.fetch(w, out=t.numpy()) for w, t in outs.items()]  # D2H results
+            d2h = sum(o.nbytes for o in out)
+            if W.pool:
+                d2h += 8 * (1 + d + d * d)
+                e2e_sampler.pool_fetch()
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        ce = {k: outs["counters"].numpy()[:, i] for i, k in enumerate(mb.binding.COUNTER_NAMES)}
+        q_e2e = float(ce["drtries"].sum()) / (N * W.iters)
+        e2e_sampler.close()
+        e2e = (e2e_s, e2e_steps, h2d, d2h, q_e2e)
 
-    t_total = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda:%d" % dev)
+    t_total = torch.tensor([total_ms, (e2e[0] * 1e3) if e2e else 0.0], dtype=torch.float64, device="cuda:%d" % dev)
     if dist is not None:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_ms_max = [float(v) for v in t_total.cpu()]
     value = world * N * done_steps / (total_ms_max * 1e-3)
-    e2e_value = world * N * MCMC_PER_STEP * e2e_steps / (e2e_ms_max * 1e-3)
 
     if rank == 0:
-        fl = flops_per_chain_step(q, rows)
         avg_launch_ms = float(np.mean(launch_ms))
-        achieved = N * MCMC_PER_STEP * fl / (avg_launch_ms * 1e-3) / 1e12
-        info = s.info()
-        # hardware FP64 instruction count per datum of the compiled ssfunction loop (see DESIGN.md;
-        # DFMA counted as 2 flops) -- explains the gap between algorithmic and pipe utilisation
-        # 9 FP64 instructions per datum in the SASS of the datum loop (7 DFMA + 1 DMUL + 1 DADD, profiles/r01_summary.md G)
-        hw_flop_per_datum = float(os.environ.get("MCMCB_HW_FLOP_PER_DATUM", "16") or 0)
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE steady-state bench launch (2^20 chains x 100 iterations),
-        # from `ncu --metrics dram__bytes...` on this command (profiles/r01_bench_launch_dram.txt).  The algorithmic
-        # state traffic is 2 x 212 B x 2^20 = 0.44 GB; the rest is the chains' cold state (accept/reject, adaptation,
-        # RNG position: ~450 B per chain, in local memory) cycling through L2: with 4 chains per thread the 3 x 10^5
-        # chains in flight hold 136 MB of it, more than L2 keeps, so every step re-reads and re-writes it.  That is
-        # 46 GB/s = 0.7 % of the measured HBM bandwidth on a kernel bound by the FP64 pipe and shared memory
-        # (one chain per thread: 0.74 GB per launch, 7 % slower).
-        traffic = {4: 58.5e9, 1: 738.7e6}.get(info["chains_per_thread"]) if (N == 1 << 20 and info["lanes_per_chain"] == 1) else None
-        roof = {"bound": "fp64", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                "frac": achieved / sustained, "traffic": traffic,
-                "traffic_unit": "bytes per launch (ncu, profiles/r01_bench_launch_dram.txt)",
-                "algorithmic_bytes_per_launch": 2.0 * 212 * N,
-                "peak_source": "in-bench DFMA microbenchmark on this GPU, sustained 2 s (burst %.2f); "
-                               "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks, neither bounds this kernel" % burst,
-                "algorithmic_flops_per_chain_step": fl, "stage2_rate_q": q, "accept_rate": 1 - stay,
-                "datum_evals_per_s": N * MCMC_PER_STEP * (1 + q) * NDATA / (avg_launch_ms * 1e-3),
-                "kernel": "k1_step_kernel<ExpReg,L=%d,smem,B=%d>" % (info["lanes_per_chain"], info["chains_per_thread"]),
-                "avg_launch_ms": avg_launch_ms, "launch_ms": launch_ms}
-        if hw_flop_per_datum > 0:
-            hw = roof["datum_evals_per_s"] * hw_flop_per_datum / 1e12
-            roof["achieved_hw"] = hw
-            roof["frac_hw"] = hw / sustained
-            roof["hw_note"] = ("FP64 flops the compiled datum loop executes (exp = 7 FP64 instructions, counted as 1 flop in "
-                               "`achieved`): %g per datum x datum_evals_per_s" % hw_flop_per_datum)
-        cores = os.cpu_count() or 1
-        if world == 1 and not args.no_cpu_baseline:
-            cpu_v, cpu_sample = cpu_baseline(cores)
-            cpu = {"value": cpu_v, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": cpu_sample}
+        rate_gpu = per_gpu * W.iters / (avg_launch_ms * 1e-3)        # chain-steps/s of one GPU inside one step
+        prof, prof_src = load_profile(W.name)
+        peaks, peaks_src = measured_peaks()
+        roof = {"bound": W.bound, "units": W.units_note(), "stage2_rate_q": q, "accept_rate": 1 - stay,
+                "kernel": W.kernel, "avg_launch_ms": avg_launch_ms, "launch_ms": launch_ms,
+                "profile": prof_src}
+        if W.bound == "fp64":
+            fl = W.flops_per_step(q, rows)
+            achieved = rate_gpu * fl / 1e12
+            roof.update({"achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "peak_source": "in-bench DFMA microbenchmark on this GPU, sustained 2 s (burst %.2f); MEASURED_PEAKS.json "
+                                        "holds only HBM and bf16-tensor peaks, neither bounds this kernel" % burst,
+                         "algorithmic_flops_per_chain_step": fl})
+            if W.ndata:
+                roof["datum_evals_per_s"] = rate_gpu * (1 + q) * W.ndata * (W.d if W.name == "c5" else 1)
         else:
-            cpu = None
-        others = None
-        if world == 1 and not args.no_other_workloads:
-            try:
-                others = other_workloads(mb, torch, dev)
-            except Exception as e:  # never let the side measurements take the headline line down
-                others = {"error": repr(e)}
+            by = W.hbm_bytes_per_step(q)
+            achieved = rate_gpu * by / 1e9
+            roof.update({"achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "peak_source": peaks_src, "algorithmic_bytes_per_chain_step": by})
+        # measured hardware counts of ONE launch of the dominant kernel, from the committed ncu capture
+        roof["traffic"] = None
+        if prof:
+            per_launch_units = prof["chains"] * prof["iterations"]
+            scale = per_gpu * W.iters / per_launch_units   # the capture may cover fewer iterations than a bench step
+            roof["traffic"] = prof["dram_bytes"] * scale
+            roof["traffic_unit"] = "bytes per bench step (ncu dram__bytes_read+write of one launch, scaled by chain-steps)"
+            hwf = prof.get("fp64_flops")
+            if hwf and W.bound == "fp64":
+                hw = hwf / per_launch_units * rate_gpu / 1e12
+                roof["achieved_hw"] = hw
+                roof["frac_hw"] = hw / sustained
+                roof["hw_note"] = ("FP64 flops the kernel executes per chain-step (ncu smsp__sass_thread_inst_executed_op_"
+                                   "dfma x2 + dadd + dmul of the captured launch: %.4g) x chain-steps/s" % (hwf / per_launch_units))
+            for k in ("fp64_pipe_pct", "issue_active_pct", "shared_wavefronts", "shared_bank_conflicts", "duration_ms"):
+                if k in prof:
+                    roof["ncu_" + k] = prof[k]
+        if W.name in ("c3", "c1"):
+            roof["algorithmic_bytes_per_launch"] = 2.0 * 212 * per_gpu
+        cores = os.cpu_count() or 1
+        cpu = None
+        if ngpus_total == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(W, cores)
+        info = None
         line = {
-            "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+            "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": ngpus_total,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args), lanes_per_chain=info["lanes_per_chain"],
-                           chains_per_thread=info["chains_per_thread"], blocks=info["blocks"],
-                           threads_per_block=info["threads_per_block"], smem_bytes=info["smem_bytes"]),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(W, args, per_gpu, args.scaling), processes=world, gpus_per_process=G,
+                           source_hash=source_hash()),
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": "every e2e step uploads data + start points, runs the first 100 iterations of fresh chains "
-                            "(stage-2 rate ~0.88 against ~0.71 in the steady state that `value` times) and downloads "
-                            "theta/mean/cov/counters of every chain into pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
             "chains_with_error_status": status_bad,
-            "other_workloads": others,
         }
+        if W.pool:
+            line["collective"] = {"pooled_ticks_in_timed_region": int(args.steps * W.iters // W.nml["adaptint"]),
+                                  "allreduce_doubles_per_tick": 1 + W.d + W.d * W.d,
+                                  "backend": "NCCL in-process (ncclCommInitAll), %d calls" % nccl_calls if G > 1 else
+                                             ("NCCL via torch.distributed callback" if nccl_world else "single GPU: local sums")}
+        if e2e:
+            e2e_s, e2e_steps, h2d, d2h, q_e2e = e2e
+            line["e2e"] = {"value": world * N * W.iters * e2e_steps / (e2e_ms_max * 1e-3), "unit": "chain-steps/s",
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                           "stage2_rate_q": q_e2e,
+                           "note": "every e2e step uploads the model data, every chain's start point (the steady-state points of the "
+                                   "device-timed chains) and the adapted proposal covariance, runs %d iterations and downloads "
+                                   "theta/mean/cov/counters of every chain into pinned host buffers" % W.iters}
+        if args.dump_stride:
+            line["dumps"] = {"dump_stride": args.dump_stride, "snapshots_popped": dumped,
+                             "bytes_per_snapshot": int(N * (W.d + 2 * len(W.sigma2) + 1) * 8),
+                             "note": "theta/ss/sigma2 of every chain streamed to pinned host buffers on a copy stream and popped by "
+                                     "the host inside the timed region; compare `value` with a run without --dump-stride"}
         print(json.dumps(line))
-    s.close()
+    if s is not None:
+        s.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -441,10 +567,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "c1"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--chains", type=int, default=0, help="override: chains per GPU")
+    ap.add_argument("--iters", type=int, default=0, help="override: MCMC iterations per bench step")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--dump-stride", type=int, default=0, help="stream theta/ss/sigma2 of every chain to the host every n iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short C2/C4/C5 side measurements")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="accepted for compatibility (no effect)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -167,7 +167,7 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
   cfg->updatesigma = 1; cfg->condmax = 0.0; cfg->alphatarget = 0.234; cfg->nuparam = 0.7;
   cfg->nchains = 1; cfg->chain_offset = 0; cfg->seed = 0; cfg->rng_mode = MCMCB_RNG_PHILOX; cfg->device = 0;
   cfg->store_chains = 1; cfg->lanes_per_chain = 0; cfg->dump_stride = 0; cfg->kernel = 0; cfg->pool_adapt = 0;
-  cfg->diag_stride = 0; cfg->diag_lags = 8;
+  cfg->diag_stride = 0; cfg->diag_lags = 8; cfg->ngpus = 1;
   std::strcpy(cfg->model, "expreg");
   std::memset(f, 0, sizeof *f);
   set_str(f->chainfile, "chain.dat"); set_str(f->s2file, "s2chain.dat"); set_str(f->ssfile, "sschain.dat");
@@ -188,6 +188,8 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
   int rc = read_group(text, "mcmc", kv, &found);
   if (rc) return rc;
   if (!found) return fail(MCMCBH_EPARSE, "namelist group &mcmc not found");
+  int sstype = 0;          // mcmcinit.F90:222-223: legacy likelihood selector of the Modest interface
+  double sstrans = -1.0;
   for (auto& [k, v] : kv) {
     bool ok = true;
     double dummy_d;
@@ -225,8 +227,9 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
     else if (k == "parffile") ok = parse_string(v, f->parffile, MCMCBH_PATH);
     else if (k == "sigma2file") ok = parse_string(v, f->sigma2file, MCMCBH_PATH);
     else if (k == "sigma2ffile") ok = parse_string(v, f->sigma2ffile, MCMCBH_PATH);
-    else if (k == "condmaxini" || k == "sstrans") ok = parse_double(v, dummy_d);
-    else if (k == "sstype") ok = parse_int(v, dummy_i);
+    else if (k == "condmaxini") ok = parse_double(v, dummy_d);
+    else if (k == "sstrans") ok = parse_double(v, sstrans);
+    else if (k == "sstype") ok = parse_int(v, sstype);
     else if (k == "dumpint") ok = parse_int(v, f->dumpint);
     else if (k == "priorsfile") ok = parse_string(v, f->priorsfile, MCMCBH_PATH);
     else if (k == "verbosity") ok = parse_int(v, f->verbosity);
@@ -245,6 +248,13 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
     else return fail(MCMCBH_EPARSE, "namelist &mcmc: unknown variable `" + k + "`");
     if (!ok) return fail(MCMCBH_EPARSE, "namelist &mcmc: bad value for `" + k + "`: " + v);
   }
+  // check_mcmcinit_parameters' side effects of sstype on the sampler (mcmcinit.F90:271-321); the ss types themselves
+  // belong to the Modest interface (`mdstlsqs`), not to the standalone library, and have no device model here
+  if (sstype == 3) { cfg->updatesigma = 0; cfg->S02 = 1.0; }               // Poisson likelihood
+  else if (sstype == 5) {                                                   // t with fixed df = sstrans
+    if (sstrans < 1.0) return fail(MCMCBH_EPARSE, "ERROR: please set sstrans = df, when sstype = 5");
+    cfg->updatesigma = 0;
+  } else if (sstype == 6) { cfg->updatesigma = 0; cfg->S02 = std::sqrt(cfg->S02); }  // Laplace
   kv.clear();
   rc = read_group(text, "mcmcb", kv, &found);
   if (rc) return rc;
@@ -262,6 +272,7 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
     else if (k == "pool_adapt") ok = parse_int(v, cfg->pool_adapt);
     else if (k == "diag_stride") ok = parse_int(v, cfg->diag_stride);
     else if (k == "diag_lags") ok = parse_int(v, cfg->diag_lags);
+    else if (k == "ngpus") ok = parse_int(v, cfg->ngpus);
     else if (k == "model") ok = parse_string(v, cfg->model, sizeof cfg->model);
     else if (k == "datafile") ok = parse_string(v, f->datafile, MCMCBH_PATH);
     else return fail(MCMCBH_EPARSE, "namelist &mcmcb: unknown variable `" + k + "`");
@@ -387,8 +398,8 @@ extern "C" int mcmcbh_write_namelist(const char* path, const mcmcb_config* c, co
                f->dumpint, f->priorsfile, f->verbosity, method, c->alphatarget, c->nuparam);
   std::fprintf(fp, "&mcmcb\n nchains = %lld,\n chain_offset = %lld,\n seed = %llu,\n device = %d,\n store_chains = %d,\n", c->nchains,
                c->chain_offset, c->seed, c->device, c->store_chains);
-  std::fprintf(fp, " lanes_per_chain = %d,\n dump_stride = %d,\n kernel = %d,\n pool_adapt = %d,\n diag_stride = %d,\n diag_lags = %d,\n",
-               c->lanes_per_chain, c->dump_stride, c->kernel, c->pool_adapt, c->diag_stride, c->diag_lags);
+  std::fprintf(fp, " lanes_per_chain = %d,\n dump_stride = %d,\n kernel = %d,\n pool_adapt = %d,\n diag_stride = %d,\n diag_lags = %d,\n ngpus = %d,\n",
+               c->lanes_per_chain, c->dump_stride, c->kernel, c->pool_adapt, c->diag_stride, c->diag_lags, c->ngpus);
   std::fprintf(fp, " model = '%s',\n datafile = '%s'\n/\n", c->model, f->datafile);
   const bool bad = std::ferror(fp);
   std::fclose(fp);
@@ -417,6 +428,7 @@ extern "C" int mcmcbh_initialize(const char* dir, const mcmcbh_files* f, int* np
   rc = mcmcbh_load_dat(join(dir, f->cov0file).c_str(), &m, &r, &c);
   if (rc || r != *npar || c != *npar) {
     if (!rc) std::free(m);
+    std::free(*par0); *par0 = nullptr;
     return fail(rc ? rc : MCMCBH_EPARSE, std::string("ERROR: Error reading file ") + f->cov0file);
   }
   // row-major file order -> column-major cmat0(npar,npar)
@@ -434,8 +446,13 @@ extern "C" int mcmcbh_initialize(const char* dir, const mcmcbh_files* f, int* np
     for (int k = 0; k < *nycol; k++) { (*sigma2)[k] = 1.0; (*nobs)[k] = 1; }  // initialize.F90:107-110
   } else {
     // mcmcsigma2.dat is 2 x nycol: first row sigma2, second row nobs (initialize.F90:105-118)
-    if (r != 2 && c != *nycol) { std::free(m); return fail(MCMCBH_EPARSE, "ERROR: error in mcmcsigma2.dat (obs: new format 4.8.2006)"); }
-    if (r * c < 2 * *nycol) { std::free(m); return fail(MCMCBH_EPARSE, "ERROR: mcmcsigma2.dat too short"); }
+    // the reference tests `size(s2n,1) /= 2 .and. size(s2n,2) /= nycol` (initialize.F90:111) and then indexes
+    // s2n(2,1:nycol) whatever the shape; here any other shape than 2 x nycol is refused
+    if (r != 2 || c != *nycol) {
+      std::free(m); std::free(*par0); std::free(*cmat0); std::free(*sigma2); std::free(*nobs);
+      *par0 = *cmat0 = *sigma2 = nullptr; *nobs = nullptr;
+      return fail(MCMCBH_EPARSE, "ERROR: error in mcmcsigma2.dat (obs: new format 4.8.2006)");
+    }
     for (int k = 0; k < *nycol; k++) { (*sigma2)[k] = m[k]; (*nobs)[k] = (int)m[(size_t)c * 1 + k]; }
     std::free(m);
   }

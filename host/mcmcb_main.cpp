@@ -116,6 +116,7 @@ int main(int argc, char** argv) {
   }
   // restart files from chain 0 (the pooled statistics when pool_adapt = 1): final covariance, its weight,
   // the mean, the last point, sigma2 + nobs
+  double w_final = 0.0;
   {
     const size_t N = (size_t)cfg.nchains;
     std::vector<double> cm(N * npar * npar), mean(N * npar), wsum(N);
@@ -124,6 +125,7 @@ int main(int argc, char** argv) {
     DEV(mcmcb_fetch(h, "wsum", wsum.data(), wsum.size() * sizeof(double)));
     double w0 = wsum[0];
     if (cfg.pool_adapt && mcmcb_pool_fetch(h, &w0, mean.data(), cm.data()) != 0) w0 = wsum[0];
+    w_final = w0;
     HOST(mcmcbh_write_dat(in_dir(dir, files.covffile).c_str(), cm.data(), npar, npar, npar));
     if (files.covnfile[0]) {
       const double wn = (double)(int)w0;
@@ -137,8 +139,18 @@ int main(int argc, char** argv) {
       HOST(mcmcbh_write_dat(in_dir(dir, files.sigma2ffile).c_str(), s2n.data(), 2, nycol, 2));
     }
   }
-  // the namelist as it was run (MCMC_aux.F90:82-83)
-  if (files.nmlffile[0]) HOST(mcmcbh_write_namelist(in_dir(dir, files.nmlffile).c_str(), &cfg, &files));
+  // the namelist of the CONTINUATION run (MCMC_aux.F90:48-52,79-83): initcmatn = int(chainwsum) when covnfile is
+  // set, then initcmatn += simuind and burnintime = 0 -- the restart weights the saved covariance with what it has seen
+  if (files.nmlffile[0]) {
+    mcmcb_config next = cfg;
+    // the reference writes its namelist VARIABLES, i.e. after check_mcmcinit_parameters (mcmcinit.F90:235-368) and
+    // after MCMC_init replaced S02 <= 0 by sigma2(1) (MCMC_init.F90:114-116)
+    mcmcb_check_config(&next, nullptr, nullptr, nullptr);
+    if (next.S02 <= 0.0) next.S02 = sigma2[0];
+    next.initcmatn = (files.covnfile[0] ? (int)w_final : next.initcmatn) + cfg.nsimu;
+    next.burnintime = 0;
+    HOST(mcmcbh_write_namelist(in_dir(dir, files.nmlffile).c_str(), &next, &files));
+  }
   if (cfg.diag_stride > 0) {
     std::vector<double> rhat(npar), ess(npar), pm(npar), pv(npar);
     long long ns = 0, nc = 0;

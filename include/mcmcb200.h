@@ -11,8 +11,10 @@
  *
  * Conventions: every call returns 0 on success or a negative MCMCB_E* code and never
  * exits the process (the reference `stop`s, e.g. matutils.F90:764-789).  The caller
- * owns all host buffers.  One host thread per handle; one handle drives one GPU
- * (multi-GPU = one handle per rank with chain_offset set).
+ * owns all host buffers.  One host thread per handle.  A handle drives `ngpus` GPUs of the box from that one thread
+ * (the reference's host is a single-process program, mcmc_main.F90:12-44): chains are sharded over devices
+ * `device .. device+ngpus-1` by contiguous global id and every call below fans out; host arrays stay chain-major over
+ * ALL chains.  One handle per rank with `chain_offset` set (one process per GPU) works as well.
  * Matrices are column-major (Fortran) unless stated.
  */
 #ifndef MCMCB200_H
@@ -25,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCMCB_ABI_VERSION 2
+#define MCMCB_ABI_VERSION 3
 
 /* error codes */
 #define MCMCB_OK 0
@@ -82,6 +84,8 @@ typedef struct mcmcb_config {
   int diag_stride;     /* >0: every diag_stride steps theta of every chain is folded into the per-chain running
                           moments behind mcmcb_diagnostics (R-hat / ESS) */
   int diag_lags;       /* autocovariance lags kept for the ESS, in units of diag_stride (0..MCMCB_DIAG_MAXLAGS) */
+  int ngpus;           /* 0 or 1: one GPU (`device`); n > 1: this handle drives devices device..device+n-1 from one host
+                          thread; pooled adaptation / diagnostics then reduce over NCCL inside the process */
   char model[32];      /* user-model name: "expreg", "gauss", "banana", "hier", or a plugin's name */
 } mcmcb_config;
 
@@ -138,10 +142,20 @@ int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out
  *  "erstayed" (1 x int64: steps rejected by the prior alone in method 'er', mcmc.F90:49) */
 int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes);
 
+/* One chain's adaptation state with typed arguments (no string keys): mean[npar], cmat[npar*npar] and R[npar*npar]
+ * column-major, *wsum, sigma2[nycol], counters[8] as in "counters" above -- what a Fortran host copies back into
+ * chainmean / chaincmat / chainwsum / R / sigma2 and its counters (mcmc.F90:28-55).  Any pointer may be NULL. */
+int mcmcb_fetch_stats(mcmcb_handle h, long long chain, double* mean, double* cmat, double* wsum, double* R,
+                      double* sigma2, long long* counters);
+
 /* streamed dumps (MCMC_dump.F90:12-30 hook): pops the oldest completed snapshot of all
  * chains' theta (nchains x npar, chain-major) from the pinned ring; returns 1 if one was
  * copied, 0 if none pending. *step receives simuind of the snapshot. */
 int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step);
+
+/* The same snapshot with what MCMC_savechain records beside theta (MCMC_aux.F90:166-185): ss (nchains x nycol) and
+ * sigma2 (nchains x nycol) of every chain at that step; ss / sigma2 may be NULL. */
+int mcmcb_dump_pop_ex(mcmcb_handle h, double* par, double* ss, double* sigma2, size_t par_bytes, int* step);
 
 /* ---- multi-GPU collectives: chains never interact in the reference, so the step loop has no
  * collective.  The two optional cross-chain features below reduce a few small vectors over every handle of
@@ -149,7 +163,8 @@ int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step);
  * sum-reduces n doubles in place in DEVICE memory across all ranks, ordered on the given CUDA stream (or
  * synchronously): ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, comm, stream) from C/Fortran,
  * torch.distributed.all_reduce from Python (mcmcf90_b200/parallel.py).  Without a callback the reduction
- * covers the handle's own chains only. */
+ * covers the handle's own chains only.  A handle with ngpus > 1 reduces over its own devices with NCCL and refuses a
+ * callback (MCMCB_EUNSUPPORTED). */
 typedef int (*mcmcb_allreduce_fn)(void* user, double* device_buf, size_t n, void* cuda_stream);
 int mcmcb_set_allreduce(mcmcb_handle h, mcmcb_allreduce_fn fn, void* user);
 
@@ -169,7 +184,10 @@ int mcmcb_diagnostics(mcmcb_handle h, double* rhat, double* ess, double* mean, d
 int mcmcb_diag_reset(mcmcb_handle h);
 
 /* introspection for measurement */
-void* mcmcb_stream(mcmcb_handle h);              /* cudaStream_t the kernels run on */
+void* mcmcb_stream(mcmcb_handle h);              /* cudaStream_t the kernels run on (first device of a group) */
+void* mcmcb_stream_of(mcmcb_handle h, int k);    /* ... on the k-th device of a group handle */
+int mcmcb_ngpus(mcmcb_handle h);                 /* devices this handle drives */
+long long mcmcb_nccl_calls(mcmcb_handle h);      /* NCCL allreduce groups issued so far (group handles) */
 long long mcmcb_launch_count(mcmcb_handle h);    /* kernels launched so far */
 int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes_per_chain, int* kernel, int* threads_per_block,
                int* blocks, size_t* smem_bytes);

@@ -17,7 +17,8 @@ EXPORTS = ["mcmcb_default_config", "mcmcb_check_config", "mcmcb_create", "mcmcb_
            "mcmcb_set_data", "mcmcb_set_priors", "mcmcb_set_initial", "mcmcb_inject_uniforms", "mcmcb_run",
            "mcmcb_sync", "mcmcb_fetch_chain", "mcmcb_fetch", "mcmcb_dump_pop", "mcmcb_stream",
            "mcmcb_launch_count", "mcmcb_info", "mcmcb_chains_per_thread", "mcmcb_dfma_peak", "mcmcb_exp_selftest",
-           "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset", "mcmcb_load_plugin"]
+           "mcmcb_set_allreduce", "mcmcb_pool_fetch", "mcmcb_diagnostics", "mcmcb_diag_reset", "mcmcb_load_plugin",
+           "mcmcb_dump_pop_ex", "mcmcb_stream_of", "mcmcb_ngpus", "mcmcb_nccl_calls", "mcmcb_fetch_stats"]
 
 # int fn(void* user, double* device_buf, size_t n, void* cuda_stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -42,7 +43,7 @@ class Config(C.Structure):
         ("nchains", C.c_longlong), ("chain_offset", C.c_longlong), ("seed", C.c_ulonglong),
         ("rng_mode", C.c_int), ("device", C.c_int), ("store_chains", C.c_int), ("lanes_per_chain", C.c_int),
         ("dump_stride", C.c_int), ("kernel", C.c_int),
-        ("pool_adapt", C.c_int), ("diag_stride", C.c_int), ("diag_lags", C.c_int),
+        ("pool_adapt", C.c_int), ("diag_stride", C.c_int), ("diag_lags", C.c_int), ("ngpus", C.c_int),
         ("model", C.c_char * 32),
     ]
 
@@ -77,8 +78,15 @@ def load_library():
     L.mcmcb_fetch_chain.argtypes = [C.c_void_p, C.c_longlong, C.c_int, dp, dp, dp, ip]
     L.mcmcb_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
     L.mcmcb_dump_pop.argtypes = [C.c_void_p, dp, C.c_size_t, ip]
+    L.mcmcb_fetch_stats.argtypes = [C.c_void_p, C.c_longlong, dp, dp, dp, dp, dp, C.POINTER(C.c_longlong)]
+    L.mcmcb_dump_pop_ex.argtypes = [C.c_void_p, dp, dp, dp, C.c_size_t, ip]
     L.mcmcb_stream.argtypes = [C.c_void_p]
     L.mcmcb_stream.restype = C.c_void_p
+    L.mcmcb_stream_of.argtypes = [C.c_void_p, C.c_int]
+    L.mcmcb_stream_of.restype = C.c_void_p
+    L.mcmcb_ngpus.argtypes = [C.c_void_p]
+    L.mcmcb_nccl_calls.argtypes = [C.c_void_p]
+    L.mcmcb_nccl_calls.restype = C.c_longlong
     L.mcmcb_launch_count.argtypes = [C.c_void_p]
     L.mcmcb_launch_count.restype = C.c_longlong
     L.mcmcb_info.argtypes = [C.c_void_p, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_size_t)]
@@ -139,7 +147,7 @@ def _dp(a):
 
 
 class Sampler:
-    """One handle = nchains independent chains on one GPU (replaces the module-global
+    """One handle = nchains independent chains on cfg.ngpus GPUs (replaces the module-global
     single chain of mcmc.F90:28-60)."""
 
     def __init__(self, cfg):
@@ -237,6 +245,15 @@ class Sampler:
         n = nrows.value
         return dict(chain=ch[:n].copy(), sschain=ss[:n].copy(), s2chain=s2.copy(), nrows=n)
 
+    def fetch_stats(self, chain):
+        """One chain's (mean, cmat, wsum, R, sigma2, counters) through the typed entry point mcmcb_fetch_stats."""
+        d, m = self.npar, self.nycol
+        mean, cm, R, s2 = np.zeros(d), np.zeros((d, d), order="F"), np.zeros((d, d), order="F"), np.zeros(m)
+        w, cnt = C.c_double(0), (C.c_longlong * 8)()
+        self._chk(self.L.mcmcb_fetch_stats(self.h, int(chain), _dp(mean), _dp(cm), C.byref(w), _dp(R), _dp(s2), cnt), "mcmcb_fetch_stats")
+        return dict(mean=mean, cmat=np.ascontiguousarray(cm), wsum=w.value, R=np.ascontiguousarray(R), sigma2=s2,
+                    counters=dict(zip(COUNTER_NAMES, [int(v) for v in cnt])))
+
     def set_allreduce(self, fn):
         """fn(device_ptr:int, n:int, cuda_stream:int) -> None sum-reduces n doubles in place over all
         ranks (mcmcf90_b200.parallel.attach builds it from torch.distributed); None detaches."""
@@ -277,6 +294,25 @@ class Sampler:
         step = C.c_int(0)
         rc = self._chk(self.L.mcmcb_dump_pop(self.h, _dp(out), out.nbytes, C.byref(step)), "mcmcb_dump_pop")
         return (step.value, out) if rc == 1 else None
+
+    def dump_pop_ex(self):
+        """(step, theta (nchains, npar), ss (nchains, nycol), sigma2 (nchains, nycol)) of the oldest finished snapshot."""
+        par = np.zeros((self.nchains, self.npar))
+        ss, s2 = np.zeros((self.nchains, self.nycol)), np.zeros((self.nchains, self.nycol))
+        step = C.c_int(0)
+        rc = self._chk(self.L.mcmcb_dump_pop_ex(self.h, _dp(par), _dp(ss), _dp(s2), par.nbytes, C.byref(step)), "mcmcb_dump_pop_ex")
+        return (step.value, par, ss, s2) if rc == 1 else None
+
+    @property
+    def ngpus(self):
+        return int(self.L.mcmcb_ngpus(self.h))
+
+    @property
+    def nccl_calls(self):
+        return int(self.L.mcmcb_nccl_calls(self.h))
+
+    def stream_of(self, k):
+        return self.L.mcmcb_stream_of(self.h, int(k))
 
     @property
     def stream(self):

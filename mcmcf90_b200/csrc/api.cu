@@ -121,6 +121,7 @@ extern "C" int mcmcb_default_config(mcmcb_config* c) {  // mcmcinit.F90:184-230
   c->pool_adapt = 0;
   c->diag_stride = 0;
   c->diag_lags = 8;
+  c->ngpus = 1;
   std::strcpy(c->model, "expreg");
   return MCMCB_OK;
 }
@@ -152,8 +153,122 @@ extern "C" int mcmcb_check_config(mcmcb_config* c, int* dodr, int* doscam, int* 
 }
 
 // ------------------------------------------------------------------ lifecycle
+// ------------------------------------------------------------------ one handle driving several GPUs
+// cfg.ngpus > 1: the handle is a GROUP of per-device handles ("kids") inside this one process and host thread --
+// the reference's host is a single-process program (mcmc_main.F90:12-44), so a Fortran user gets the whole box
+// without MPI.  Chains are sharded by contiguous global id; every call fans out; the kernels of the
+// kids run concurrently because launches are asynchronous.  The pooled-adaptation and diagnostics reductions go
+// over NCCL (one communicator per device from ncclCommInitAll, calls bracketed by ncclGroupStart/End); the library
+// is dlopen'ed so that a process that never asks for ngpus > 1 with pooling does not need it.
+namespace grp {
+struct Nccl {
+  void* lib = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl& nccl() { static Nccl n; return n; }
+static int nccl_load(mcmcb_handle g) {
+  Nccl& n = nccl();
+  if (n.lib) return 0;
+  const char* env = std::getenv("MCMCB_NCCL_LIB");
+  const char* cand[] = {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
+  for (const char* c : cand) {
+    n.lib = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+    if (n.lib) break;
+  }
+  if (!n.lib) { g->err = std::string("cannot load NCCL (set MCMCB_NCCL_LIB): ") + dlerror(); return MCMCB_EUNSUPPORTED; }
+  n.CommInitAll = (int (*)(void**, int, const int*))dlsym(n.lib, "ncclCommInitAll");
+  n.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
+  n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+  n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
+  n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
+  n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+  if (!n.CommInitAll || !n.AllReduce || !n.GroupStart || !n.GroupEnd || !n.CommDestroy) {
+    g->err = "NCCL library lacks the expected symbols";
+    n.lib = nullptr;
+    return MCMCB_EUNSUPPORTED;
+  }
+  return 0;
+}
+static int comms(mcmcb_handle g) {  // lazily: only pooled adaptation / diagnostics need them
+  if (!g->nccl_comms.empty()) return 0;
+  int rc = nccl_load(g);
+  if (rc) return rc;
+  std::vector<int> devs;
+  for (auto* k : g->kids) devs.push_back(k->cfg.device);
+  g->nccl_comms.assign(g->kids.size(), nullptr);
+  const int e = nccl().CommInitAll(g->nccl_comms.data(), (int)devs.size(), devs.data());
+  if (e != 0) {
+    g->err = std::string("ncclCommInitAll: ") + (nccl().GetErrorString ? nccl().GetErrorString(e) : "error");
+    g->nccl_comms.clear();
+    return MCMCB_ECUDA;
+  }
+  return 0;
+}
+// sum-reduce n doubles at bufs[k] (device memory of kid k) in place over all kids, ordered on each kid's stream
+static int allreduce(mcmcb_handle g, const std::vector<double*>& bufs, size_t n) {
+  int rc = comms(g);
+  if (rc) return rc;
+  Nccl& nc = nccl();
+  int e = nc.GroupStart();
+  for (size_t k = 0; k < g->kids.size() && e == 0; k++)
+    e = nc.AllReduce(bufs[k], bufs[k], n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g->nccl_comms[k], g->kids[k]->stream);
+  const int e2 = nc.GroupEnd();
+  if (e == 0) e = e2;
+  if (e != 0) { g->err = std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "error"); return MCMCB_ECUDA; }
+  g->nccl_calls++;
+  return 0;
+}
+static void shard(long long N, int G, int k, long long* n, long long* off) {  // contiguous ranges, remainder to the first kids
+  const long long base = N / G, rem = N % G;
+  *n = base + (k < rem ? 1 : 0);
+  *off = (long long)k * base + (k < rem ? k : rem);
+}
+}  // namespace grp
+
+static int create_group(const mcmcb_config* cfg, mcmcb_handle* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) return MCMCB_ECUDA;
+  const int G = cfg->ngpus;
+  if (cfg->device < 0 || cfg->device + G > ndev || cfg->nchains < G) return MCMCB_EINVAL;
+  mcmcb_handle g = new mcmcb_handle_s();
+  g->cfg = *cfg;
+  for (int k = 0; k < G; k++) {
+    mcmcb_config c = *cfg;
+    c.ngpus = 1;
+    c.device = cfg->device + k;
+    long long n = 0, off = 0;
+    grp::shard(cfg->nchains, G, k, &n, &off);
+    c.nchains = n;
+    c.chain_offset = cfg->chain_offset + off;
+    // stored chains are the first store_chains GLOBAL chains
+    const long long want = cfg->store_chains < 0 ? cfg->nchains : cfg->store_chains;
+    const long long mine = std::max<long long>(0, std::min<long long>(want - off, n));
+    c.store_chains = (int)mine;
+    mcmcb_handle kid = nullptr;
+    const int rc = mcmcb_create(&c, &kid);
+    if (rc) {
+      for (auto* q : g->kids) mcmcb_destroy(q);
+      delete g;
+      return rc;
+    }
+    g->kids.push_back(kid);
+  }
+  g->npar = g->kids[0]->npar;
+  g->nycol = g->kids[0]->nycol;
+  g->model = g->kids[0]->model;
+  *out = g;
+  return MCMCB_OK;
+}
+
 extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (!cfg || !out || cfg->abi_version != MCMCB_ABI_VERSION || cfg->nchains < 1 || cfg->nsimu < 1) return MCMCB_EINVAL;
+  if (cfg->ngpus < 0) return MCMCB_EINVAL;
+  if (cfg->ngpus > 1) return create_group(cfg, out);
   mcmcb_handle h = new mcmcb_handle_s();
   h->cfg = *cfg;
   int rc = mcmcb_check_config(&h->cfg, &h->dodr, &h->doscam, &h->usesvd);
@@ -202,7 +317,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_hist, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
-                  h->d_cmat, h->d_gcm, h->d_gmean, h->d_gw, h->d_rowbuf, h->d_scratch, h->d_cmat0_full, h->d_qstd,
+                  h->d_cmat, h->d_gcm, h->d_gmean, h->d_gw, h->d_rowbuf, h->d_coef, h->d_scratch, h->d_cmat0_full, h->d_qstd,
                   h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial,
                   h->d_fetch};
   for (void* p : ptrs)
@@ -217,6 +332,14 @@ static void free_dev(mcmcb_handle h) {
 
 extern "C" int mcmcb_destroy(mcmcb_handle h) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (size_t k = 0; k < h->kids.size(); k++) {
+      if (k < h->nccl_comms.size() && h->nccl_comms[k]) { cudaSetDevice(h->kids[k]->cfg.device); grp::nccl().CommDestroy(h->nccl_comms[k]); }
+      mcmcb_destroy(h->kids[k]);
+    }
+    delete h;
+    return MCMCB_OK;
+  }
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->copy_stream);
@@ -227,10 +350,20 @@ extern "C" int mcmcb_destroy(mcmcb_handle h) {
   return MCMCB_OK;
 }
 
-extern "C" const char* mcmcb_last_error(mcmcb_handle h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" const char* mcmcb_last_error(mcmcb_handle h) {
+  if (!h) return "null handle";
+  if (h->err.empty())
+    for (auto* k : h->kids)
+      if (!k->err.empty()) return k->err.c_str();
+  return h->err.c_str();
+}
 
 extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
   if (!h || !blob || n == 0) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) { const int rc = mcmcb_set_data(k, blob, n); if (rc) return rc; }
+    return MCMCB_OK;
+  }
   CK(cudaSetDevice(h->cfg.device));
   size_t bytes = ((n * sizeof(double) + 15) / 16) * 16;
   if (h->d_blob && bytes != h->blob_bytes) { cudaFree(h->d_blob); h->d_blob = nullptr; }
@@ -248,6 +381,10 @@ extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
 
 extern "C" int mcmcb_set_priors(mcmcb_handle h, const double* mu, const double* sig, int npar) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) { const int rc = mcmcb_set_priors(k, mu, sig, npar); if (rc) return rc; }
+    return MCMCB_OK;
+  }
   CK(cudaSetDevice(h->cfg.device));
   if (h->d_prior) { cudaFree(h->d_prior); h->d_prior = nullptr; }
   if (!mu || !sig) return MCMCB_OK;
@@ -263,6 +400,15 @@ extern "C" int mcmcb_set_priors(mcmcb_handle h, const double* mu, const double* 
 extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const double* par0, long long par0_stride,
                                  const double* cmat0, const double* sigma2, const int* nobs) {
   if (!h || !par0 || !cmat0 || !sigma2 || !nobs || npar < 1 || nycol < 1) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) {
+      const double* p0 = par0 + (par0_stride ? (size_t)(k->cfg.chain_offset - h->cfg.chain_offset) * par0_stride : 0);
+      const int rc = mcmcb_set_initial(k, npar, nycol, p0, par0_stride, cmat0, sigma2, nobs);
+      if (rc) return rc;
+    }
+    h->npar = npar; h->nycol = nycol; h->initial_set = true;
+    return MCMCB_OK;
+  }
   if (h->model->npar > 0 && npar != h->model->npar) return MCMCB_EINVAL;
   if (nycol != h->model->ny) return MCMCB_EINVAL;
   if (par0_stride != 0 && par0_stride < npar) return MCMCB_EINVAL;
@@ -348,6 +494,14 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
 
 extern "C" int mcmcb_inject_uniforms(mcmcb_handle h, const double* u, size_t per_chain) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) {
+      const double* uk = u ? u + (size_t)(k->cfg.chain_offset - h->cfg.chain_offset) * per_chain : nullptr;
+      const int rc = mcmcb_inject_uniforms(k, uk, per_chain);
+      if (rc) return rc;
+    }
+    return MCMCB_OK;
+  }
   CK(cudaSetDevice(h->cfg.device));
   if (h->d_inj) { cudaFree(h->d_inj); h->d_inj = nullptr; }
   h->inj_per_chain = 0;
@@ -360,11 +514,20 @@ extern "C" int mcmcb_inject_uniforms(mcmcb_handle h, const double* u, size_t per
 }
 
 // ------------------------------------------------------------------ streamed dumps
+// What a snapshot holds: theta, ss, sspri and sigma2 of every chain at one step -- the arguments of the reference's
+// per-step hooks (MCMC_dump(oldpar), MCMC_userfun; MCMC_dump.F90:12-30, MCMC_userfun.F90:12-19) plus the two values
+// MCMC_savechain records beside them (MCMC_aux.F90:166-185), thinned to every dump_stride-th step.
+static size_t dump_scalar_fields(mcmcb_handle h) { return 2 * (size_t)h->nycol + 1; }  // ss[ny], sspri, sigma2[ny]
+static size_t dump_doubles(mcmcb_handle h) {
+  if (h->model->kernel == 2) return (size_t)h->cfg.nchains * h->dp + dump_scalar_fields(h) * h->pitch;
+  return ((size_t)h->npar + dump_scalar_fields(h)) * h->pitch;  // K1: theta, ss, sspri, sigma2 are the first SoA fields
+}
+
 static int dump_enqueue(mcmcb_handle h) {
-  // snapshot theta (field-major, npar x pitch) device->device on the compute stream, then
-  // device->pinned host on the copy stream, so the next launch overlaps the PCIe copy
+  // snapshot device->device on the compute stream, then device->pinned host on the copy stream, so the next
+  // launch overlaps the PCIe copy
   const bool k2 = h->model->kernel == 2;
-  const size_t bytes = k2 ? sizeof(double) * (size_t)h->cfg.nchains * h->dp : sizeof(double) * (size_t)h->npar * h->pitch;
+  const size_t bytes = sizeof(double) * dump_doubles(h);
   if (h->dump_slots.empty()) {
     h->dump_slots.resize(4);
     for (auto& s : h->dump_slots) {
@@ -383,7 +546,14 @@ static int dump_enqueue(mcmcb_handle h) {
       if (*it == k) { h->dump_fifo.erase(it); break; }
     h->dumps_dropped++;
   }
-  CK(cudaMemcpyAsync(s.dev, k2 ? h->d_theta : h->d_st /* theta is field 0 */, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (k2) {
+    const size_t tb = sizeof(double) * (size_t)h->cfg.nchains * h->dp;
+    CK(cudaMemcpyAsync(s.dev, h->d_theta, tb, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(s.dev + (size_t)h->cfg.nchains * h->dp, h->d_st /* ss, sspri, sigma2 are fields 0.. */,
+                       bytes - tb, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    CK(cudaMemcpyAsync(s.dev, h->d_st, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
   CK(cudaEventRecord(s.ready, h->stream));
   CK(cudaStreamWaitEvent(h->copy_stream, s.ready, 0));
   CK(cudaMemcpyAsync(s.host, s.dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -395,28 +565,61 @@ static int dump_enqueue(mcmcb_handle h) {
   return 0;
 }
 
-extern "C" int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step) {
-  if (!h || !out) return MCMCB_EINVAL;
-  if (h->dump_fifo.empty()) return 0;
-  int k = h->dump_fifo.front();
+static bool dump_front_ready(mcmcb_handle h) {
+  if (h->dump_fifo.empty()) return false;
+  return cudaEventQuery(h->dump_slots[h->dump_fifo.front()].ev) == cudaSuccess;
+}
+
+// one handle: copy the front snapshot out (caller checked dump_front_ready)
+static void dump_take(mcmcb_handle h, double* par, double* ss, double* sigma2, int* step) {
+  const int k = h->dump_fifo.front();
   auto& s = h->dump_slots[k];
-  if (cudaEventQuery(s.ev) != cudaSuccess) return 0;
   const long long N = h->cfg.nchains;
-  if (out_bytes < sizeof(double) * (size_t)N * h->npar) return MCMCB_EINVAL;
+  const int d = h->npar, ny = h->nycol;
   const bool k2 = h->model->kernel == 2;
-  for (int f = 0; f < h->npar; f++)
-    for (long long c = 0; c < N; c++)
-      out[(size_t)c * h->npar + f] = k2 ? s.host[(size_t)c * h->dp + f] : s.host[(size_t)f * h->pitch + c];
+  const double* sc = k2 ? s.host + (size_t)N * h->dp : s.host + (size_t)d * h->pitch;  // [ss.., sspri, sigma2..][pitch]
+  if (par)
+    for (int f = 0; f < d; f++)
+      for (long long c = 0; c < N; c++) par[(size_t)c * d + f] = k2 ? s.host[(size_t)c * h->dp + f] : s.host[(size_t)f * h->pitch + c];
+  for (int f = 0; f < ny; f++)
+    for (long long c = 0; c < N; c++) {
+      if (ss) ss[(size_t)c * ny + f] = sc[(size_t)f * h->pitch + c];
+      if (sigma2) sigma2[(size_t)c * ny + f] = sc[(size_t)(ny + 1 + f) * h->pitch + c];
+    }
   if (step) *step = s.step;
   s.state = 0;
   h->dump_fifo.pop_front();
+}
+
+extern "C" int mcmcb_dump_pop_ex(mcmcb_handle h, double* par, double* ss, double* sigma2, size_t par_bytes, int* step) {
+  if (!h || !par) return MCMCB_EINVAL;
+  if (par_bytes < sizeof(double) * (size_t)h->cfg.nchains * h->npar) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {  // a snapshot is complete when every device has delivered its part
+    for (auto* k : h->kids)
+      if (!dump_front_ready(k)) return 0;
+    for (auto* k : h->kids) {
+      const size_t off = (size_t)(k->cfg.chain_offset - h->cfg.chain_offset);
+      dump_take(k, par + off * h->npar, ss ? ss + off * h->nycol : nullptr, sigma2 ? sigma2 + off * h->nycol : nullptr, step);
+    }
+    return 1;
+  }
+  if (!dump_front_ready(h)) return 0;
+  dump_take(h, par, ss, sigma2, step);
   return 1;
 }
 
+extern "C" int mcmcb_dump_pop(mcmcb_handle h, double* out, size_t out_bytes, int* step) {
+  return mcmcb_dump_pop_ex(h, out, nullptr, nullptr, out_bytes, step);
+}
+
 // ------------------------------------------------------------------ pooled adaptation / diagnostics
-static int do_allreduce(mcmcb_handle h, double* dev, size_t n) {
+// `hs` is the handle itself, or the kids of a group handle: the reductions below run over all of them (NCCL inside
+// the process) and, for a plain handle, over every rank the host's allreduce callback spans.
+static int allreduce_many(mcmcb_handle top, const std::vector<mcmcb_handle>& hs, const std::vector<double*>& bufs, size_t n) {
+  if (hs.size() > 1) return grp::allreduce(top, bufs, n);
+  mcmcb_handle h = hs[0];
   if (!h->ar_fn) return 0;  // single handle: the local sums are the global sums
-  const int rc = h->ar_fn(h->ar_user, dev, n, (void*)h->stream);
+  const int rc = h->ar_fn(h->ar_user, bufs[0], n, (void*)h->stream);
   if (rc) { h->err = "allreduce callback failed"; return MCMCB_ECUDA; }
   return 0;
 }
@@ -430,14 +633,16 @@ static bool is_pool_tick(const mcmcb_config& c, long long i) {
   return i >= (long long)c.burnintime + c.adaptint + c.adapthist;
 }
 
-static int pool_tick(mcmcb_handle h) {
-  const size_t d = (size_t)h->npar;
-  int rc = h->model->pool(h, 1);
-  if (!rc) rc = do_allreduce(h, h->d_pool, 1 + d);
-  if (!rc) rc = h->model->pool(h, 2);
-  if (!rc) rc = do_allreduce(h, h->d_pool + 1 + d, d * d);
-  if (!rc) rc = h->model->pool(h, 3);
-  h->pool_ticks++;
+static int pool_tick(mcmcb_handle top, const std::vector<mcmcb_handle>& hs) {
+  const size_t d = (size_t)hs[0]->npar;
+  std::vector<double*> b1, b2;
+  for (auto* h : hs) { b1.push_back(h->d_pool); b2.push_back(h->d_pool + 1 + d); }
+  int rc = 0;
+  for (auto* h : hs) { if (!rc) { CK(cudaSetDevice(h->cfg.device)); rc = h->model->pool(h, 1); } }
+  if (!rc) rc = allreduce_many(top, hs, b1, 1 + d);
+  for (auto* h : hs) { if (!rc) { CK(cudaSetDevice(h->cfg.device)); rc = h->model->pool(h, 2); } }
+  if (!rc) rc = allreduce_many(top, hs, b2, d * d);
+  for (auto* h : hs) { if (!rc) { CK(cudaSetDevice(h->cfg.device)); rc = h->model->pool(h, 3); } h->pool_ticks++; }
   return rc;
 }
 
@@ -464,48 +669,63 @@ static int diag_snapshot(mcmcb_handle h) {
 }
 
 // ------------------------------------------------------------------ run
-extern "C" int mcmcb_run(mcmcb_handle h, int nsteps) {
-  if (!h || nsteps < 0) return MCMCB_EINVAL;
-  if (!h->initial_set || !h->d_blob) return MCMCB_EINVAL;
-  if (h->cfg.rng_mode == MCMCB_RNG_INJECTED && !h->d_inj) return MCMCB_EINVAL;
-  CK(cudaSetDevice(h->cfg.device));
-  const mcmcb_config& c = h->cfg;
+static int run_many(mcmcb_handle top, const std::vector<mcmcb_handle>& hs, int nsteps) {
+  for (auto* h : hs) {
+    if (!h->initial_set || !h->d_blob) return MCMCB_EINVAL;
+    if (h->cfg.rng_mode == MCMCB_RNG_INJECTED && !h->d_inj) return MCMCB_EINVAL;
+  }
+  const mcmcb_config& c = hs[0]->cfg;  // the kids of a group differ in nchains / chain_offset / device only
   int left = nsteps;
   do {
     // a launch ends where the host has something to do: streamed dump, diagnostics snapshot, pooled tick.
     // simuind after k more steps = 1 + steps_done + k (the first launch also evaluates the initial point)
+    const long long done = hs[0]->steps_done;
     int n = left;
-    if (c.dump_stride > 0) n = std::min<long long>(n, c.dump_stride - h->steps_done % c.dump_stride);
-    if (c.diag_stride > 0) n = std::min<long long>(n, c.diag_stride - h->steps_done % c.diag_stride);
-    if (c.pool_adapt) n = std::min<long long>(n, c.adaptint - (1 + h->steps_done) % c.adaptint);
-    int rc = h->model->step(h, n);
-    if (rc) return rc;
-    h->steps_done += n;
+    if (c.dump_stride > 0) n = std::min<long long>(n, c.dump_stride - done % c.dump_stride);
+    if (c.diag_stride > 0) n = std::min<long long>(n, c.diag_stride - done % c.diag_stride);
+    if (c.pool_adapt) n = std::min<long long>(n, c.adaptint - (1 + done) % c.adaptint);
+    for (auto* h : hs) {  // asynchronous launches: the devices of a group run side by side
+      CK(cudaSetDevice(h->cfg.device));
+      const int rc = h->model->step(h, n);
+      if (rc) return rc;
+      h->steps_done += n;
+    }
     left -= n;
-    if (n > 0 && is_pool_tick(c, 1 + h->steps_done)) {
-      rc = pool_tick(h);
+    if (n > 0 && is_pool_tick(c, 1 + hs[0]->steps_done)) {
+      const int rc = pool_tick(top, hs);
       if (rc) return rc;
     }
-    if (n > 0 && c.diag_stride > 0 && h->steps_done % c.diag_stride == 0) {
-      rc = diag_snapshot(h);
-      if (rc) return rc;
-    }
-    if (n > 0 && c.dump_stride > 0 && h->steps_done % c.dump_stride == 0) {
-      rc = dump_enqueue(h);
-      if (rc) return rc;
+    for (auto* h : hs) {
+      CK(cudaSetDevice(h->cfg.device));
+      if (n > 0 && c.diag_stride > 0 && h->steps_done % c.diag_stride == 0) {
+        const int rc = diag_snapshot(h);
+        if (rc) return rc;
+      }
+      if (n > 0 && c.dump_stride > 0 && h->steps_done % c.dump_stride == 0) {
+        const int rc = dump_enqueue(h);
+        if (rc) return rc;
+      }
     }
   } while (left > 0);
   return MCMCB_OK;
 }
 
+extern "C" int mcmcb_run(mcmcb_handle h, int nsteps) {
+  if (!h || nsteps < 0) return MCMCB_EINVAL;
+  if (!h->kids.empty()) return run_many(h, h->kids, nsteps);
+  return run_many(h, std::vector<mcmcb_handle>{h}, nsteps);
+}
+
 extern "C" int mcmcb_set_allreduce(mcmcb_handle h, mcmcb_allreduce_fn fn, void* user) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) return fn ? MCMCB_EUNSUPPORTED : MCMCB_OK;  // a group reduces over its own devices (NCCL)
   h->ar_fn = fn;
   h->ar_user = user;
   return MCMCB_OK;
 }
 
 extern "C" int mcmcb_pool_fetch(mcmcb_handle h, double* wsum, double* mean, double* cov) {
+  if (h && !h->kids.empty()) return mcmcb_pool_fetch(h->kids[0], wsum, mean, cov);  // identical on every device
   if (!h || !h->d_pool) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
   const size_t d = (size_t)h->npar, n = 1 + d + d * d;
@@ -525,31 +745,44 @@ extern "C" int mcmcb_pool_fetch(mcmcb_handle h, double* wsum, double* mean, doub
 
 extern "C" int mcmcb_diag_reset(mcmcb_handle h) {
   if (!h) return MCMCB_EINVAL;
+  for (auto* k : h->kids) k->diag_n = 0;
   h->diag_n = 0;
   return MCMCB_OK;
 }
 
 // R-hat and ESS from the chain-summed moments (Gelman et al., BDA3 11.4-11.5; Stan's multi-chain ESS with
 // Geyer's initial positive sequence, lags limited to diag_lags)
-extern "C" int mcmcb_diagnostics(mcmcb_handle h, double* rhat, double* ess, double* mean, double* var, long long* nsnap,
+extern "C" int mcmcb_diagnostics(mcmcb_handle top, double* rhat, double* ess, double* mean, double* var, long long* nsnap,
                                  long long* nchains_total) {
-  if (!h || !h->d_diag || h->diag_n < 2) return MCMCB_EINVAL;
-  CK(cudaSetDevice(h->cfg.device));
+  if (!top) return MCMCB_EINVAL;
+  std::vector<mcmcb_handle> hs = top->kids.empty() ? std::vector<mcmcb_handle>{top} : top->kids;
+  mcmcb_handle h = hs[0];
+  if (!h->d_diag || h->diag_n < 2) return MCMCB_EINVAL;
   const int d = h->npar, K = h->diag_K, nv = 2 + K;
-  DiagParams p = diag_params(h);
-  double* buf = h->d_diag_buf;
+  std::vector<double*> b1, b2;
+  for (auto* q : hs) { b1.push_back(q->d_diag_buf); b2.push_back(q->d_diag_buf + 1 + d); }
   dim3 grid(POOL_BLOCKS, d);
-  diag_reduce_kernel<<<grid, POOL_THREADS, 0, h->stream>>>(p, 1, buf, h->d_diag_partial);
-  diag_final_kernel<<<(d * 2 + 255) / 256, 256, 0, h->stream>>>(h->d_diag_partial, POOL_BLOCKS, 2, d, 1, buf);
+  for (auto* q : hs) {
+    if (cudaSetDevice(q->cfg.device) != cudaSuccess) return MCMCB_ECUDA;
+    DiagParams p = diag_params(q);
+    diag_reduce_kernel<<<grid, POOL_THREADS, 0, q->stream>>>(p, 1, q->d_diag_buf, q->d_diag_partial);
+    diag_final_kernel<<<(d * 2 + 255) / 256, 256, 0, q->stream>>>(q->d_diag_partial, POOL_BLOCKS, 2, d, 1, q->d_diag_buf);
+  }
   CK(cudaGetLastError());
-  int rc = do_allreduce(h, buf, 1 + (size_t)d);
+  int rc = allreduce_many(top, hs, b1, 1 + (size_t)d);
   if (rc) return rc;
-  diag_reduce_kernel<<<grid, POOL_THREADS, 0, h->stream>>>(p, 2, buf, h->d_diag_partial);
-  diag_final_kernel<<<(d * nv + 255) / 256, 256, 0, h->stream>>>(h->d_diag_partial, POOL_BLOCKS, nv, d, 2, buf + 1 + d);
+  for (auto* q : hs) {
+    if (cudaSetDevice(q->cfg.device) != cudaSuccess) return MCMCB_ECUDA;
+    DiagParams p = diag_params(q);
+    diag_reduce_kernel<<<grid, POOL_THREADS, 0, q->stream>>>(p, 2, q->d_diag_buf, q->d_diag_partial);
+    diag_final_kernel<<<(d * nv + 255) / 256, 256, 0, q->stream>>>(q->d_diag_partial, POOL_BLOCKS, nv, d, 2, q->d_diag_buf + 1 + d);
+    q->launches += 4;
+  }
   CK(cudaGetLastError());
-  rc = do_allreduce(h, buf + 1 + d, (size_t)nv * d);
+  rc = allreduce_many(top, hs, b2, (size_t)nv * d);
   if (rc) return rc;
-  h->launches += 4;
+  CK(cudaSetDevice(h->cfg.device));
+  double* buf = h->d_diag_buf;
   std::vector<double> b(1 + (size_t)d + (size_t)nv * d);
   CK(cudaMemcpyAsync(b.data(), buf, sizeof(double) * b.size(), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -587,6 +820,11 @@ extern "C" int mcmcb_diagnostics(mcmcb_handle h, double* rhat, double* ess, doub
 
 extern "C" int mcmcb_sync(mcmcb_handle h) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) { const int rc = mcmcb_sync(k); if (rc) return rc; }
+    return MCMCB_OK;
+  }
+  CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->copy_stream));
   return MCMCB_OK;
@@ -595,25 +833,129 @@ extern "C" int mcmcb_sync(mcmcb_handle h) {
 // ------------------------------------------------------------------ fetch
 extern "C" int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t out_bytes) {
   if (!h || !what || !out || !h->initial_set) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {  // every array is chain-major: the kids' parts are consecutive slices
+    if (h->cfg.nchains <= 0 || out_bytes % (size_t)h->cfg.nchains != 0) return MCMCB_EINVAL;
+    const size_t per = out_bytes / (size_t)h->cfg.nchains;  // bytes per chain as the caller sized it
+    for (auto* k : h->kids) {
+      const size_t off = (size_t)(k->cfg.chain_offset - h->cfg.chain_offset);
+      const int rc = mcmcb_fetch(k, what, (char*)out + off * per, per * (size_t)k->cfg.nchains);
+      if (rc) return rc;
+    }
+    return MCMCB_OK;
+  }
   CK(cudaSetDevice(h->cfg.device));
   return h->model->fetch(h, what, out, out_bytes);
 }
 
 extern "C" int mcmcb_fetch_chain(mcmcb_handle h, long long chain, int ld, double* chain_out, double* sschain_out,
                                  double* s2chain_out, int* nrows) {
+  if (h && !h->kids.empty()) {
+    for (auto* k : h->kids) {
+      const long long off = k->cfg.chain_offset - h->cfg.chain_offset;
+      if (chain >= off && chain < off + k->cfg.nchains) return mcmcb_fetch_chain(k, chain - off, ld, chain_out, sschain_out, s2chain_out, nrows);
+    }
+    return MCMCB_EINVAL;
+  }
   if (!h || !h->initial_set || chain < 0 || chain >= h->store_chains) return MCMCB_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
   return h->model->fetch_chain(h, chain, ld, chain_out, sschain_out, s2chain_out, nrows);
 }
 
+// One chain's adaptation state and counters with typed arguments -- what a Fortran host copies back into the module
+// globals chainmean / chaincmat / chainwsum / R and the counters (mcmc.F90:28-55) without string keys.
+extern "C" int mcmcb_fetch_stats(mcmcb_handle h, long long chain, double* mean, double* cmat, double* wsum, double* R,
+                                 double* sigma2, long long* counters) {
+  if (!h || !h->initial_set || chain < 0 || chain >= h->cfg.nchains) return MCMCB_EINVAL;
+  if (!h->kids.empty()) {
+    for (auto* k : h->kids) {
+      const long long off = k->cfg.chain_offset - h->cfg.chain_offset;
+      if (chain >= off && chain < off + k->cfg.nchains) return mcmcb_fetch_stats(k, chain - off, mean, cmat, wsum, R, sigma2, counters);
+    }
+    return MCMCB_EINVAL;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  const int d = h->npar, ny = h->nycol;
+  const size_t P = (size_t)h->pitch;
+  // column `chain` of nf consecutive SoA fields -> contiguous host values (one strided copy)
+  auto col = [&](const void* base, size_t elem, int f0, int nf, void* dst) -> cudaError_t {
+    return cudaMemcpy2DAsync(dst, elem, (const char*)base + ((size_t)f0 * P + (size_t)chain) * elem, P * elem, elem, (size_t)nf,
+                             cudaMemcpyDeviceToHost, h->stream);
+  };
+  std::vector<double> tri;
+  std::vector<int> ic;
+  int i_first = 0, i_nd = 0;
+  if (h->model->kernel == 1) {
+    const K1Layout Lo = k1_layout(d, ny);
+    const int T = d * (d + 1) / 2;
+    tri.assign(2 * (size_t)T, 0.0);
+    if (mean) CK(col(h->d_st, 8, Lo.mean, d, mean));
+    if (wsum) CK(col(h->d_st, 8, Lo.wsum, 1, wsum));
+    if (sigma2) CK(col(h->d_st, 8, Lo.s2, ny, sigma2));
+    if (cmat) CK(col(h->d_st, 8, Lo.cm, T, tri.data()));
+    if (R) CK(col(h->d_st, 8, Lo.r, T, tri.data() + T));
+    ic.assign(Lo.i_nf, 0);
+    if (counters) CK(col(h->d_ist, 4, 0, Lo.i_nf, ic.data()));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < d; j++)
+      for (int i = 0; i <= j; i++) {
+        if (cmat) cmat[(size_t)j * d + i] = cmat[(size_t)i * d + j] = tri[(size_t)j * (j + 1) / 2 + i];
+        if (R) { R[(size_t)j * d + i] = tri[T + (size_t)j * (j + 1) / 2 + i]; if (i != j) R[(size_t)i * d + j] = 0.0; }
+      }
+    i_first = Lo.i_stayed; i_nd = Lo.i_ndlo;
+  } else {
+    const K2Layout Lo = k2_layout(ny);
+    std::vector<double> rm;
+    if (mean) CK(cudaMemcpyAsync(mean, h->d_mean + (size_t)chain * h->dp, sizeof(double) * d, cudaMemcpyDeviceToHost, h->stream));
+    if (cmat) CK(cudaMemcpyAsync(cmat, h->d_cmat + (size_t)chain * d * d, sizeof(double) * d * d, cudaMemcpyDeviceToHost, h->stream));
+    if (R) {
+      rm.resize((size_t)d * d);
+      CK(cudaMemcpyAsync(rm.data(), h->d_Rm + (size_t)chain * h->r_stride, sizeof(double) * d * d, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (wsum) CK(col(h->d_st, 8, Lo.wsum, 1, wsum));
+    if (sigma2) CK(col(h->d_st, 8, Lo.s2, ny, sigma2));
+    ic.assign(Lo.i_nf, 0);
+    if (counters) CK(col(h->d_ist, 4, 0, Lo.i_nf, ic.data()));
+    CK(cudaStreamSynchronize(h->stream));
+    if (R)  // Cholesky factor: row-major upper -> column-major; SVD factor is stored column-major already
+      for (int j = 0; j < d; j++)
+        for (int i = 0; i < d; i++)
+          R[(size_t)j * d + i] = h->factor_mode == FACTOR_CHOL ? (i <= j ? rm[(size_t)i * d + j] : 0.0) : rm[(size_t)j * d + i];
+    i_first = Lo.i_stayed; i_nd = Lo.i_ndlo;
+  }
+  if (counters) {  // stayed, bndstayed, draccepted, drtries, chainind, simuind, status are the first seven int fields
+    for (int k = 0; k < 7; k++) counters[k] = ic[i_first + k];
+    counters[7] = (long long)(((unsigned long long)(unsigned)ic[i_nd + 1] << 32) | (unsigned)ic[i_nd]);
+  }
+  return MCMCB_OK;
+}
+
 // ------------------------------------------------------------------ introspection
-extern "C" void* mcmcb_stream(mcmcb_handle h) { return h ? (void*)h->stream : nullptr; }
-extern "C" long long mcmcb_launch_count(mcmcb_handle h) { return h ? h->launches : 0; }
-extern "C" int mcmcb_chains_per_thread(mcmcb_handle h) { return (h && h->model && h->model->kernel == 1) ? h->k1_batch : 1; }
+extern "C" void* mcmcb_stream(mcmcb_handle h) {
+  if (h && !h->kids.empty()) return (void*)h->kids[0]->stream;
+  return h ? (void*)h->stream : nullptr;
+}
+extern "C" void* mcmcb_stream_of(mcmcb_handle h, int k) {  // stream of the k-th device of a group handle
+  if (!h) return nullptr;
+  if (h->kids.empty()) return k == 0 ? (void*)h->stream : nullptr;
+  return (k >= 0 && k < (int)h->kids.size()) ? (void*)h->kids[k]->stream : nullptr;
+}
+extern "C" int mcmcb_ngpus(mcmcb_handle h) { return h ? (h->kids.empty() ? 1 : (int)h->kids.size()) : 0; }
+extern "C" long long mcmcb_nccl_calls(mcmcb_handle h) { return h ? h->nccl_calls : 0; }
+extern "C" long long mcmcb_launch_count(mcmcb_handle h) {
+  if (!h) return 0;
+  long long n = h->launches;
+  for (auto* k : h->kids) n += k->launches;
+  return n;
+}
+extern "C" int mcmcb_chains_per_thread(mcmcb_handle h) {
+  if (h && !h->kids.empty()) return mcmcb_chains_per_thread(h->kids[0]);
+  return (h && h->model && h->model->kernel == 1) ? h->k1_batch : 1;
+}
 
 extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int* kernel, int* tpb, int* blocks,
                           size_t* smem) {
   if (!h) return MCMCB_EINVAL;
+  if (!h->kids.empty()) return mcmcb_info(h->kids[0], npar, nycol, lanes, kernel, tpb, blocks, smem);
   if (npar) *npar = h->npar;
   if (nycol) *nycol = h->nycol;
   if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : h->L;

@@ -70,6 +70,7 @@ struct K2Params {
   double* Rm;      // [chain][d*d]  row-major upper factor (Cholesky mode)
   double* cmat;    // [chain][d*d]  symmetric, full
   double* rowbuf;  // [chain][cap][d+1]  completed rows + weights since the last adaptation
+  double* coef;    // [chain][2 * (cap + 1)] covmat recursion coefficients of the logged rows (tick kernels' scratch)
   int rowcap;
   const double* par0;      // [chain][d]
   const double* cmat0;     // [d*d] column-major full
@@ -112,20 +113,27 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
     filled = 1;
   }
   while (filled < n) {
-    double u1, u2;
-    g.uniform_pair_at(g.nd + 2ull * lane, u1, u2);
+    // lane l looks 2l draws ahead of the stream position.  With an injected stream the look-ahead may pass its end
+    // although the pairs actually consumed do not: unavailable pairs are never read, and exhaustion is declared --
+    // by the whole warp at once -- only if a pair that the sequential polar loop would have consumed is missing
+    const bool avail = g.inj == nullptr || g.nd + 2ull * lane + 1ull < g.inj_n;
+    double u1 = 0.5, u2 = 0.5;
+    if (avail) g.uniform_pair_at(g.nd + 2ull * lane, u1, u2);
     const double x1 = 2.0 * u1 - 1.0, x2 = 2.0 * u2 - 1.0;
     const double xx = x1 * x1 + x2 * x2;
-    const bool ok = (xx < 1.0 && xx != 0.0);
+    const bool ok = avail && (xx < 1.0 && xx != 0.0);
     const unsigned m = __ballot_sync(FULL, ok);
-    if (g.exhausted) {  // injected stream ran out: fill with zeros, flag is reported by the caller
+    const unsigned mav = __ballot_sync(FULL, avail);
+    const int need = (n - filled + 1) >> 1;  // accepted pairs still needed
+    const int have = __popc(m);
+    const int use = have < need ? have : need;
+    const int span = have >= need ? (int)__fns(m, 0, need) + 1 : 32;  // candidate pairs consumed by this round
+    if (mav != FULL && __ffs(~mav) - 1 < span) {  // injected stream ran out: fill with zeros, the caller reports the flag
+      g.exhausted = 1;
       for (int k = filled + lane; k < n; k += 32) zs[k] = 0.0;
       filled = n;
       break;
     }
-    const int need = (n - filled + 1) >> 1;  // accepted pairs still needed
-    const int have = __popc(m);
-    const int use = have < need ? have : need;
     const int rank = __popc(m & ((1u << lane) - 1u));
     double sp = 0.0;
     bool made_spare = false;
@@ -141,9 +149,7 @@ __device__ __forceinline__ void warp_normals(Rng& g, double* zs, int n, int lane
       g.spare = __shfl_sync(FULL, sp, __ffs(ms) - 1);
       g.has_spare = true;
     }
-    int consumed = 32;
-    if (have >= need) consumed = (int)__fns(m, 0, need) + 1;  // stop right after the last pair used
-    g.nd += 2ull * consumed;
+    g.nd += 2ull * span;  // stop right after the last pair used
     filled += 2 * use;
   }
   __syncwarp();
@@ -336,13 +342,13 @@ static __global__ void k2_initR_kernel(K2Params p, double* scratch) {
 constexpr int ABS_E = 8;    // cm entries per thread and tile
 constexpr int ABS_RC = 8;   // dv rows per shared-memory chunk
 
-// shared scratch: coef[2 * nrows] then chunk[ABS_RC * d]
-__host__ __device__ __forceinline__ size_t absorb_smem_doubles(int rowcap, int d) { return 2 * (size_t)(rowcap + 1) + (size_t)ABS_RC * d; }
+// shared scratch: chunk[ABS_RC * d] -- O(d), independent of the row capacity (the per-row coefficients live in global
+// memory, K2Params::coef: rowcap grows with burnintime and would otherwise pass the 48 KB / 227 KB launch limits)
+__host__ __device__ __forceinline__ size_t absorb_smem_doubles(int d) { return (size_t)ABS_RC * d; }
 
 __device__ __forceinline__ void cta_absorb_rows(double* rb, int nrows, double* cm, double* mean, double& wsum, int d,
-                                                double* sh, bool unit_weights = false) {
-  double* coef = sh;                       // (f1, f2) per row; f2 = -1: no-op row, f2 = -2: reset (first row, wsum == 0)
-  double* chunk = sh + 2 * (size_t)nrows;  // ABS_RC x d
+                                                double* coef, double* chunk, bool unit_weights = false) {
+  // coef: (f1, f2) per row, global; f2 = -1: no-op row, f2 = -2: reset (first row, wsum == 0).  chunk: ABS_RC x d, shared
   const int tid = threadIdx.x, nt = blockDim.x;
   // ---- phase 1: rows in order; every thread tracks wsum, thread k owns component k
   double ws = wsum;
@@ -479,7 +485,8 @@ __device__ __forceinline__ void cta_ap_window(double* rb, int nbuf, const double
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
 static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
-  extern __shared__ double sh[];  // absorb_smem_doubles(rowcap, d)
+  extern __shared__ double sh[];  // absorb_smem_doubles(d)
+  double* coef = p.coef + (size_t)blockIdx.x * 2 * (p.rowcap + 1);
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);
   const long long c = blockIdx.x;
@@ -512,13 +519,13 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
       double* gmean = p.gmean + c * p.dp;
       double gw = p.gw[c];
       __syncthreads();
-      cta_absorb_rows(rb, nbuf, gcm, gmean, gw, d, sh, true);
+      cta_absorb_rows(rb, nbuf, gcm, gmean, gw, d, coef, sh, true);
       for (int k = threadIdx.x; k < d * d; k += blockDim.x) cm[k] = gcm[k];
       for (int k = threadIdx.x; k < d; k += blockDim.x) { mean[k] = gmean[k]; rb[k] = theta[k]; }
       if (threadIdx.x == 0) rb[d] = 1.0;
       __syncthreads();
       wsum = gw;
-      cta_absorb_rows(rb, 1, cm, mean, wsum, d, sh, true);
+      cta_absorb_rows(rb, 1, cm, mean, wsum, d, coef, sh, true);
       const bool ok = cta_calculate_R(cm, Rm, tmp, d, red);
       // what the AM branch starts from: see k1_finish (the reference resets at simuind == burnintime+adaptint+adapthist
       // only if that step is a tick, otherwise it carries on from the greedy covariance)
@@ -558,7 +565,7 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
     for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
     if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
     __syncthreads();
-    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, sh);
+    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, coef, sh);
     if (threadIdx.x == 0) {
       st[Lo.wsum * p.pitch] = wsum;
       ist[Lo.i_pend * p.pitch] = 0;

@@ -184,7 +184,7 @@ static __global__ void k3_initR_kernel(K2Params p, double* scratch, int mode) {
 
 // MCMC_adapt.F90:12-174 at step index p.tick_i for the SVD factor modes, one CTA per chain.
 static __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
-  extern __shared__ double sh[];  // d doubles + d ints (as d doubles) + absorb_smem_doubles(rowcap, d)
+  extern __shared__ double sh[];  // d doubles + d ints (as d doubles) + absorb_smem_doubles(d)
   __shared__ double red[K2_ADAPT_THREADS / 32];
   constexpr K2Layout Lo = k2_layout(1);
   const long long c = blockIdx.x;
@@ -232,7 +232,7 @@ static __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
     for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
     if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
     __syncthreads();
-    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, dvec);
+    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, p.coef + (size_t)blockIdx.x * 2 * (p.rowcap + 1), dvec);
     if (threadIdx.x == 0) {
       st[Lo.wsum * p.pitch] = wsum;
       ist[Lo.i_pend * p.pitch] = 0;

@@ -278,8 +278,10 @@ struct K1 {
       if (exp_dn < 2048) exp_dn = 0;
     }
     smem += sizeof(double) * (size_t)exp_dn;
+    // the attribute belongs to the kernel function, not to the handle: another handle with a different blob may have
+    // lowered it since this handle's last launch, so it is set before every launch (cheap)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!h->attr_set) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
       if (occ < 1) occ = 1;
@@ -484,6 +486,7 @@ struct K2 {
     p.cmat = h->d_cmat;
     p.rowbuf = h->d_rowbuf;
     p.rowcap = h->rowcap;
+    p.coef = h->d_coef;
     p.par0 = h->d_par0;
     p.cmat0 = h->d_cmat0_full;
     p.sigma2_0 = h->d_sigma2;
@@ -530,6 +533,9 @@ struct K2 {
     h->dp = ((d + 31) / 32) * 32;
     h->rowcap = c.burnintime + 2 * std::max(c.adaptint, 1) + c.adapthist + 2;
     const bool greedy = c.greedy && c.doburnin && c.method != MCMCB_RAM && h->factor_mode == FACTOR_CHOL;
+    // plain AM (no burn-in branch, no AP window): every adaptint-th step is a tick that empties the buffer, so at most
+    // adaptint rows are logged between two ticks (at d = 200 a row is 1.6 KB: 2^18 SCAM chains keep 43 GB instead of 85)
+    if (!c.doburnin && c.adapthist <= 1 && c.adaptint > 0 && (c.badaptint <= 0 || c.badaptint == c.adaptint)) h->rowcap = c.adaptint + 2;
     if (c.method == MCMCB_RAM || (!c.doadapt && !greedy)) h->rowcap = 1;
     CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
     CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
@@ -547,6 +553,7 @@ struct K2 {
     CK(cudaMalloc(&h->d_qstd, sizeof(double) * NR * h->dp));
     CK(cudaMemsetAsync(h->d_qstd, 0, sizeof(double) * NR * h->dp, h->stream));
     CK(cudaMalloc(&h->d_rowbuf, sizeof(double) * (size_t)N * (h->rowcap + 1) * (d + 1)));
+    CK(cudaMalloc(&h->d_coef, sizeof(double) * (size_t)N * 2 * (h->rowcap + 1)));
     if (greedy) {  // unit-weight accumulators of the greedy burn-in (MCMC_adapt.F90:83-101)
       CK(cudaMalloc(&h->d_gcm, sizeof(double) * (size_t)N * d * d));
       CK(cudaMalloc(&h->d_gmean, sizeof(double) * (size_t)N * h->dp));
@@ -585,8 +592,8 @@ struct K2 {
     const int W = h->k2_warps;
     size_t smem = sizeof(double) * (size_t)W * K2_NVEC * h->dp + (SMEM ? h->blob_bytes : 0) +
                   (h->r_resident ? sizeof(double) * (size_t)W * h->npar * h->npar : 0);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!h->attr_set) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
       h->occ = std::max(occ, 1);
@@ -632,8 +639,8 @@ struct K2 {
     const size_t T = (size_t)d * (d + 1) / 2, Tp = (T + 1) & ~(size_t)1;
     const size_t smem = sizeof(double) * (size_t)ngroups * ((size_t)K2_NVEC * h->dp + Tp + 2 * K2G_RED + 4) +
                         (SMEM ? h->blob_bytes : 0);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!h->attr_set) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       h->occ = 1;
       h->attr_set = true;
     }
@@ -707,10 +714,10 @@ struct K2 {
         p.tick_i = (int)h->k2_i;
         if (h->factor_mode == FACTOR_CHOL)
           k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
-                            sizeof(double) * absorb_smem_doubles(h->rowcap, h->npar), h->stream>>>(p, h->d_scratch);
+                            sizeof(double) * absorb_smem_doubles(h->npar), h->stream>>>(p, h->d_scratch);
         else
           k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
-                            sizeof(double) * (2 * h->npar + absorb_smem_doubles(h->rowcap, h->npar)), h->stream>>>(
+                            sizeof(double) * (2 * h->npar + absorb_smem_doubles(h->npar)), h->stream>>>(
               p, h->d_scratch, h->factor_mode);
         h->launches++;
         CK(cudaGetLastError());

@@ -70,7 +70,7 @@ struct mcmcb_handle_s {
   unsigned* d_tile = nullptr;
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
-         *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr;
+         *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr, *d_coef = nullptr;
   double *d_gcm = nullptr, *d_gmean = nullptr, *d_gw = nullptr;  // greedy burn-in accumulators (K2)
   int dp = 0, rowcap = 0, factor_mode = 0;
   long long r_stride = 0, q_stride = 0;
@@ -95,4 +95,8 @@ struct mcmcb_handle_s {
   int dump_head = 0;
   long long dumps_dropped = 0;
   std::string err;
+  // group handle (cfg.ngpus > 1): per-device handles and their NCCL communicators; no device state of its own
+  std::vector<mcmcb_handle_s*> kids;
+  std::vector<void*> nccl_comms;
+  long long nccl_calls = 0;
 };

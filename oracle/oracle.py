@@ -43,10 +43,29 @@ def build(force=False):
     return so
 
 
+_NATIVE = False
+
+
+def use_native(on=True):
+    """Timing only (bench.py's CPU baseline): switch to the -O3 -march=native build of the same source, compiled on
+    the box it runs on.  The parity tests always use the reference-flag build."""
+    global _NATIVE, _LIB
+    if bool(on) != _NATIVE:
+        _NATIVE, _LIB = bool(on), None
+
+
+def _build_native():
+    so = os.path.join(_HERE, "libmcmcoracle_native.so")
+    src = os.path.join(_HERE, "mcmc_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libmcmcoracle_native.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(_build_native() if _NATIVE else build())
         dp = C.POINTER(C.c_double)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.POINTER(Cfg), C.c_int, dp, C.c_long, C.c_int, C.c_int, dp, dp, dp, C.POINTER(C.c_int)]

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_matches_header_size():
     # the ctypes mirror must have the C struct's size; create() rejects a wrong abi_version
     c = mb.default_config()
-    assert c.abi_version == 2
+    assert c.abi_version == 3
     h = C.c_void_p()
     c.abi_version = 99
     assert mb.load_library().mcmcb_create(C.byref(c), C.byref(h)) == -1

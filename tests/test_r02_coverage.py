@@ -1,0 +1,311 @@
+"""Round-2 GPU parity cases the round-1 suite did not reach (VERDICT "untested configs", NS1, N3, ADVICE):
+
+* BASELINE C3 at its batched shape: n = 10^4 data in shared memory, FOUR chains per thread (the tile plan only hands
+  out 4-chain tiles from ~3*10^5 chains up), 350 steps = 3 adaptation ticks with delayed rejection, vs the oracle;
+* BASELINE C5's dimension: SCAM on the 200-parameter hierarchical model (CTA Jacobi at 200 x 200), vs the oracle;
+* BASELINE C4's shape: pooled RAM at d = 50 on the banana target, vs the lock-step oracle;
+* streamed dumps: EVERY popped snapshot (theta, ss, sigma2) vs the oracle's state at that step, K1 and K2;
+* restart files: values of mcmccovf.dat / mcmcmean.dat vs the oracle, and a two-leg run through nmlffile + *f.dat
+  (MCMC_aux.F90:46-83) whose second leg equals an oracle run started from the same files;
+* one handle driving several GPUs (ngpus > 1): shards equal a single-GPU handle bit for bit; pooled ticks over NCCL;
+* a burn-in long enough that the tick kernels' row buffer passes 48 KB (ADVICE: launch used to fail).
+"""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import mcmcf90_b200 as mb
+from oracle import oracle as O
+from tests import cases
+from tests.test_host_driver import HOST, NML_SHIPPED, write_testcase
+
+pytestmark = pytest.mark.gpu
+BLOB11 = mb.models.blob_expreg(cases.DATA_X, cases.DATA_Y)
+CNT = ("stayed", "bndstayed", "draccepted", "drtries", "chainind", "simuind", "ndrawn")
+
+
+def ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def gauss_target(d, rho=0.6):
+    s = 1.0 + 2.0 * np.arange(d) / max(d - 1, 1)
+    sig = rho ** np.abs(np.subtract.outer(np.arange(d), np.arange(d))) * np.outer(s, s)
+    lam = np.linalg.inv(sig)
+    return np.zeros(d), 0.5 * (lam + lam.T)
+
+
+def oracle_chain(nml, model_id, blob, par0, cmat0, sigma2, nobs, seed, chain_id):
+    ch = O.Chain(O.make_cfg(**nml), model_id, blob, par0, cmat0, sigma2, nobs)
+    ch.philox(seed, chain_id)
+    return ch
+
+
+# ------------------------------------------------------------------------------------------------ C3, 4 chains/thread
+def test_c3_four_chains_per_thread_three_ticks_with_dr():
+    N, steps = 148 * 512 * 4 + 4096, 350  # enough chains for full rounds of 4-chain tiles plus smaller tiles
+    x, y = cases.synth_expreg(10000)
+    blob = mb.models.blob_expreg(x, y)
+    nml = dict(nsimu=steps + 1, adaptint=100, drscale=2.0, initcmatn=1, updatesigma=1, N0=1.0, S02=0.5)
+    rng = np.random.default_rng(11)
+    par0 = cases.PAR0 * (1 + 0.01 * rng.normal(size=(N, 2)))
+    cmat0 = cases.CMAT0 * (11.0 / 10000)
+    s = mb.Sampler(mb.default_config(nchains=N, seed=2024, store_chains=0, **nml))
+    s.set_data(blob)
+    s.set_initial(par0, cmat0, [0.5], [10000])
+    s.run(steps)
+    assert s.info()["chains_per_thread"] == 4
+    cnt, par, mean, cm, s2, ss = s.counters(), s.fetch("par"), s.fetch("mean"), s.fetch("cmat"), s.fetch("sigma2"), s.fetch("ss")
+    assert (cnt["status"] == 0).all() and (cnt["simuind"] == steps + 1).all()
+    oblob = O.blob_expreg(x, y)
+    for c in (0, 77777, 148 * 512 * 4 - 1, N - 1):  # first tile, the bulk, the last 4-chain tile, the last small tile
+        ch = oracle_chain(nml, O.MODEL_EXPREG, oblob, par0[c], cmat0, [0.5], [10000], 2024, c)
+        ch.run()
+        r = ch.results()
+        for k in CNT:
+            assert cnt[k][c] == r[k], (c, k)
+        np.testing.assert_allclose(par[c], r["par"], rtol=1e-10)
+        np.testing.assert_allclose(ss[c], r["sschain"][-1, 0], rtol=1e-10)
+        np.testing.assert_allclose(s2[c], r["sigma2"], rtol=1e-10)
+        np.testing.assert_allclose(mean[c], r["mean"], rtol=1e-10)
+        iu = np.triu_indices(2)
+        np.testing.assert_allclose(cm[c][iu], r["cmat"][iu], rtol=1e-7)
+        assert r["drtries"] > 100 and r["chainind"] > 30
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ C5 dimension
+def test_scam_200_parameter_hierarchical_model():
+    G, J, N = 198, 10, 4
+    rng = np.random.default_rng(5)
+    y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
+    d = G + 2
+    blob = mb.models.blob_hier(y)
+    # a covariance that stays full rank with well separated eigenvalues (eigenvectors of a degenerate
+    # covariance are not unique: parity there is distributional)
+    cmat0 = np.diag(0.01 * (1.0 + np.arange(d) / d))
+    nml = dict(method="scam", nsimu=7, adaptint=3, initcmatn=400, updatesigma=0)
+    par0 = 0.1 + 0.01 * rng.normal(size=(N, d))
+    s = mb.Sampler(mb.default_config(nchains=N, seed=9, model="hier", **nml))
+    s.set_data(blob)
+    s.set_initial(par0, cmat0, [1.0], [1])
+    s.run(6)
+    cnt, par, q, ss = s.counters(), s.fetch("par"), s.fetch("qcovstd"), s.fetch("ss")
+    assert (cnt["status"] == 0).all()
+    for c in range(N):
+        ch = oracle_chain(nml, O.MODEL_HIER, O.blob_hier(y), par0[c], cmat0, [1.0], [1], 9, c)
+        ch.run()
+        r = ch.results()
+        for k in CNT:
+            assert cnt[k][c] == r[k], (c, k, cnt[k][c], r[k])
+        np.testing.assert_allclose(par[c], r["par"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(ss[c], r["sschain"][-1, 0], rtol=1e-10)
+        np.testing.assert_allclose(q[c], r["qcovstd"], rtol=1e-8)
+        assert r["ndrawn"] > 6 * d  # two ticks happened and all 200 components were proposed every sweep
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ C4 shape
+def test_pooled_ram_banana_d50():
+    d, N = 50, 64
+    blob = mb.models.blob_banana(d, 0.03)
+    nml = dict(method="ram", nsimu=41, adaptint=20, updatesigma=0, alphatarget=0.234, nuparam=0.7)
+    par0 = 0.1 * np.random.default_rng(6).normal(size=(N, d))
+    s = mb.Sampler(mb.default_config(nchains=N, seed=3, model="banana", pool_adapt=1, **nml))
+    s.set_data(blob)
+    s.set_initial(par0, np.eye(d), [1.0], [1])
+    s.run(40)
+    chains, ticks = O.run_pooled(O.make_cfg(**nml), O.MODEL_BANANA, blob, par0, np.eye(d), [1.0], [1], seed=3)
+    assert len(ticks) == 2
+    cnt, par, R = s.counters(), s.fetch("par"), s.fetch("R")
+    iu = np.triu_indices(d)
+    bad = 0
+    for k, ch in enumerate(chains):
+        r = ch.results()
+        same = all(cnt[key][k] == r[key] for key in CNT)
+        bad += not same
+        if same:
+            np.testing.assert_allclose(par[k], r["par"], rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(R[k][iu], r["R"][iu], rtol=1e-6, atol=1e-9)
+    assert bad <= 2  # dchdd amplifies rounding as ||a|| -> 1: a flip desynchronises a chain for good
+    W, _, S = s.pool_fetch()
+    assert W == N
+    np.testing.assert_allclose(S, ticks[-1][3], rtol=1e-6, atol=1e-9 * np.abs(ticks[-1][3]).max())
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ streamed dumps
+@pytest.mark.parametrize("kernel", ["k1", "k2"])
+def test_every_streamed_snapshot_matches_the_oracle(kernel):
+    N, stride, nsnap = 24, 25, 4
+    if kernel == "k1":
+        nml = dict(cases.NML_DRAM, nsimu=stride * nsnap + 1, adaptint=50)
+        args = ("expreg", BLOB11, np.tile(cases.PAR0, (N, 1)), cases.CMAT0, cases.SIGMA2, cases.NOBS)
+        oid = O.MODEL_EXPREG
+    else:
+        d = 6
+        mu, lam = gauss_target(d)
+        nml = dict(nsimu=stride * nsnap + 1, adaptint=50, drscale=2.0, initcmatn=1, updatesigma=1, N0=4.0, S02=1.0)
+        args = ("gauss", mb.models.blob_gauss(mu, lam), 0.1 * np.random.default_rng(8).normal(size=(N, d)), 0.05 * np.eye(d),
+                [1.0], [3])
+        oid = O.MODEL_GAUSS
+    s = mb.Sampler(mb.default_config(nchains=N, seed=21, model=args[0], dump_stride=stride, **nml))
+    s.set_data(args[1])
+    s.set_initial(*args[2:])
+    snaps = []
+    for _ in range(nsnap):  # pop between runs: the ring holds 4 snapshots
+        s.run(stride)
+        got = s.dump_pop_ex()
+        assert got is not None
+        snaps.append(got)
+    assert s.dump_pop_ex() is None
+    assert [g[0] for g in snaps] == [1 + stride * (k + 1) for k in range(nsnap)]
+    for c in range(N):
+        ch = oracle_chain(nml, oid, args[1], args[2][c], args[3], args[4], args[5], 21, c)
+        for step, par, ss, s2 in snaps:
+            ch.advance(step)
+            r = ch.results()
+            assert r["simuind"] == step
+            np.testing.assert_allclose(par[c], r["par"], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(ss[c], r["sschain"][-1, :-1], rtol=1e-9)
+            np.testing.assert_allclose(s2[c], r["sigma2"], rtol=1e-9)
+    assert np.array_equal(snaps[-1][1], s.fetch("par"))
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ restart files
+def test_restart_files_and_continuation_run(tmp_path):
+    leg1, leg2 = str(tmp_path / "leg1"), str(tmp_path / "leg2")
+    os.makedirs(leg1)
+    nml = NML_SHIPPED.replace("method = 'dram'", "method = 'dram'\n nmlffile = 'final.nml'\n covnfile = 'mcmccovn.dat'") \
+                     .replace("drscale     = 0", "drscale     = 2.0").replace("burnintime  = 1000", "burnintime  = 0") \
+                     .replace("doburnin    = 1", "doburnin    = 0").replace("nsimu       = 1000", "nsimu       = 300") \
+                     .replace("adaptint    = 200", "adaptint    = 50\n initcmatn = 1")
+    write_testcase(leg1, nml, "&mcmcb nchains = 2, seed = 17, store_chains = 1 /\n")
+    # covnfile is read by initialize when it exists (initialize.F90:93-103): absent in leg 1
+    r = subprocess.run([os.path.join(HOST, "mcmcb_main"), leg1], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kw1 = dict(nsimu=300, doadapt=1, adaptint=50, initcmatn=1, burnintime=0, doburnin=0, drscale=2.0, updatesigma=1, N0=1.0,
+               S02=0.0)
+    ch = oracle_chain(kw1, O.MODEL_EXPREG, O.blob_expreg(cases.DATA_X, cases.DATA_Y), cases.PAR0, cases.CMAT0, cases.SIGMA2,
+                      cases.NOBS, 17, 0)
+    ch.run()
+    ref = ch.results()
+    # step 300 is an adaptation tick: the files hold chaincmat / chainmean / chainwsum as MCMC_writechains saves them
+    covf = np.loadtxt(os.path.join(leg1, "mcmccovf.dat"))
+    np.testing.assert_allclose(covf[np.triu_indices(2)], ref["cmat"][np.triu_indices(2)], rtol=1e-8)
+    np.testing.assert_allclose(covf, covf.T, rtol=0, atol=0)
+    np.testing.assert_allclose(np.loadtxt(os.path.join(leg1, "mcmcmean.dat")), ref["mean"], rtol=1e-10)
+    assert float(np.loadtxt(os.path.join(leg1, "mcmccovn.dat"))) == float(int(ref["wsum"]))
+    np.testing.assert_allclose(np.loadtxt(os.path.join(leg1, "mcmcparf.dat")), ref["par"], rtol=1e-10)
+    text = open(os.path.join(leg1, "final.nml")).read()
+    # MCMC_aux.F90:48-52,79-83: initcmatn = int(chainwsum) + simuind, burnintime = 0
+    assert "initcmatn = %d," % (int(ref["wsum"]) + 300) in text and "burnintime = 0," in text
+
+    # ---- leg 2: the user copies the *f.dat files over the inputs and runs with the written namelist
+    shutil.copytree(leg1, leg2)
+    for src, dst in (("mcmccovf.dat", "mcmccov.dat"), ("mcmcparf.dat", "mcmcpar.dat"), ("mcmcsigma2f.dat", "mcmcsigma2.dat"),
+                     ("final.nml", "mcmcinit.nml")):
+        shutil.copy(os.path.join(leg2, src), os.path.join(leg2, dst))
+    r = subprocess.run([os.path.join(HOST, "mcmcb_main"), leg2], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    par0 = np.loadtxt(os.path.join(leg2, "mcmcpar.dat"))
+    cmat0 = np.loadtxt(os.path.join(leg2, "mcmccov.dat"))
+    s2n = np.loadtxt(os.path.join(leg2, "mcmcsigma2.dat"))
+    n0 = int(np.loadtxt(os.path.join(leg2, "mcmccovn.dat")))  # initialize reads initcmatn from covnfile when it exists
+    kw2 = dict(kw1, initcmatn=n0, S02=0.5)  # the written namelist carries S02 = sigma2(1) of leg 1 (MCMC_init.F90:114-116)
+    ch2 = oracle_chain(kw2, O.MODEL_EXPREG, O.blob_expreg(cases.DATA_X, cases.DATA_Y), par0, cmat0, [s2n[0]], [int(s2n[1])], 17, 0)
+    ch2.run()
+    ref2 = ch2.results()
+    chain = np.loadtxt(os.path.join(leg2, "chain.dat"), ndmin=2)
+    assert chain.shape == ref2["chain"].shape and np.array_equal(chain[:, -1], ref2["chain"][:, -1])
+    np.testing.assert_allclose(chain[:, :-1], ref2["chain"][:, :-1], rtol=1e-9)
+    np.testing.assert_allclose(np.loadtxt(os.path.join(leg2, "mcmcmean.dat")), ref2["mean"], rtol=1e-9)
+    assert float(np.loadtxt(os.path.join(leg2, "mcmccovn.dat"))) == float(int(ref2["wsum"]))
+
+
+# ------------------------------------------------------------------------------------------------ long burn-in
+def test_tick_kernels_with_a_row_buffer_beyond_48k():
+    # rowcap = burnintime + 2 adaptint + ... rows: 16 bytes of per-row coefficients used to live in shared memory
+    d, N = 6, 8
+    mu, lam = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    nml = dict(nsimu=5301, adaptint=100, burnintime=5000, doburnin=1, scalelimit=0.05, initcmatn=1, updatesigma=0, drscale=0.0)
+    par0 = 0.1 * np.random.default_rng(3).normal(size=(N, d))
+    s = mb.Sampler(mb.default_config(nchains=N, seed=4, model="gauss", **nml))
+    s.set_data(blob)
+    s.set_initial(par0, 0.05 * np.eye(d), [1.0], [1])
+    s.run(5300)
+    cnt, par = s.counters(), s.fetch("par")
+    assert (cnt["status"] == 0).all()
+    for c in (0, N - 1):
+        ch = oracle_chain(nml, O.MODEL_GAUSS, blob, par0[c], 0.05 * np.eye(d), [1.0], [1], 4, c)
+        ch.run()
+        r = ch.results()
+        for k in CNT:
+            assert cnt[k][c] == r[k], (c, k)
+        np.testing.assert_allclose(par[c], r["par"], rtol=1e-8, atol=1e-10)
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ one handle, n GPUs
+def test_group_handle_of_one_device_equals_plain_handle():
+    nml = dict(cases.NML_DRAM, nsimu=201)
+    out = []
+    for g in (0, 1):
+        s = mb.Sampler(mb.default_config(nchains=100, seed=5, ngpus=g, **nml))
+        s.set_data(BLOB11)
+        s.set_initial(cases.PAR0, cases.CMAT0, cases.SIGMA2, cases.NOBS)
+        s.run(200)
+        out.append((s.fetch("par"), s.fetch("counters")))
+        assert s.ngpus == 1
+        s.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("pool", [0, 1])
+def test_one_handle_drives_two_gpus(pool):
+    if ndev() < 2:
+        pytest.skip("needs 2 GPUs on the box (run under `gpurun --gpus 2`)")
+    N = 1001  # odd: the shards differ in size
+    nml = dict(cases.NML_DRAM, nsimu=301, adaptint=50)
+    par0 = cases.PAR0 * (1 + 0.01 * np.random.default_rng(1).normal(size=(N, 2)))
+
+    def run(ngpus):
+        s = mb.Sampler(mb.default_config(nchains=N, seed=3, ngpus=ngpus, pool_adapt=pool, store_chains=N, dump_stride=100, **nml))
+        s.set_data(BLOB11)
+        s.set_initial(par0, cases.CMAT0, cases.SIGMA2, cases.NOBS)
+        s.run(300)
+        snaps = []
+        while True:
+            g = s.dump_pop_ex()
+            if g is None:
+                break
+            snaps.append(g)
+        res = dict(par=s.fetch("par"), cnt=s.fetch("counters"), cm=s.fetch("cmat"), R=s.fetch("R"), snaps=snaps,
+                   chain=s.fetch_chain(N - 1)["chain"], ngpus=s.ngpus, nccl=s.nccl_calls)
+        if pool:
+            res["pool"] = s.pool_fetch()
+        s.close()
+        return res
+
+    one, two = run(1), run(2)
+    assert one["ngpus"] == 1 and two["ngpus"] == 2
+    assert [g[0] for g in two["snaps"]] == [101, 201, 301]
+    if not pool:  # no collective: results do not depend on the number of devices, bit for bit
+        assert two["nccl"] == 0
+        for k in ("par", "cnt", "cm", "R", "chain"):
+            assert np.array_equal(one[k], two[k]), k
+        for a, b in zip(one["snaps"], two["snaps"]):
+            assert all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+    else:  # pooled ticks: 6 ticks x 2 allreduces over NCCL; block-partial sums are formed per device -> rounding level
+        assert two["nccl"] == 12
+        assert np.array_equal(one["cnt"][:, :6], two["cnt"][:, :6])
+        np.testing.assert_allclose(one["par"], two["par"], rtol=1e-9)
+        np.testing.assert_allclose(one["pool"][2], two["pool"][2], rtol=1e-10)
+        assert one["pool"][0] == two["pool"][0]
+        assert np.array_equal(two["R"], np.broadcast_to(two["R"][0], two["R"].shape))
