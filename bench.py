@@ -132,7 +132,7 @@ class Workload:
         self.cmat0, self.sigma2, self.nobs = np.eye(d), [1.0], [1]
         self.par0 = lambda nn, off: np.zeros((nn, d))
         self.pool, self.bound = 1, "hbm"
-        self.kernel = "k2_step_kernel"
+        self.kernel = "k4_ram_step_kernel"
 
     def _c5(self):
         groups, per = 198, 10

@@ -38,7 +38,7 @@ std::vector<ModelEntry>& registry() {
 }
 int register_model(const ModelEntry& e) {
   for (auto& x : registry())
-    if (std::strcmp(x.name, e.name) == 0 && x.kernel == e.kernel) {
+    if (std::strcmp(x.name, e.name) == 0 && x.kernel == e.kernel && x.npar == e.npar) {
       x = e;
       return 0;
     }
@@ -53,11 +53,12 @@ using namespace mcmcb::launch;
 // the built-in models register themselves from their own translation units (builtin_*.cu), exactly like a
 // user plugin does (include/mcmcb200_plugin.cuh)
 
-const ModelEntry* find_model(const char* name, int kernel) {
+const ModelEntry* find_model(const char* name, int kernel, int npar = -1) {
   // kernel == 0 (auto): a model registered for both kernel families runs on the register kernel (compile-time npar)
+  // when it has a registration for this npar (npar < 0: not known yet -- any), else on the warp-per-chain kernels
   for (int want : {kernel == 0 ? 1 : kernel, kernel == 0 ? 2 : kernel})
     for (auto& e : registry())
-      if (std::strcmp(e.name, name) == 0 && e.kernel == want) return &e;
+      if (std::strcmp(e.name, name) == 0 && e.kernel == want && (npar < 0 || e.npar == 0 || e.npar == npar)) return &e;
   return nullptr;
 }
 
@@ -317,7 +318,7 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
 static void free_dev(mcmcb_handle h) {
   void* ptrs[] = {h->d_st, h->d_ist, h->d_par0, h->d_cmat0, h->d_sigma2, h->d_nobs, h->d_blob, h->d_prior,
                   h->d_inj, h->d_store_rows, h->d_store_cnt, h->d_store_s2, h->d_hist, h->d_tile, h->d_theta, h->d_mean, h->d_Rm,
-                  h->d_cmat, h->d_gcm, h->d_gmean, h->d_gw, h->d_rowbuf, h->d_coef, h->d_scratch, h->d_cmat0_full, h->d_qstd,
+                  h->d_cmat, h->d_gcm, h->d_gmean, h->d_gw, h->d_rowbuf, h->d_coef, h->d_Rp, h->d_scratch, h->d_cmat0_full, h->d_qstd,
                   h->d_pool, h->d_pool_partial, h->d_Rpool, h->d_fail, h->d_diag, h->d_diag_buf, h->d_diag_partial,
                   h->d_fetch};
   for (void* p : ptrs)
@@ -409,6 +410,15 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
     h->npar = npar; h->nycol = nycol; h->initial_set = true;
     return MCMCB_OK;
   }
+  if (!h->d_st) {
+    // now that npar is known: the register kernel if the model has a compile-time registration for it (and the
+    // sampler needs no SVD factor), else its run-time-npar registration for the warp-per-chain kernels
+    const int want = (h->doscam || h->usesvd) ? (h->cfg.kernel == 1 ? 1 : 2) : h->cfg.kernel;
+    const ModelEntry* m = find_model(h->cfg.model, want, npar);
+    if (!m) return h->model->npar > 0 && npar != h->model->npar ? MCMCB_EINVAL : MCMCB_EUNSUPPORTED;
+    if (m->kernel != 1 && h->cfg.method != MCMCB_RAM && h->usesvd && h->cfg.greedy && h->cfg.doburnin) return MCMCB_EUNSUPPORTED;
+    h->model = m;
+  }
   if (h->model->npar > 0 && npar != h->model->npar) return MCMCB_EINVAL;
   if (nycol != h->model->ny) return MCMCB_EINVAL;
   if (par0_stride != 0 && par0_stride < npar) return MCMCB_EINVAL;
@@ -473,6 +483,12 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   // smaller tiles when there are too few chains to fill every warp (MCMCB_K1_BATCH overrides, tuning only)
   h->k1_batch = 1;
   if (const char* e = std::getenv("MCMCB_EXP_DIRECT")) h->k1_exp_direct = e[0] != '0';  // tuning experiments only
+  if (const char* e = std::getenv("MCMCB_K1_SUPERTILE")) h->k1_supertile = e[0] != '0';
+  h->k1_threads = K1_THREADS;
+  if (const char* e = std::getenv("MCMCB_K1_BLOCK")) {
+    const int t = std::atoi(e);
+    if (t >= 32 && t <= K1_THREADS && t % 32 == 0) h->k1_threads = t;
+  }
   {
     const char* e = std::getenv("MCMCB_ER_EXIT");
     h->er_exit = h->cfg.method == MCMCB_ER && e && e[0] == '1';
@@ -958,9 +974,9 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (!h->kids.empty()) return mcmcb_info(h->kids[0], npar, nycol, lanes, kernel, tpb, blocks, smem);
   if (npar) *npar = h->npar;
   if (nycol) *nycol = h->nycol;
-  if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : h->L;
+  if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : (h->k4 ? 1 : h->L);
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
-  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : K1_THREADS;
+  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : h->k1_threads;
   if (blocks) *blocks = h->blocks;
   if (smem) *smem = h->smem;
   return MCMCB_OK;

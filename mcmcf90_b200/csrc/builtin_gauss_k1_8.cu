@@ -1,0 +1,7 @@
+// Built-in user model GaussK<8>: the Gaussian target of testcases/mcmcrun4.F90 with a compile-time npar = 8 for the
+// register kernel, registered like a user plugin registers a model (include/mcmcb200_plugin.cuh).
+#include "models.cuh"
+#include "mcmcb200_plugin.cuh"
+
+using GaussK8 = mcmcb::GaussK<8>;
+MCMCB_REGISTER_MODEL_K1(GaussK8)

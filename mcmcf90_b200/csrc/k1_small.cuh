@@ -91,6 +91,10 @@ struct K1Params {
   double* hist;
   int hist_rows;
   long long tier[3];  // tiles of 4, 2 and 1 sub-tiles, in this order along the chain range (k1_step_kernel)
+  // bulk of a large population: `wtiles` SUPER-tiles, each `rounds` 4-sub-tile tiles run back to back by one warp
+  // (super-tile s = tiles s, s + wtiles, ...); they come first along the chain range, the tiers above follow them
+  long long wtiles;
+  int rounds;
   double exp_c1, exp_c2;    // MCMCB_EXP_C1L / C2L: see mcmcb_expmul_fast for why they travel as parameters
   int exp_dn;               // entries of the direct exp table staged behind the blob (0 = none), mcmcb_expmul_direct
 };
@@ -808,17 +812,27 @@ struct has_ssfunction_batch<M, decltype((void)&M::template ssfunction_batch<2>)>
 // exponential-regression model is bound by shared-memory wavefronts (broadcast data reads + conflicting table
 // lookups), so cutting the data reads per chain-datum is what this buys.  The per-chain arithmetic
 // and its order are those of NB == 1: results are bit-identical.
+//
+// K > 1 (super-tile): every chain slot runs K chains one after the other (chain `first + k * kstride + ...`, k = 0..K-1)
+// and moves on to its next chain as soon as the current one has done its nsteps steps, without waiting for the other
+// slots of the warp.  Under delayed rejection a chain needs nsteps + Binomial(nsteps, q) evaluations; the warp runs
+// until its slowest slot is done, and the maximum over 32 NB slots of a SUM of K such counts is relatively
+// sqrt(K) closer to the mean than the maximum of single counts (the wait for the slowest chain of every tile was
+// ~6 % of the launch on BASELINE C3).  Chains are independent: results do not depend on K.
 template <class M, int L, bool EREXIT, int NB>
-__device__ __forceinline__ void k1_run_tile(const K1Params& p, const mcmcb_ctx& ctx, long long first, int sub, int gl) {
+__device__ __forceinline__ void k1_run_tile(const K1Params& p, const mcmcb_ctx& ctx, long long first, int sub, int gl,
+                                            int K = 1, long long kstride = 0) {
   constexpr int D = M::NPAR, NY = M::NY;
   K1State<D, NY> S[NB];
   double prop[NB][D];
+  int kk[NB];
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     const long long ch = first + b * (32 / L) + sub;  // consecutive lanes, consecutive chains
     S[b].valid = ch < p.nchains;
     k1_load_state<M>(S[b], p, S[b].valid ? ch : p.nchains - 1);
     S[b].stored = S[b].valid && (ch < p.store_chains) && gl == 0;
+    kk[b] = 0;
 #pragma unroll
     for (int k = 0; k < D; k++) prop[b][k] = S[b].th[k];
   }
@@ -863,7 +877,19 @@ __device__ __forceinline__ void k1_run_tile(const K1Params& p, const mcmcb_ctx& 
 #pragma unroll
     for (int b = 0; b < NB; b++) {
       const double prn = M::priorfun(prop[b], D, ctx);
-      if (act[b]) k1_finish<M>(&S[b], &p, prop[b], ssn[b], prn, inb[b]);
+      if (act[b]) {
+        k1_finish<M>(&S[b], &p, prop[b], ssn[b], prn, inb[b]);
+        if (K > 1 && S[b].phase == 0 && S[b].done >= p.nsteps && kk[b] + 1 < K) {  // this slot's next chain
+          if (S[b].valid && gl == 0) k1_store_state<M>(S[b], p);
+          kk[b]++;
+          const long long ch = first + (long long)kk[b] * kstride + b * (32 / L) + sub;
+          S[b].valid = ch < p.nchains;
+          k1_load_state<M>(S[b], p, S[b].valid ? ch : p.nchains - 1);
+          S[b].stored = S[b].valid && (ch < p.store_chains) && gl == 0;
+#pragma unroll
+          for (int k = 0; k < D; k++) prop[b][k] = S[b].th[k];
+        }
+      }
     }
   }
 #pragma unroll
@@ -904,19 +930,23 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_step_kernel(const __grid_con
   ctx.exp_td = p.exp_dn > 0 ? mcmcb_exp_direct_base(exp_direct, p.exp_dn) : 0u;
 
   const long long t4 = p.tier[0], t2 = p.tier[1], t1 = p.tier[2];
+  const long long ws = (B >= 4 && p.rounds > 0) ? p.wtiles : 0;  // super-tiles come first in the work queue
+  const long long base = ws * p.rounds * 4 * SUB;                // first chain after the super-tiles' range
   for (;;) {
     unsigned tile = 0;
     if (lane == 0) tile = atomicAdd(p.tile_counter, 1u);
     tile = __shfl_sync(FULL, tile, 0);
-    const long long t = tile;
-    if (t >= t4 + t2 + t1) break;
+    long long t = tile;
+    if (t >= ws + t4 + t2 + t1) break;
     if constexpr (B >= 4) {
-      if (t < t4) { k1_run_tile<M, L, EREXIT, 4>(p, ctx, t * 4 * SUB, sub, gl); continue; }
+      if (t < ws) { k1_run_tile<M, L, EREXIT, 4>(p, ctx, t * 4 * SUB, sub, gl, p.rounds, ws * 4 * SUB); continue; }
+      t -= ws;
+      if (t < t4) { k1_run_tile<M, L, EREXIT, 4>(p, ctx, base + t * 4 * SUB, sub, gl); continue; }
     }
     if constexpr (B >= 2) {
-      if (t < t4 + t2) { k1_run_tile<M, L, EREXIT, 2>(p, ctx, (t4 * 4 + (t - t4) * 2) * SUB, sub, gl); continue; }
+      if (t < t4 + t2) { k1_run_tile<M, L, EREXIT, 2>(p, ctx, base + (t4 * 4 + (t - t4) * 2) * SUB, sub, gl); continue; }
     }
-    k1_run_tile<M, L, EREXIT, 1>(p, ctx, (t4 * 4 + t2 * 2 + (t - t4 - t2)) * SUB, sub, gl);
+    k1_run_tile<M, L, EREXIT, 1>(p, ctx, base + (t4 * 4 + t2 * 2 + (t - t4 - t2)) * SUB, sub, gl);
   }
 }
 

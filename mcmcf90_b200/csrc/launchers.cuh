@@ -15,6 +15,7 @@
 #include "k2_large.cuh"
 #include "k2g_group.cuh"
 #include "k3_scam.cuh"
+#include "k4_ram.cuh"
 #include "mcmcb200.h"
 #include "pool.cuh"
 #include "registry.h"
@@ -283,13 +284,13 @@ struct K1 {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!h->attr_set) {
       int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K1_THREADS, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->k1_threads, smem));
       if (occ < 1) occ = 1;
       h->occ = occ;
       h->attr_set = true;
     }
     const long long subs = (h->cfg.nchains * L + 31) / 32;  // sub-tiles: the chains one warp owns with one chain per thread
-    const long long wpb = K1_THREADS / 32;
+    const long long wpb = h->k1_threads / 32;
     const long long need = (subs + wpb - 1) / wpb;
     long long blocks = std::min<long long>((long long)h->num_sms * h->occ, need);
     if (blocks < 1) blocks = 1;
@@ -301,7 +302,15 @@ struct K1 {
     q.exp_dn = exp_dn;
     const long long W = blocks * wpb;
     long long n4 = 0, n2 = 0, n1 = 0, rem = subs;
-    if (B >= 4) { n4 = (rem / (4 * W)) * W; rem -= 4 * n4; }
+    // full rounds of 4-sub-tile tiles: one super-tile per warp, its `rounds` tiles run back to back (k1_run_tile)
+    q.rounds = 0; q.wtiles = 0;
+    if (B >= 4 && h->k1_supertile) {
+      q.rounds = (int)(rem / (4 * W));
+      q.wtiles = q.rounds > 0 ? W : 0;
+      rem -= 4 * W * q.rounds;
+    } else if (B >= 4) {
+      n4 = (rem / (4 * W)) * W; rem -= 4 * n4;
+    }
     if (B >= 4 && rem > 3 * W) { n4 += (rem + 3) / 4; rem = 0; }
     if (B >= 4 && rem > 2 * W) { n2 = W; rem -= 2 * W; }           // 2 + 1 per warp
     else if (B >= 2 && B < 4) { n2 = (rem / (2 * W)) * W; rem -= 2 * n2; }
@@ -309,7 +318,7 @@ struct K1 {
     n1 = rem;
     q.tier[0] = n4; q.tier[1] = n2; q.tier[2] = n1;
     CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
-    kern<<<(unsigned)blocks, K1_THREADS, smem, h->stream>>>(q);
+    kern<<<(unsigned)blocks, h->k1_threads, smem, h->stream>>>(q);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -535,7 +544,8 @@ struct K2 {
     const bool greedy = c.greedy && c.doburnin && c.method != MCMCB_RAM && h->factor_mode == FACTOR_CHOL;
     // plain AM (no burn-in branch, no AP window): every adaptint-th step is a tick that empties the buffer, so at most
     // adaptint rows are logged between two ticks (at d = 200 a row is 1.6 KB: 2^18 SCAM chains keep 43 GB instead of 85)
-    if (!c.doburnin && c.adapthist <= 1 && c.adaptint > 0 && (c.badaptint <= 0 || c.badaptint == c.adaptint)) h->rowcap = c.adaptint + 2;
+    if (!c.doburnin && c.burnintime == 0 && c.adapthist <= 1 && c.adaptint > 0 && (c.badaptint <= 0 || c.badaptint == c.adaptint))
+      h->rowcap = c.adaptint + 2;
     if (c.method == MCMCB_RAM || (!c.doadapt && !greedy)) h->rowcap = 1;
     CK(cudaMalloc(&h->d_st, sizeof(double) * (size_t)Lo.nf * h->pitch));
     CK(cudaMalloc(&h->d_ist, sizeof(int) * (size_t)Lo.i_nf * h->pitch));
@@ -655,6 +665,32 @@ struct K2 {
     return 0;
   }
 
+  // thread-per-chain RAM kernel (k4_ram.cuh): when the population gives every lane of every resident warp a chain
+  static bool use_k4(mcmcb_handle h) {
+    const mcmcb_config& c = h->cfg;
+    if (c.method != MCMCB_RAM || !c.doadapt || h->factor_mode != FACTOR_CHOL || h->npar > K4_DM) return false;
+    if (const char* e = getenv("MCMCB_K4")) return e[0] == '1';  // tuning / tests: force on or off
+    return c.nchains >= (long long)h->num_sms * 64;
+  }
+
+  static int launch_k4(mcmcb_handle h, const K2Params& p) {
+    const int d = h->npar;
+    const size_t T = (size_t)d * (d + 1) / 2;
+    const long long N = h->cfg.nchains;
+    if (!h->d_Rp) CK(cudaMalloc(&h->d_Rp, sizeof(double) * T * (size_t)h->pitch));
+    const unsigned blocks = (unsigned)((N + K4_THREADS - 1) / K4_THREADS);
+    k4_pack_kernel<<<blocks, K4_THREADS, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
+    k4_ram_step_kernel<M><<<blocks, K4_THREADS, 0, h->stream>>>(p, h->d_Rp);
+    k4_unpack_kernel<<<blocks, K4_THREADS, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
+    h->launches += 3;
+    h->blocks = (int)blocks;
+    h->smem = 0;
+    h->k2_warps = K4_THREADS / 32;
+    h->k4 = true;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   static bool is_tick(const mcmcb_config& c, long long i) {
     if (c.method == MCMCB_RAM) return false;
     if (!c.doadapt && !c.doburnin) return false;
@@ -665,6 +701,12 @@ struct K2 {
 
   static int step(mcmcb_handle h, int nsteps) {
     const mcmcb_config& c = h->cfg;
+    if (use_k4(h)) {  // RAM has no adaptation ticks: one launch for the whole call
+      if (nsteps == 0 && h->k2_i > 1) return 0;
+      const int rc = launch_k4(h, params(h, nsteps));
+      h->k2_i += nsteps;
+      return rc;
+    }
     // the blob shares shared memory with the per-warp vectors
     // shared-memory plan: K2_MAX_WARPS warps per CTA (latency hiding: these kernels are issue/latency bound),
     // the model blob beside the per-warp vectors when it fits.  RAM rewrites its factor every step, so for RAM

@@ -262,6 +262,51 @@ struct GaussN {
   }
 };
 
+// The same Gaussian target with a COMPILE-TIME number of parameters, for the register kernel (thread or lane group per
+// chain): testcases/mcmcrun4.F90 has npar = 5 (mcmcrun4.F90:11), and a warp per chain would idle 27 of its 32 lanes on
+// it.  Registered under the same name "gauss" for D = 3..8 (builtin_gauss_k1_*.cu); mcmcb_set_initial picks the
+// register kernel when the run-time npar has a registration (and the sampler needs no SVD factor), else the
+// warp-per-chain kernel.  Same blob as GaussN.
+template <int D>
+struct GaussK {
+  static constexpr int NPAR = D;
+  static constexpr int NY = 1;
+  static const char* name() { return "gauss"; }
+  __device__ __forceinline__ static bool checkbounds(const double*, int, const mcmcb_ctx&) { return true; }
+  __device__ __forceinline__ static double priorfun(const double* theta, int len, const mcmcb_ctx& c) {
+    return mcmcb_default_priorfun(theta, len, c);
+  }
+  __device__ __forceinline__ static void ssfunction(const double* theta, int, int, const mcmcb_ctx& c, double* ss) {
+    constexpr int dpad = (D + 1) & ~1;
+    const double* __restrict__ mu = c.data + 2;
+    const double* __restrict__ lam = c.data + 2 + dpad;
+    double df[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) df[j] = theta[j] - mu[j];
+    double acc = 0.0;
+    if (c.nlanes == 1) {  // one lane owns the chain: rows in order, like the reference's matmul + dot_product
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) w = fma(lam[j * D + i], df[j], w);
+        acc = fma(w, df[i], acc);
+      }
+    } else {
+      for (int i = c.lane; i < D; i += c.nlanes) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) w = fma(lam[j * D + i], df[j], w);
+        double dfi = df[0];
+#pragma unroll
+        for (int j = 1; j < D; j++) dfi = (j == i) ? df[j] : dfi;  // df[i] without a dynamically indexed local array
+        acc = fma(w, dfi, acc);
+      }
+    }
+    ss[0] = acc;
+  }
+};
+
 // Twisted Gaussian ("banana"): phi = (t1, t2 + b t1^2 - 100 b, t3..td),
 // ss = phi1^2/100 + sum_{i>=2} phi_i^2.   blob: [d, b]
 struct BananaN {

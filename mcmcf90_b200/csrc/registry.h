@@ -65,16 +65,19 @@ struct mcmcb_handle_s {
   double* d_hist = nullptr;  // AP window ring of the register kernel (adapthist > 1)
   int hist_rows = 0;
   bool er_exit = false;  // method 'er': run the early-exit kernel (MCMCB_ER_EXIT=1)
+  int k1_threads = 512;       // threads per CTA of the register kernel (<= MCMCB_K1_THREADS; MCMCB_K1_BLOCK overrides)
+  bool k1_supertile = true;   // bulk of a large population as per-warp super-tiles (MCMCB_K1_SUPERTILE=0: off)
   bool k1_exp_direct = true;  // stage the direct exp table in the shared memory left over (MCMCB_EXP_DIRECT=0: off)
   int k1_batch = 1;  // chains per thread of the register kernel (thread-per-chain mapping only)
   unsigned* d_tile = nullptr;
   // large-npar kernel (K2): per-chain vectors [chain][dp] and matrices [chain][d*d]
   double *d_theta = nullptr, *d_mean = nullptr, *d_Rm = nullptr, *d_cmat = nullptr, *d_rowbuf = nullptr,
-         *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr, *d_coef = nullptr;
+         *d_scratch = nullptr, *d_cmat0_full = nullptr, *d_qstd = nullptr, *d_coef = nullptr, *d_Rp = nullptr;
   double *d_gcm = nullptr, *d_gmean = nullptr, *d_gw = nullptr;  // greedy burn-in accumulators (K2)
   int dp = 0, rowcap = 0, factor_mode = 0;
   long long r_stride = 0, q_stride = 0;
   bool r_resident = false;
+  bool k4 = false;  // the thread-per-chain RAM kernel (k4_ram.cuh) ran the last launch
   int k2_warps = 8;
   int k2_group_threads = 0;  // > 0: the group-of-warps-per-chain kernel (k2g_group.cuh) runs, this many threads per chain
   long long k2_i = 1;  // simuind shared by all chains of the handle

@@ -46,6 +46,8 @@ def plan(W, iters):
     if W.kernel == "k1_step_kernel":
         return max(iters, W.nml.get("adaptint", iters)), iters
     a = W.nml["adaptint"]
+    if W.kernel == "k4_ram_step_kernel":  # one launch per mcmcb_run piece; pooled runs are cut at the pooled ticks
+        return a - 1, min(iters, a)
     return a - 1, min(iters, a - 1)
 
 
