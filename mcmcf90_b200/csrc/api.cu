@@ -309,7 +309,11 @@ extern "C" int mcmcb_create(const mcmcb_config* cfg, mcmcb_handle* out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MCMCB_ECUDA; }
   h->store_chains = c.store_chains < 0 ? (int)std::min<long long>(c.nchains, 1 << 30) : (int)std::min<long long>(c.store_chains, c.nchains);
+  // npar is fixed by the model only if every registration of this name a later mcmcb_set_initial may pick agrees on it
+  // (a name registered for several compile-time npar, or for the run-time-npar kernels too: known at set_initial)
   h->npar = h->model->npar;
+  for (auto& e : registry())
+    if (std::strcmp(e.name, c.model) == 0 && (c.kernel == 0 || e.kernel == c.kernel) && e.npar != h->npar) h->npar = 0;
   h->nycol = h->model->ny;
   *out = h;
   return MCMCB_OK;
@@ -485,10 +489,6 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   if (const char* e = std::getenv("MCMCB_EXP_DIRECT")) h->k1_exp_direct = e[0] != '0';  // tuning experiments only
   if (const char* e = std::getenv("MCMCB_K1_SUPERTILE")) h->k1_supertile = e[0] != '0';
   h->k1_threads = K1_THREADS;
-  if (const char* e = std::getenv("MCMCB_K1_BLOCK")) {
-    const int t = std::atoi(e);
-    if (t >= 32 && t <= K1_THREADS && t % 32 == 0) h->k1_threads = t;
-  }
   {
     const char* e = std::getenv("MCMCB_ER_EXIT");
     h->er_exit = h->cfg.method == MCMCB_ER && e && e[0] == '1';
@@ -500,6 +500,14 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
     int want = h->blob_n >= 2048 ? MCMCB_K1_DEFAULT_BATCH : 1;
     if (const char* e = std::getenv("MCMCB_K1_BATCH")) want = std::atoi(e);
     h->k1_batch = (want == 2 || want == 4) ? want : 1;
+  }
+  // CTA size of the register kernel.  With four chains per thread the chains in flight keep ~1.3 KB of local-memory state
+  // per thread; 384 threads per CTA run as fast as 512 (8.85e7 against 8.87e7 chain-steps/s on BASELINE C3) and move
+  // 36 GB instead of 65 GB through HBM per launch (profiles/r02_ab_k1_block.txt); 256: 12 GB, 2.5 % slower.
+  if (h->k1_batch == 4 && K1_THREADS >= 384) h->k1_threads = 384;
+  if (const char* e = std::getenv("MCMCB_K1_BLOCK")) {
+    const int t = std::atoi(e);
+    if (t >= 32 && t <= K1_THREADS && t % 32 == 0) h->k1_threads = t;
   }
   int rc = h->model->init(h);
   if (rc) return rc;

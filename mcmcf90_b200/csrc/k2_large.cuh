@@ -499,6 +499,9 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   double* mean = p.mean + c * p.dp;
   double* theta = p.theta + c * p.dp;
   double* rb = p.rowbuf + (size_t)c * (p.rowcap + 1) * (d + 1);
+  // the factorisation's work matrix stays in this chain's slice of the global scratch (L2): a d x d copy in shared memory
+  // (80 KB at d = 100) was measured SLOWER on BASELINE C2 -- 10.5 ms per tick against 7.5 -- because it leaves two CTAs per
+  // SM where eight hide each other's barrier latency (profiles/r02_summary.md)
   double* tmp = scratch + (size_t)c * d * d;
   const int ma = cf.adaptint > 0 ? i % cf.adaptint : 1;
   const int mb = cf.badaptint > 0 ? i % cf.badaptint : 1;

@@ -18,8 +18,8 @@
 //     into Rp before the launch and back after it (k4_pack / k4_unpack: 2 x 30 KB per chain per launch against
 //     ~35 KB per chain per STEP), so pooled ticks, fetches and checkpoints do not know this kernel exists.
 //
-// Algorithmic HBM bytes per chain-step: 16 d(d+1)/2 + state.  This kernel moves 8 T for the proposal,
-// 16 T for an update, 24 T for a downdate (T = d(d+1)/2).
+// Algorithmic HBM bytes per chain-step: 16 d(d+1)/2 + state.  This kernel reads the factor twice and
+// writes it twice per step (32 T bytes, T = d(d+1)/2): the sweeps that rewrite it also form the next proposal.
 //
 // Operation order: proposal = dtrmv('u','t','n') (matutils.F90:108-109), dchud / dchdd / drotg / dnrm2 as the
 // register kernel's (k1_small.cuh), i.e. the reference's; draws in the reference's order from the chain's own stream.
@@ -29,6 +29,7 @@
 namespace mcmcb {
 
 constexpr int K4_THREADS = 128;
+constexpr int K4_U = 8;               // factor elements loaded ahead of the dependent recurrences (memory-level parallelism)
 constexpr int K4_DM = 32 * K2_MAXM;  // largest npar (local arrays are sized for it; only npar entries are touched)
 
 __host__ __device__ constexpr size_t k4_pk(int i, int j) { return (size_t)j * (j + 1) / 2 + i; }  // i <= j
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_ram_step_kernel(const __grid_co
   int* ist = p.ist + cc;
   double* gth = p.theta + cc * p.dp;
 
-  double th[K4_DM], z[K4_DM], prop[K4_DM], cv[K4_DM], sv[K4_DM];
+  double th[K4_DM], zbuf[2][K4_DM], prop[K4_DM], cv[K4_DM], sv[K4_DM];
   for (int k = 0; k < d; k++) { th[k] = gth[k]; prop[k] = th[k]; }
   double ss1[NY], s2[NY];
 #pragma unroll
@@ -103,16 +104,54 @@ __global__ void __launch_bounds__(K4_THREADS) k4_ram_step_kernel(const __grid_co
       for (int k = 0; k < NY; k++) { srow[d + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
     }
   }
+  // The factor is streamed TWICE per step, not four times: the pass that rewrites it (update: one ascending sweep;
+  // downdate: solve sweep + rotation sweep) also forms the NEXT step's proposal R'z from the columns it has just
+  // finished, with that step's normals drawn right after this step's last draw (the adaptation itself draws nothing,
+  // so the chain's draw order is the reference's).  Lanes of a warp that update and lanes that downdate share the
+  // loads of the first sweep.  The last step of a launch does not look ahead: a launch leaves no pre-drawn state.
+  int zi = 0;
+  bool have_prop = false;
+  double su2 = 0.0;
   while (done < p.nsteps) {
-    // ---------------- proposal theta + R'z (MCMC_propose_ram, MCMC_run_ram.F90:87-101; dtrmv order)
-    double su2 = 0.0;
-    for (int k = 0; k < d; k++) { z[k] = g.normal(); }
-    for (int k = 0; k < d; k++) su2 += z[k] * z[k];  // sum(u**2), MCMC_run_ram.F90:168-170
-    for (int j = d - 1; j >= 0; j--) {
-      const double* col = R + k4_pk(0, j) * P;
-      double acc = z[j] * col[(size_t)j * P];
-      for (int i = j - 1; i >= 0; i--) acc += col[(size_t)i * P] * z[i];
-      prop[j] = th[j] + acc;
+    double* z = zbuf[zi];
+    if (!have_prop) {
+      // ---------------- proposal theta + R'z (MCMC_propose_ram, MCMC_run_ram.F90:87-101; dtrmv order)
+      su2 = 0.0;
+      for (int k = 0; k < d; k++) { z[k] = g.normal(); }
+      for (int k = 0; k < d; k++) su2 += z[k] * z[k];  // sum(u**2), MCMC_run_ram.F90:168-170
+      // The column sums are formed in the order the fused sweeps below would have used had the previous step run in
+      // this launch (descending rows after a downdate = dtrmv's own order, ascending otherwise), so that a run does
+      // not depend, bit for bit, on how it is cut into launches.
+      bool desc = false;
+      if (simuind > 1 && c.doadapt && !(simuind < c.burnintime && c.doburnin))
+        desc = 1.0 / pow((double)(float)simuind, c.nuparam) * (rama - c.alphatarget) < 0.0;
+      for (int j = 0; j < d; j++) {
+        const double* col = R + k4_pk(0, j) * P;
+        double acc = 0.0;
+        if (desc) {
+          int r = j;
+          for (; r >= K4_U - 1; r -= K4_U) {  // K4_U loads in flight before the dependent sum consumes them
+            double rv[K4_U];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) rv[u] = col[(size_t)(r - u) * P];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) acc += rv[u] * z[r - u];
+          }
+          for (; r >= 0; r--) acc += col[(size_t)r * P] * z[r];
+          prop[j] = th[j] + acc;
+        } else {
+          int r = 0;
+          for (; r + K4_U <= j; r += K4_U) {
+            double rv[K4_U];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) rv[u] = col[(size_t)(r + u) * P];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) acc += rv[u] * z[r + u];
+          }
+          for (; r < j; r++) acc += col[(size_t)r * P] * z[r];
+          prop[j] = th[j] + (acc + col[(size_t)j * P] * z[j]);
+        }
+      }
     }
     const bool inb = M::checkbounds(prop, d, ctx);
     double ssn[NY];
@@ -167,32 +206,77 @@ __global__ void __launch_bounds__(K4_THREADS) k4_ram_step_kernel(const __grid_co
         for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
       }
     }
-    // ---------------- MCMC_adapt_ram, MCMC_run_ram.F90:104-179
+    // ---------------- MCMC_adapt_ram (MCMC_run_ram.F90:104-179) fused with the next step's proposal
+    int mode = 0;  // 0: factor unchanged, 1: cholupdate (dchud.f:122-139), 2: choldowndate (dchdd.f:141-179)
+    double a = 0.0;
     if (c.doadapt && !(i < c.burnintime && c.doburnin)) {
-      const double a = 1.0 / pow((double)(float)i, c.nuparam) * (rama - c.alphatarget);
-      if (a >= 0.0) {  // cholupdate(R, u/sum(u**2)*a): dchud.f:122-139, column by column
-        for (int j = 0; j < d; j++) {
-          double* col = R + k4_pk(0, j) * P;
-          double xj = z[j] / su2 * a;
-          for (int r = 0; r < j; r++) {
-            const double rij = col[(size_t)r * P];
+      a = 1.0 / pow((double)(float)i, c.nuparam) * (rama - c.alphatarget);
+      mode = (a >= 0.0) ? 1 : 2;
+    }
+    const bool last = done + 1 >= p.nsteps;
+    double* zn = zbuf[zi ^ 1];
+    double su2n = 0.0;
+    if (!last) {
+      for (int k = 0; k < d; k++) { zn[k] = g.normal(); }
+      for (int k = 0; k < d; k++) su2n += zn[k] * zn[k];
+    } else {
+      for (int k = 0; k < d; k++) zn[k] = 0.0;  // the look-ahead sums below are formed and dropped
+    }
+    if (mode != 0 || !last) {
+      // ---- sweep 1, ascending: update lanes rotate and finish their columns; downdate lanes solve R'a = x;
+      //      lanes whose factor stays as it is only form the next proposal
+      for (int j = 0; j < d; j++) {
+        double* col = R + k4_pk(0, j) * P;
+        double xj = (mode == 1) ? z[j] / su2 * a : ((mode == 2) ? -z[j] / su2 * a : 0.0);
+        double acc = 0.0;  // modes 0, 1: next proposal's column sum; mode 2: the solve's ddot
+        int r = 0;
+        for (; r + K4_U <= j; r += K4_U) {
+          double rv[K4_U];
+#pragma unroll
+          for (int u = 0; u < K4_U; u++) rv[u] = col[(size_t)(r + u) * P];
+          if (mode == 1) {
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) {
+              const double t = cv[r + u] * rv[u] + sv[r + u] * xj;
+              xj = cv[r + u] * xj - sv[r + u] * rv[u];
+              col[(size_t)(r + u) * P] = t;
+              acc += t * zn[r + u];
+            }
+          } else if (mode == 2) {
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) acc += rv[u] * sv[r + u];
+          } else {
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) acc += rv[u] * zn[r + u];
+          }
+        }
+        for (; r < j; r++) {
+          const double rij = col[(size_t)r * P];
+          if (mode == 1) {
             const double t = cv[r] * rij + sv[r] * xj;
             xj = cv[r] * xj - sv[r] * rij;
             col[(size_t)r * P] = t;
+            acc += t * zn[r];
+          } else if (mode == 2) {
+            acc += rij * sv[r];
+          } else {
+            acc += rij * zn[r];
           }
-          double rjj = col[(size_t)j * P], cj, sj;
+        }
+        double rjj = col[(size_t)j * P];
+        if (mode == 1) {
+          double cj, sj;
           drotg(rjj, xj, cj, sj);
           col[(size_t)j * P] = rjj;
           cv[j] = cj; sv[j] = sj;
+          prop[j] = th[j] + (acc + rjj * zn[j]);
+        } else if (mode == 2) {
+          sv[j] = (xj - acc) / rjj;  // dchdd.f:142-147
+        } else {
+          prop[j] = th[j] + (acc + rjj * zn[j]);
         }
-      } else {  // choldowndate(R, -u/sum(u**2)*a): dchdd.f:141-179
-        sv[0] = (-z[0] / su2 * a) / R[0];
-        for (int j = 1; j < d; j++) {
-          const double* col = R + k4_pk(0, j) * P;
-          double t = 0.0;
-          for (int r = 0; r < j; r++) t += col[(size_t)r * P] * sv[r];
-          sv[j] = ((-z[j] / su2 * a) - t) / col[(size_t)j * P];
-        }
+      }
+      if (mode == 2) {
         double norm;
         if (d == 1) {
           norm = fabs(sv[0]);
@@ -207,7 +291,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_ram_step_kernel(const __grid_co
           }
           norm = scale * sqrt(ssq);
         }
-        if (!(norm < 1.0)) {
+        const bool ok = norm < 1.0;
+        if (!ok) {
           status |= MCMCB_ST_DOWNDATE_FAIL;  // the reference stops here (matutils.F90:716-722): flag, skip the update
         } else {
           double alpha = sqrt(1.0 - norm * norm);
@@ -219,19 +304,46 @@ __global__ void __launch_bounds__(K4_THREADS) k4_ram_step_kernel(const __grid_co
             sv[r] = bb / nr;
             alpha = scale * nr;
           }
-          for (int j = 0; j < d; j++) {
-            double* col = R + k4_pk(0, j) * P;
-            double xx = 0.0;
-            for (int r = j; r >= 0; r--) {
-              const double rij = col[(size_t)r * P];
-              const double t = cv[r] * xx + sv[r] * rij;
-              col[(size_t)r * P] = cv[r] * rij - sv[r] * xx;
-              xx = t;
+        }
+        // ---- sweep 2, columns descending like dchdd.f:171-179: apply the rotations (when the downdate exists) and
+        //      form the next proposal from the finished columns, in dtrmv's own order
+        for (int j = 0; j < d; j++) {
+          double* col = R + k4_pk(0, j) * P;
+          double xx = 0.0, acc = 0.0;
+          int r = j;
+          for (; r >= K4_U - 1; r -= K4_U) {
+            double rv[K4_U];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) rv[u] = col[(size_t)(r - u) * P];
+#pragma unroll
+            for (int u = 0; u < K4_U; u++) {
+              double nr = rv[u];
+              if (ok) {
+                const double t = cv[r - u] * xx + sv[r - u] * rv[u];
+                nr = cv[r - u] * rv[u] - sv[r - u] * xx;
+                col[(size_t)(r - u) * P] = nr;
+                xx = t;
+              }
+              acc += nr * zn[r - u];
             }
           }
+          for (; r >= 0; r--) {
+            double nr = col[(size_t)r * P];
+            if (ok) {
+              const double t = cv[r] * xx + sv[r] * nr;
+              const double v = cv[r] * nr - sv[r] * xx;
+              col[(size_t)r * P] = v;
+              xx = t;
+              nr = v;
+            }
+            acc += nr * zn[r];
+          }
+          prop[j] = th[j] + acc;
         }
       }
     }
+    have_prop = !last;
+    if (!last) { zi ^= 1; su2 = su2n; }
     if (g.exhausted) status |= MCMCB_ST_RNG_EXHAUSTED;
     done++;
   }

@@ -46,15 +46,24 @@ def test_golden_run_lengths_are_consistent():
                                        ("gauss_dram", 1e-9), ("gauss_ram", 1e-8), ("gauss_er", 1e-9), ("gauss_ap", 1e-9),
                                        ("gauss_greedy", 1e-9)])
 def test_cuda_path_reproduces_golden(name, rtol):
+    # the 6-dimensional Gaussian cases run on BOTH kernel families: "gauss" has a compile-time-npar registration for the
+    # register kernel at npar = 6 (the automatic choice) and the run-time-npar one for the warp-per-chain kernels
+    for kernel in ((0, 2) if name.startswith("gauss_") else (0,)):
+        _golden_case(name, rtol, kernel)
+
+
+def _golden_case(name, rtol, kernel):
     model_id, blob, par0, cmat0, sigma2, nobs = G.inputs(name)
     model = {O.MODEL_EXPREG: "expreg", O.MODEL_HIER: "hier", O.MODEL_GAUSS: "gauss"}[model_id]
     N = 3  # the same stream in every chain: all chains must reproduce the golden run
-    cfg = mb.default_config(nchains=N, store_chains=-1, model=model, rng_mode=mb.RNG_INJECTED, **G.CASES[name])
+    cfg = mb.default_config(nchains=N, store_chains=-1, model=model, rng_mode=mb.RNG_INJECTED, kernel=kernel, **G.CASES[name])
     s = mb.Sampler(cfg)
     s.set_data(blob)
     s.set_initial(np.asarray(par0, dtype=float), cmat0, sigma2, nobs)
     s.inject_uniforms(np.tile(G.uniforms(name), (N, 1)))
     s.run(G.NSIMU - 1)
+    if name.startswith("gauss_"):
+        assert s.info()["kernel"] == (2 if kernel == 2 else 1)
     cnt = s.counters()
     par = s.fetch("par")
     for c in range(N):

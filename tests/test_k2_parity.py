@@ -24,7 +24,9 @@ def gauss_target(d, rho=0.9, seed=0):
 
 def run_gpu(nml, N, model, blob, par0, cmat0, u=None, seed=0, splits=None, chain_offset=0, sigma2=(1.0,), nobs=(1,),
             prior=None):
-    cfg = mb.default_config(nchains=N, seed=seed, store_chains=-1, model=model, chain_offset=chain_offset,
+    # kernel=2: these are the parity tests of the warp-per-chain kernels ("gauss" at npar = 3..6, 8 would otherwise take
+    # its compile-time-npar registration for the register kernel, tests/test_r02_coverage.py)
+    cfg = mb.default_config(nchains=N, seed=seed, store_chains=-1, model=model, chain_offset=chain_offset, kernel=2,
                             rng_mode=mb.RNG_INJECTED if u is not None else mb.RNG_PHILOX, **nml)
     s = mb.Sampler(cfg)
     s.set_data(blob)
