@@ -418,6 +418,7 @@ def run_ours(args):
     rows = float((c1["chainind"] - c0["chainind"]).sum()) / (N * done_steps)
     stay = float((c1["stayed"] - c0["stayed"]).sum()) / (N * done_steps)
     status_bad = int((c1["status"] != 0).sum())
+    info = s.info()
 
     # ---- end to end through the C ABI with host buffers, from the steady state of the chains above
     e2e = None
@@ -493,6 +494,8 @@ def run_ours(args):
                          "algorithmic_flops_per_chain_step": fl})
             if W.ndata:
                 roof["datum_evals_per_s"] = rate_gpu * (1 + q) * W.ndata * (W.d if W.name == "c5" else 1)
+            if W.name == "c3":  # round 1's definition, for continuity: the 9 FP64 instructions (16 flops) of the datum loop only
+                roof["frac_hw_datum_loop"] = roof["datum_evals_per_s"] * 16 / 1e12 / sustained
         else:
             by = W.hbm_bytes_per_step(q)
             achieved = rate_gpu * by / 1e9
@@ -521,13 +524,14 @@ def run_ours(args):
         cpu = None
         if ngpus_total == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(W, cores)
-        info = None
         line = {
             "metric": "chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": ngpus_total,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(W, args, per_gpu, args.scaling), processes=world, gpus_per_process=G,
-                           source_hash=source_hash()),
+                           source_hash=source_hash(), lanes_per_chain=info["lanes_per_chain"],
+                           chains_per_thread=info["chains_per_thread"], blocks=info["blocks"],
+                           threads_per_block=info["threads_per_block"], smem_bytes=info["smem_bytes"]),
             "clocks": clk,
             "gpu_launches": int(launches),
             "roofline": roof,

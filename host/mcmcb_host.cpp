@@ -176,6 +176,7 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
   set_str(f->parfile, "mcmcpar.dat"); set_str(f->parffile, "mcmcparf.dat"); set_str(f->sigma2file, "mcmcsigma2.dat");
   set_str(f->sigma2ffile, "mcmcsigma2f.dat"); set_str(f->datafile, "data.dat");
   f->verbosity = 1; f->printint = 500; f->dumpint = 0; f->usrfunlen = 0; f->filepars = 1;
+  f->svddim = 0; f->sstype = 0; f->condmaxini = 1.0e15; f->sstrans = -1.0;
 
   std::ifstream in(path);
   if (!in) return fail(MCMCBH_ENOFILE, std::string("File ") + path + " not found, no MCMC run");  // mcmcinit.F90:121-125
@@ -192,8 +193,6 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
   double sstrans = -1.0;
   for (auto& [k, v] : kv) {
     bool ok = true;
-    double dummy_d;
-    int dummy_i;
     if (k == "nsimu") ok = parse_int(v, cfg->nsimu);
     else if (k == "doadapt") ok = parse_int(v, cfg->doadapt);
     else if (k == "doburnin") ok = parse_int(v, cfg->doburnin);
@@ -216,7 +215,7 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
     else if (k == "chainfile") ok = parse_string(v, f->chainfile, MCMCBH_PATH);
     else if (k == "s2file") ok = parse_string(v, f->s2file, MCMCBH_PATH);
     else if (k == "ssfile") ok = parse_string(v, f->ssfile, MCMCBH_PATH);
-    else if (k == "svddim") ok = parse_int(v, dummy_i);
+    else if (k == "svddim") ok = parse_int(v, f->svddim);
     else if (k == "condmax") ok = parse_double(v, cfg->condmax);
     else if (k == "cov0file") ok = parse_string(v, f->cov0file, MCMCBH_PATH);
     else if (k == "covffile") ok = parse_string(v, f->covffile, MCMCBH_PATH);
@@ -227,9 +226,9 @@ extern "C" int mcmcbh_read_namelist(const char* path, mcmcb_config* cfg, mcmcbh_
     else if (k == "parffile") ok = parse_string(v, f->parffile, MCMCBH_PATH);
     else if (k == "sigma2file") ok = parse_string(v, f->sigma2file, MCMCBH_PATH);
     else if (k == "sigma2ffile") ok = parse_string(v, f->sigma2ffile, MCMCBH_PATH);
-    else if (k == "condmaxini") ok = parse_double(v, dummy_d);
-    else if (k == "sstrans") ok = parse_double(v, sstrans);
-    else if (k == "sstype") ok = parse_int(v, sstype);
+    else if (k == "condmaxini") ok = parse_double(v, f->condmaxini);
+    else if (k == "sstrans") { ok = parse_double(v, sstrans); f->sstrans = sstrans; }
+    else if (k == "sstype") { ok = parse_int(v, sstype); f->sstype = sstype; }
     else if (k == "dumpint") ok = parse_int(v, f->dumpint);
     else if (k == "priorsfile") ok = parse_string(v, f->priorsfile, MCMCBH_PATH);
     else if (k == "verbosity") ok = parse_int(v, f->verbosity);
@@ -394,6 +393,7 @@ extern "C" int mcmcbh_write_namelist(const char* path, const mcmcb_config* c, co
                f->covffile, f->covnfile, f->meanfile, f->nmlffile);
   std::fprintf(fp, " parfile = '%s',\n parffile = '%s',\n sigma2file = '%s',\n sigma2ffile = '%s',\n", f->parfile, f->parffile,
                f->sigma2file, f->sigma2ffile);
+  std::fprintf(fp, " svddim = %d,\n condmaxini = %.17g,\n sstype = %d,\n sstrans = %.17g,\n", f->svddim, f->condmaxini, f->sstype, f->sstrans);
   std::fprintf(fp, " dumpint = %d,\n priorsfile = '%s',\n verbosity = %d,\n method = '%s',\n alphatarget = %.17g,\n nuparam = %.17g\n/\n",
                f->dumpint, f->priorsfile, f->verbosity, method, c->alphatarget, c->nuparam);
   std::fprintf(fp, "&mcmcb\n nchains = %lld,\n chain_offset = %lld,\n seed = %llu,\n device = %d,\n store_chains = %d,\n", c->nchains,

@@ -32,6 +32,9 @@ typedef struct mcmcbh_files {
   char sigma2file[MCMCBH_PATH], sigma2ffile[MCMCBH_PATH];
   char datafile[MCMCBH_PATH]; /* &mcmcb: the user model's data (what its ssfunction loads, e.g. data.dat) */
   int verbosity, printint, dumpint, usrfunlen, filepars;
+  /* legacy variables of the Modest interface, read and written back as they are (mcmcinit.F90:218-223) */
+  int svddim, sstype;
+  double condmaxini, sstrans;
 } mcmcbh_files;
 
 const char* mcmcbh_last_error(void);

@@ -29,7 +29,10 @@
 namespace mcmcb {
 
 constexpr int K4_THREADS = 128;
-constexpr int K4_U = 8;               // factor elements loaded ahead of the dependent recurrences (memory-level parallelism)
+#ifndef MCMCB_K4_U
+#define MCMCB_K4_U 8
+#endif
+constexpr int K4_U = MCMCB_K4_U;               // factor elements loaded ahead of the dependent recurrences (memory-level parallelism)
 constexpr int K4_DM = 32 * K2_MAXM;  // largest npar (local arrays are sized for it; only npar entries are touched)
 
 __host__ __device__ constexpr size_t k4_pk(int i, int j) { return (size_t)j * (j + 1) / 2 + i; }  // i <= j

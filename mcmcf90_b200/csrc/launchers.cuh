@@ -678,14 +678,18 @@ struct K2 {
     const size_t T = (size_t)d * (d + 1) / 2;
     const long long N = h->cfg.nchains;
     if (!h->d_Rp) CK(cudaMalloc(&h->d_Rp, sizeof(double) * T * (size_t)h->pitch));
-    const unsigned blocks = (unsigned)((N + K4_THREADS - 1) / K4_THREADS);
-    k4_pack_kernel<<<blocks, K4_THREADS, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
-    k4_ram_step_kernel<M><<<blocks, K4_THREADS, 0, h->stream>>>(p, h->d_Rp);
-    k4_unpack_kernel<<<blocks, K4_THREADS, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
+    // CTA size: 32, 64 and 128 threads measured identical on BASELINE C4 (5.71e7 chain-steps/s each,
+    // profiles/r02_summary.md); MCMCB_K4_BLOCK overrides for experiments
+    int threads = K4_THREADS;
+    if (const char* e = getenv("MCMCB_K4_BLOCK")) threads = std::max(32, std::min(K4_THREADS, (atoi(e) / 32) * 32));
+    const unsigned blocks = (unsigned)((N + threads - 1) / threads);
+    k4_pack_kernel<<<blocks, threads, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
+    k4_ram_step_kernel<M><<<blocks, threads, 0, h->stream>>>(p, h->d_Rp);
+    k4_unpack_kernel<<<blocks, threads, 0, h->stream>>>(h->d_Rm, h->r_stride, h->d_Rp, h->pitch, N, d);
     h->launches += 3;
     h->blocks = (int)blocks;
     h->smem = 0;
-    h->k2_warps = K4_THREADS / 32;
+    h->k2_warps = threads / 32;
     h->k4 = true;
     CK(cudaGetLastError());
     return 0;

@@ -50,7 +50,8 @@ class Files(C.Structure):
     _fields_ = [(n, C.c_char * 256) for n in ("chainfile", "s2file", "ssfile", "priorsfile", "cov0file", "covffile",
                                               "covnfile", "meanfile", "nmlffile", "parfile", "parffile", "sigma2file",
                                               "sigma2ffile", "datafile")] + \
-               [(n, C.c_int) for n in ("verbosity", "printint", "dumpint", "usrfunlen", "filepars")]
+               [(n, C.c_int) for n in ("verbosity", "printint", "dumpint", "usrfunlen", "filepars", "svddim", "sstype")] + \
+               [(n, C.c_double) for n in ("condmaxini", "sstrans")]
 
 
 def hostlib():
@@ -135,7 +136,8 @@ def test_namelist_write_back_round_trips(tmp_path):
     L = hostlib()
     p = tmp_path / "in.nml"
     p.write_text("&mcmc nsimu=777, method='er', drscale=1.5, adapthist=40, greedy=1, burnintime=30, doburnin=1, "
-                 "condmax=1d10, chainfile='c h.mat', nmlffile='final.nml', S02=0.125, covnfile='n.dat' /\n"
+                 "condmax=1d10, chainfile='c h.mat', nmlffile='final.nml', S02=0.125, covnfile='n.dat', svddim=2, "
+                 "condmaxini=1d12, sstype=5, sstrans=4.0 /\n"
                  "&mcmcb nchains=12, seed=99, model='gauss', datafile='d.dat', diag_stride=5, kernel=2 /\n")
     a, fa, b, fb = Config(), Files(), Config(), Files()
     assert L.mcmcbh_read_namelist(str(p).encode(), C.byref(a), C.byref(fa)) == 0, L.mcmcbh_last_error()
@@ -144,6 +146,8 @@ def test_namelist_write_back_round_trips(tmp_path):
     assert L.mcmcbh_read_namelist(str(out).encode(), C.byref(b), C.byref(fb)) == 0, L.mcmcbh_last_error()
     assert bytes(a) == bytes(b) and bytes(fa) == bytes(fb)
     assert (b.method, b.nsimu, b.drscale, b.condmax, fb.chainfile, fb.nmlffile) == (3, 777, 1.5, 1e10, b"c h.mat", b"final.nml")
+    # legacy variables are written back as read; sstype = 5 (t likelihood) switches the sigma2 update off (mcmcinit.F90:300-309)
+    assert (fb.svddim, fb.sstype, fb.condmaxini, fb.sstrans, b.updatesigma) == (2, 5, 1e12, 4.0, 0)
     text = out.read_text()
     assert text.startswith("&mcmc") and "method = 'er'" in text and "&mcmcb" in text
 
