@@ -10,6 +10,7 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "k1_small.cuh"
@@ -224,6 +225,20 @@ static int allreduce(mcmcb_handle g, const std::vector<double*>& bufs, size_t n)
   g->nccl_calls++;
   return 0;
 }
+// run fn(kid index) for every device of a group at once (one host thread per device for the duration of the call):
+// uploads, downloads and their synchronisations then overlap across devices instead of running one device after another
+template <class F>
+static int for_kids(mcmcb_handle g, F fn) {
+  const size_t n = g->kids.size();
+  std::vector<int> rc(n, 0);
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < n; k++) th.emplace_back([&, k] { rc[k] = fn((int)k); });
+  rc[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (int r : rc)
+    if (r) return r;
+  return 0;
+}
 static void shard(long long N, int G, int k, long long* n, long long* off) {  // contiguous ranges, remainder to the first kids
   const long long base = N / G, rem = N % G;
   *n = base + (k < rem ? 1 : 0);
@@ -365,10 +380,7 @@ extern "C" const char* mcmcb_last_error(mcmcb_handle h) {
 
 extern "C" int mcmcb_set_data(mcmcb_handle h, const double* blob, size_t n) {
   if (!h || !blob || n == 0) return MCMCB_EINVAL;
-  if (!h->kids.empty()) {
-    for (auto* k : h->kids) { const int rc = mcmcb_set_data(k, blob, n); if (rc) return rc; }
-    return MCMCB_OK;
-  }
+  if (!h->kids.empty()) return grp::for_kids(h, [&](int k) { return mcmcb_set_data(h->kids[k], blob, n); });
   CK(cudaSetDevice(h->cfg.device));
   size_t bytes = ((n * sizeof(double) + 15) / 16) * 16;
   if (h->d_blob && bytes != h->blob_bytes) { cudaFree(h->d_blob); h->d_blob = nullptr; }
@@ -406,11 +418,12 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
                                  const double* cmat0, const double* sigma2, const int* nobs) {
   if (!h || !par0 || !cmat0 || !sigma2 || !nobs || npar < 1 || nycol < 1) return MCMCB_EINVAL;
   if (!h->kids.empty()) {
-    for (auto* k : h->kids) {
+    const int rc = grp::for_kids(h, [&](int i) {
+      mcmcb_handle k = h->kids[i];
       const double* p0 = par0 + (par0_stride ? (size_t)(k->cfg.chain_offset - h->cfg.chain_offset) * par0_stride : 0);
-      const int rc = mcmcb_set_initial(k, npar, nycol, p0, par0_stride, cmat0, sigma2, nobs);
-      if (rc) return rc;
-    }
+      return mcmcb_set_initial(k, npar, nycol, p0, par0_stride, cmat0, sigma2, nobs);
+    });
+    if (rc) return rc;
     h->npar = npar; h->nycol = nycol; h->initial_set = true;
     return MCMCB_OK;
   }
@@ -507,8 +520,9 @@ extern "C" int mcmcb_set_initial(mcmcb_handle h, int npar, int nycol, const doub
   if (h->k1_batch == 4 && K1_THREADS >= 384) h->k1_threads = 384;
   if (const char* e = std::getenv("MCMCB_K1_BLOCK")) {
     const int t = std::atoi(e);
-    if (t >= 32 && t <= K1_THREADS && t % 32 == 0) h->k1_threads = t;
+    if (t >= 32 && t <= K1_THREADS && t % 32 == 0) { h->k1_threads = t; h->k1_threads_fixed = true; }
   }
+  h->k1_threads_used = h->k1_threads;
   int rc = h->model->init(h);
   if (rc) return rc;
   h->initial_set = true;
@@ -860,12 +874,11 @@ extern "C" int mcmcb_fetch(mcmcb_handle h, const char* what, void* out, size_t o
   if (!h->kids.empty()) {  // every array is chain-major: the kids' parts are consecutive slices
     if (h->cfg.nchains <= 0 || out_bytes % (size_t)h->cfg.nchains != 0) return MCMCB_EINVAL;
     const size_t per = out_bytes / (size_t)h->cfg.nchains;  // bytes per chain as the caller sized it
-    for (auto* k : h->kids) {
+    return grp::for_kids(h, [&](int i) {
+      mcmcb_handle k = h->kids[i];
       const size_t off = (size_t)(k->cfg.chain_offset - h->cfg.chain_offset);
-      const int rc = mcmcb_fetch(k, what, (char*)out + off * per, per * (size_t)k->cfg.nchains);
-      if (rc) return rc;
-    }
-    return MCMCB_OK;
+      return mcmcb_fetch(k, what, (char*)out + off * per, per * (size_t)k->cfg.nchains);
+    });
   }
   CK(cudaSetDevice(h->cfg.device));
   return h->model->fetch(h, what, out, out_bytes);
@@ -984,7 +997,7 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (nycol) *nycol = h->nycol;
   if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : (h->k4 ? 1 : h->L);
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
-  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : h->k1_threads;
+  if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : h->k1_threads_used;
   if (blocks) *blocks = h->blocks;
   if (smem) *smem = h->smem;
   return MCMCB_OK;

@@ -290,35 +290,57 @@ struct K1 {
       h->attr_set = true;
     }
     const long long subs = (h->cfg.nchains * L + 31) / 32;  // sub-tiles: the chains one warp owns with one chain per thread
-    const long long wpb = h->k1_threads / 32;
+    // tile plan for W resident warps: full rounds of B-sub-tile tiles while every warp still gets one (as one super-tile
+    // per warp), then one last round of smaller tiles sized to what is left per warp.  Returns the plan's length in
+    // units of one sub-tile's run time (a tile of b sub-tiles takes ~b units; a round lasts as long as its tiles).
+    struct Plan { long long n4, n2, n1, wtiles, units; int rounds; };
+    auto plan = [&](long long W) {
+      Plan P{0, 0, 0, 0, 0, 0};
+      long long rem = subs;
+      if (B >= 4) {
+        const long long full = rem / (4 * W);
+        rem -= 4 * W * full;
+        P.units += 4 * full;
+        if (h->k1_supertile) { P.rounds = (int)full; P.wtiles = full > 0 ? W : 0; }
+        else P.n4 = full * W;
+      }
+      if (B >= 4 && rem > 3 * W) { P.n4 += (rem + 3) / 4; rem = 0; P.units += 4; }
+      if (B >= 4 && rem > 2 * W) { P.n2 = W; rem -= 2 * W; P.units += 2; }           // 2 + 1 per warp
+      else if (B >= 2 && B < 4) { P.n2 = (rem / (2 * W)) * W; P.units += 2 * (rem / (2 * W)); rem -= 2 * P.n2; }
+      if (B >= 2 && rem > W) { P.n2 += (rem + 1) / 2; rem = 0; P.units += 2; }
+      P.n1 = rem;
+      if (rem > 0) P.units += 1;
+      return P;
+    };
+    // CTA size.  The default (384 threads with four chains per thread) is right when the population is many rounds
+    // deep; a population of only a few sub-tiles per warp can leave most warps idle in the last round (2^20 chains
+    // sharded over 8 GPUs = 131 072 per GPU: 3 units of which the last keeps 31 % of the warps busy).  With four chains
+    // per thread the CTA size is therefore chosen among 6..12 warps for the best estimated use of the resident warps
+    // (fewer warps per SM cost ~0.6 % each, profiles/r02_ab_k1_block.txt); MCMCB_K1_BLOCK fixes it.
+    int threads = h->k1_threads;
+    if (B >= 4 && !h->k1_threads_fixed) {
+      double best = -1.0;
+      for (int w = h->k1_threads / 32; w >= 6; w--) {
+        const long long Wc = std::min<long long>((long long)h->num_sms * h->occ, (subs + w - 1) / w) * w;
+        const Plan P = plan(Wc);
+        const double use = (double)subs / ((double)P.units * (double)Wc) * (1.0 - 0.006 * (h->k1_threads / 32 - w));
+        if (use > best + 1e-9) { best = use; threads = 32 * w; }
+      }
+    }
+    const long long wpb = threads / 32;
     const long long need = (subs + wpb - 1) / wpb;
     long long blocks = std::min<long long>((long long)h->num_sms * h->occ, need);
     if (blocks < 1) blocks = 1;
     h->blocks = (int)blocks;
     h->smem = smem;
-    // tile plan: full rounds of B-sub-tile tiles while every warp still gets one, then one last round of smaller
-    // tiles sized to what is left per warp
+    h->k1_threads_used = threads;
     K1Params q = p;
     q.exp_dn = exp_dn;
-    const long long W = blocks * wpb;
-    long long n4 = 0, n2 = 0, n1 = 0, rem = subs;
-    // full rounds of 4-sub-tile tiles: one super-tile per warp, its `rounds` tiles run back to back (k1_run_tile)
-    q.rounds = 0; q.wtiles = 0;
-    if (B >= 4 && h->k1_supertile) {
-      q.rounds = (int)(rem / (4 * W));
-      q.wtiles = q.rounds > 0 ? W : 0;
-      rem -= 4 * W * q.rounds;
-    } else if (B >= 4) {
-      n4 = (rem / (4 * W)) * W; rem -= 4 * n4;
-    }
-    if (B >= 4 && rem > 3 * W) { n4 += (rem + 3) / 4; rem = 0; }
-    if (B >= 4 && rem > 2 * W) { n2 = W; rem -= 2 * W; }           // 2 + 1 per warp
-    else if (B >= 2 && B < 4) { n2 = (rem / (2 * W)) * W; rem -= 2 * n2; }
-    if (B >= 2 && rem > W) { n2 += (rem + 1) / 2; rem = 0; }
-    n1 = rem;
-    q.tier[0] = n4; q.tier[1] = n2; q.tier[2] = n1;
+    const Plan P = plan(blocks * wpb);
+    q.rounds = P.rounds; q.wtiles = P.wtiles;
+    q.tier[0] = P.n4; q.tier[1] = P.n2; q.tier[2] = P.n1;
     CK(cudaMemsetAsync(h->d_tile, 0, sizeof(unsigned), h->stream));
-    kern<<<(unsigned)blocks, h->k1_threads, smem, h->stream>>>(q);
+    kern<<<(unsigned)blocks, threads, smem, h->stream>>>(q);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -731,6 +753,10 @@ struct K2 {
     if (!resident && h->factor_mode == FACTOR_CHOL && h->r_stride > 0 && c.method != MCMCB_RAM &&
         (size_t)h->num_sms * W * (d2 / 2) > ((size_t)64 << 20))
       W = std::max(8, W / 2);
+    if (const char* e = getenv("MCMCB_K2_WARPS")) {  // tuning experiments only
+      const int w = atoi(e);
+      if (w >= 1 && w <= K2_MAX_WARPS && !resident) W = w;
+    }
     const size_t used = (size_t)W * (vec1 + (resident ? d2 : 0));
     if (used + 1024 > h->max_smem) W = (int)std::max<size_t>(1, (h->max_smem - 1024) / vec1);
     smem_blob = (size_t)W * (vec1 + (resident ? d2 : 0)) + h->blob_bytes + 1024 <= h->max_smem;

@@ -66,6 +66,8 @@ struct mcmcb_handle_s {
   int hist_rows = 0;
   bool er_exit = false;  // method 'er': run the early-exit kernel (MCMCB_ER_EXIT=1)
   int k1_threads = 512;       // threads per CTA of the register kernel (<= MCMCB_K1_THREADS; MCMCB_K1_BLOCK overrides)
+  bool k1_threads_fixed = false;  // MCMCB_K1_BLOCK given: no per-launch choice
+  int k1_threads_used = 512;  // what the last launch used
   bool k1_supertile = true;   // bulk of a large population as per-warp super-tiles (MCMCB_K1_SUPERTILE=0: off)
   bool k1_exp_direct = true;  // stage the direct exp table in the shared memory left over (MCMCB_EXP_DIRECT=0: off)
   int k1_batch = 1;  // chains per thread of the register kernel (thread-per-chain mapping only)
