@@ -26,9 +26,20 @@
  *   __device__ static double priorfun   (const double* theta, int len,  const mcmcb_ctx& c);
  *   __device__ static void   ssfunction (const double* theta, int npar, int ny,
  *                                        const mcmcb_ctx& c, double* ss);
+ *
+ * Optional members (detected at compile time; a model without them runs unchanged):
+ *   ssfunction_er(theta,npar,ny,ctx,sscrit,ss)   early-rejection form (external_inc.h:20-24)
+ *   template<int B> ssfunction_batch(...)        B parameter vectors in one sweep over the data (register kernel)
+ *   template<class V> ssfunction_view(const V& theta,npar,ny,ctx,ss)  ss of a VIEW of the parameter vector (anything with
+ *       operator[]): the thread-per-chain SCAM kernel hands in theta + delta*U(:,j) composed on the fly, so a
+ *       single-component move (MCMC_run_scam.F90:94-117) never materialises its proposal; needs
+ *       `static constexpr bool MCMCB_VIEW_DEFAULTS = true` (checkbounds always true, priorfun = the default prior).
  */
 #ifndef MCMCB200_MODEL_CUH
 #define MCMCB200_MODEL_CUH
+
+/* what ssfunction_view is probed with (detection only) */
+struct mcmcb_view_probe { __device__ double operator[](int) const { return 0.0; } };
 
 struct mcmcb_ctx {
   const double* data;       /* model blob: shared memory when it fits (TMA-staged once per CTA), else global */

@@ -16,6 +16,7 @@
 #include "k2g_group.cuh"
 #include "k3_scam.cuh"
 #include "k4_ram.cuh"
+#include "k5_scam.cuh"
 #include "mcmcb200.h"
 #include "pool.cuh"
 #include "registry.h"
@@ -717,6 +718,29 @@ struct K2 {
     return 0;
   }
 
+  // thread-per-chain SCAM kernel (k5_scam.cuh): a large population that shares ONE rotation (pooled adaptation)
+  static bool use_k5(mcmcb_handle h) {
+    if (h->factor_mode != FACTOR_SCAM || h->r_stride != 0 || h->q_stride != 0 || h->npar > K4_DM) return false;
+    if (const char* e = getenv("MCMCB_K5")) return e[0] == '1';  // tuning / tests: force on or off
+    return h->cfg.nchains >= (long long)h->num_sms * 64;
+  }
+
+  template <bool SMEM>
+  static int launch_k5(mcmcb_handle h, const K2Params& p) {
+    auto kern = k5_scam_step_kernel<M, SMEM>;
+    const size_t smem = SMEM ? h->blob_bytes : 0;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)((h->cfg.nchains + K5_THREADS - 1) / K5_THREADS);
+    kern<<<blocks, K5_THREADS, smem, h->stream>>>(p);
+    h->launches++;
+    h->blocks = (int)blocks;
+    h->smem = smem;
+    h->k2_warps = K5_THREADS / 32;
+    h->k4 = true;  // one thread per chain (mcmcb_info)
+    CK(cudaGetLastError());
+    return 0;
+  }
+
   static bool is_tick(const mcmcb_config& c, long long i) {
     if (c.method == MCMCB_RAM) return false;
     if (!c.doadapt && !c.doburnin) return false;
@@ -769,6 +793,7 @@ struct K2 {
     const bool group = plan_group(h, GT, ngroups, gblob);
     if (group) { resident = false; W = GT * ngroups / 32; h->k2_group_threads = GT; }
     if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
+    const bool k5 = use_k5(h);
     int left = nsteps;
     bool first = true;
     while (left > 0 || first) {
@@ -777,8 +802,10 @@ struct K2 {
       for (int k = 1; k <= left; k++)
         if (is_tick(c, h->k2_i + k)) { seg = k; break; }
       K2Params p = params(h, seg);
-      int rc = group ? (gblob ? launch_group<true>(h, p, GT, ngroups) : launch_group<false>(h, p, GT, ngroups))
-                     : (smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p));
+      int rc;
+      if (k5) rc = (h->blob_bytes + 2048 <= h->max_smem) ? launch_k5<true>(h, p) : launch_k5<false>(h, p);
+      else rc = group ? (gblob ? launch_group<true>(h, p, GT, ngroups) : launch_group<false>(h, p, GT, ngroups))
+                      : (smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p));
       if (rc) return rc;
       h->k2_i += seg;
       left -= seg;

@@ -415,3 +415,70 @@ def test_thread_per_chain_ram_kernel_matches_the_oracle(case, monkeypatch):
     b = out["0"]
     same = sum(all(a["cnt"][k][c] == b["cnt"][k][c] for k in CNT) for c in range(N))
     assert same >= N - 2
+
+
+# ------------------------------------------------------------------------------------------------ thread-per-chain SCAM
+@pytest.mark.parametrize("G,J,N,steps", [(6, 4, 64, 59), (198, 10, 8, 3)])
+def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, monkeypatch):
+    """k5_scam_step_kernel (one thread per chain, shared rotation, proposal never materialised: HierN::ssfunction_axpy)
+    is what large pooled SCAM populations run on (BASELINE C5); forced here on a small population.  Up to the first
+    pooled tick every chain is the reference's own SCAM chain: exact counters against the oracle."""
+    rng = np.random.default_rng(G)
+    y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
+    blob = mb.models.blob_hier(y)
+    d = G + 2
+    nml = dict(method="scam", nsimu=steps + 1, adaptint=steps + 1, initcmatn=1, updatesigma=1, N0=2.0, S02=1.0)
+    par0 = 0.1 + 0.05 * rng.normal(size=(N, d))
+    cmat0 = np.diag(0.02 * (1.0 + np.arange(d) / d))
+    monkeypatch.setenv("MCMCB_K5", "1")
+    s = mb.Sampler(mb.default_config(nchains=N, seed=23, model="hier", pool_adapt=1, store_chains=2, **nml))
+    s.set_data(blob)
+    s.set_initial(par0, cmat0, [1.0], [G * J])
+    s.run(steps // 2)
+    s.run(steps - steps // 2)
+    assert s.info()["lanes_per_chain"] == 1
+    cnt, par, ss, s2 = s.counters(), s.fetch("par"), s.fetch("ss"), s.fetch("sigma2")
+    assert (cnt["status"] == 0).all()
+    for c in (0, 1, N - 1):
+        ch = oracle_chain(nml, O.MODEL_HIER, blob, par0[c], cmat0, [1.0], [G * J], 23, c)
+        ch.run()
+        r = ch.results()
+        for k in CNT:
+            assert cnt[k][c] == r[k], (c, k, cnt[k][c], r[k])
+        np.testing.assert_allclose(par[c], r["par"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(ss[c], r["sschain"][-1, 0], rtol=1e-10)
+        np.testing.assert_allclose(s2[c], r["sigma2"], rtol=1e-9)
+        if c == 1:
+            g = s.fetch_chain(1)
+            assert np.array_equal(g["chain"][:, -1], r["chain"][:, -1])
+            np.testing.assert_allclose(g["chain"][:, :-1], r["chain"][:, :-1], rtol=1e-8, atol=1e-10)
+    s.close()
+
+
+def test_thread_per_chain_scam_kernel_across_pooled_ticks(monkeypatch):
+    """Across pooled ticks both step kernels take their rotation from the same device SVD of the pooled covariance: the
+    thread-per-chain kernel walks the chains of the warp-per-chain kernel (sums differ at rounding level)."""
+    G, J, N = 6, 4, 96
+    rng = np.random.default_rng(7)
+    y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
+    blob = mb.models.blob_hier(y)
+    d = G + 2
+    nml = dict(method="scam", nsimu=151, adaptint=50, initcmatn=1, updatesigma=0)
+    par0 = 0.1 * rng.normal(size=(N, d))
+    out = {}
+    for k5 in ("1", "0"):
+        monkeypatch.setenv("MCMCB_K5", k5)
+        s = mb.Sampler(mb.default_config(nchains=N, seed=3, model="hier", pool_adapt=1, **nml))
+        s.set_data(blob)
+        s.set_initial(par0, 0.1 * np.eye(d), [1.0], [1])
+        s.run(150)
+        assert s.info()["lanes_per_chain"] == (1 if k5 == "1" else 32)
+        out[k5] = dict(cnt=s.counters(), par=s.fetch("par"), pool=s.pool_fetch(), q=s.fetch("qcovstd"))
+        assert (out[k5]["cnt"]["status"] == 0).all()
+        s.close()
+    a, b = out["1"], out["0"]
+    same = sum(all(a["cnt"][k][c] == b["cnt"][k][c] for k in CNT) for c in range(N))
+    assert same >= N - 4, same
+    assert a["pool"][0] == b["pool"][0]
+    np.testing.assert_allclose(a["pool"][1], b["pool"][1], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(a["q"][0], b["q"][0], rtol=1e-5)
