@@ -376,8 +376,21 @@ def run_ours(args):
         while args.dump_stride and s.dump_pop_ex() is not None:
             dumped += 1
 
+    def run_step():
+        """One bench step = W.iters iterations of every chain.  With streamed dumps the host pops snapshots while the
+        device runs on: the call is issued in pieces of at most 8 snapshots so that the ring never overflows."""
+        if not args.dump_stride:
+            s.run(W.iters, sync=False)
+            return
+        left = W.iters
+        while left > 0:
+            n = min(left, args.dump_stride * 8)
+            s.run(n, sync=False)
+            drain()
+            left -= n
+
     for _ in range(args.warmup):
-        s.run(W.iters, sync=False)
+        run_step()
         drain()
     s.sync()
     drain()
@@ -400,7 +413,7 @@ def run_ours(args):
     rec(e_all0)
     for a, b in evs:
         rec(a)
-        s.run(W.iters, sync=False)
+        run_step()
         rec(b)
         drain()
     rec(e_all1)

@@ -567,7 +567,9 @@ static int dump_enqueue(mcmcb_handle h) {
   const bool k2 = h->model->kernel == 2;
   const size_t bytes = sizeof(double) * dump_doubles(h);
   if (h->dump_slots.empty()) {
-    h->dump_slots.resize(4);
+    // ring of snapshots in flight between the copy stream and the host's mcmcb_dump_pop: 4..16 slots, about 1 GB of pinned
+    // host memory at most (a full ring overwrites its oldest snapshot and counts it as dropped)
+    h->dump_slots.resize((size_t)std::max<long long>(4, std::min<long long>(16, (1ll << 30) / (long long)std::max<size_t>(bytes, 1))));
     for (auto& s : h->dump_slots) {
       CK(cudaMalloc(&s.dev, bytes));
       CK(cudaMallocHost(&s.host, bytes));
