@@ -369,12 +369,19 @@ def run_ours(args):
         sus.append(mb.dfma_peak(dev)[0])
     sustained = float(np.mean(sus[len(sus) // 2:]))
 
-    dumped = 0
+    dumped = enq = 0
 
-    def drain():  # a consumer of the streamed dumps: pops whatever is complete (host-side transposition included)
+    def drain(keep=0):
+        """The consumer of the streamed dumps: pops what is complete (host-side transposition included) and, when more than
+        `keep` snapshots are still outstanding, waits for them -- a consumer that falls behind loses the oldest snapshots."""
         nonlocal dumped
-        while args.dump_stride and s.dump_pop_ex() is not None:
-            dumped += 1
+        while args.dump_stride:
+            if s.dump_pop_ex() is not None:
+                dumped += 1
+            elif enq - dumped > keep:
+                time.sleep(0.0005)
+            else:
+                break
 
     def run_step():
         """One bench step = W.iters iterations of every chain.  With streamed dumps the host pops snapshots while the
@@ -382,11 +389,13 @@ def run_ours(args):
         if not args.dump_stride:
             s.run(W.iters, sync=False)
             return
+        nonlocal enq
         left = W.iters
         while left > 0:
-            n = min(left, args.dump_stride * 8)
+            n = min(left, args.dump_stride * 4)
             s.run(n, sync=False)
-            drain()
+            enq += n // args.dump_stride
+            drain(keep=4)   # at most 8 snapshots outstanding in a ring of up to 16
             left -= n
 
     for _ in range(args.warmup):
@@ -418,9 +427,9 @@ def run_ours(args):
         drain()
     rec(e_all1)
     s.sync()
+    drain()
     barrier()
     clk = clocks.stop()
-    drain()
     total_ms = max(e_all0[k].elapsed_time(e_all1[k]) for k in range(G))
     launch_ms = [max(a[k].elapsed_time(b[k]) for k in range(G)) for a, b in evs]
     launches = s.launches - l0
@@ -566,7 +575,7 @@ def run_ours(args):
                                    "device-timed chains) and the adapted proposal covariance, runs %d iterations and downloads "
                                    "theta/mean/cov/counters of every chain into pinned host buffers" % W.iters}
         if args.dump_stride:
-            line["dumps"] = {"dump_stride": args.dump_stride, "snapshots_popped": dumped,
+            line["dumps"] = {"dump_stride": args.dump_stride, "snapshots_popped": dumped, "snapshots_enqueued": enq,
                              "bytes_per_snapshot": int(N * (W.d + 2 * len(W.sigma2) + 1) * 8),
                              "note": "theta/ss/sigma2 of every chain streamed to pinned host buffers on a copy stream and popped by "
                                      "the host inside the timed region; compare `value` with a run without --dump-stride"}
