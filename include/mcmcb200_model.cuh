@@ -41,6 +41,14 @@
 /* what ssfunction_view is probed with (detection only) */
 struct mcmcb_view_probe { __device__ double operator[](int) const { return 0.0; } };
 
+/* how many independent accumulation chains a view asks the model to keep in flight (a view type may carry a
+   `static constexpr int ILP`; kernels that run few warps per SM ask for more).  Models are free to ignore it: it must not
+   change the order in which the partial sums join the total. */
+template <class V, class = void>
+struct mcmcb_view_ilp { static constexpr int value = 4; };
+template <class V>
+struct mcmcb_view_ilp<V, decltype((void)V::ILP)> { static constexpr int value = V::ILP; };
+
 struct mcmcb_ctx {
   const double* data;       /* model blob: shared memory when it fits (TMA-staged once per CTA), else global */
   unsigned long long ndata; /* blob length in doubles */

@@ -222,6 +222,11 @@ __device__ __forceinline__ void drotg(double& da, double& db, double& c, double&
 // ----------------------------------------------------------------- TMA bulk staging
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 8 bytes global -> shared without a register in between (LDGSTS); pair with cp.async.commit_group / wait_group
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 // One thread stages `bytes` (multiple of 16) from global to shared with cp.async.bulk
 // (TMA, SASS UBLKCP) completing on an mbarrier; every thread then waits on the barrier.
 __device__ __forceinline__ void tma_stage_blob(void* smem_dst, const void* gsrc, uint32_t bytes,

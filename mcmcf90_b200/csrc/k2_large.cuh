@@ -95,6 +95,7 @@ struct K2Params {
   double* gmean;   // [chain][dp]
   double* gw;      // [chain]
   int r_resident;  // 1: the warp keeps its chain's factor in shared memory for the whole launch (d*d doubles per warp)
+  int absorbed;    // tick kernels: 1 = k2_absorb_resident_kernel has already folded the logged rows into (wsum, mean, cmat)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -483,6 +484,163 @@ __device__ __forceinline__ void cta_ap_window(double* rb, int nbuf, const double
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same recursion with EVERY logged row of the chain resident in shared memory (one CTA per SM).
+//
+// cta_absorb_rows streams the rows through an 8-row window: at npar = 200 that is 11 passes over the row buffer, 286
+// barriers and as many exposed L2 round trips per chain, and the tick of 262 144 SCAM chains took 1.02 s where the FP64
+// work is ~0.09 s (profiles/r02_summary.md).  Here the CTA loads the chain's whole row buffer once ((adaptint + 1) x npar
+// doubles: 162 KB at BASELINE C5, 161 KB at C2), runs phase 1 out of shared memory with no barrier (thread k owns
+// component k of every row), and phase 2 on 4 x 4 register tiles of the upper triangle: 8 shared-memory doubles per
+// row feed 16 entry updates (48 FP64 instructions), so the FP64 pipe and not the shared-memory port bounds it, there is no
+// barrier inside, and both images of a tile are written as 32-byte runs.  Every entry sees the reference's sequence of
+// operations (matutils.F90:283-310): bit-identical to cta_absorb_rows, checked by tests/test_r02_coverage.py.
+constexpr int K2_ABSR_THREADS = 640;  // npar = 200: 1275 tiles = two passes of 640 threads at 99.6 %
+
+// shared memory: rows[nrows * d] | weight[nrows] | coef[2 * nrows], nrows = rowcap + 1
+__host__ __device__ __forceinline__ size_t absorb_resident_smem_bytes(int d, int rowcap) {
+  const size_t nrows = (size_t)rowcap + 1;
+  return sizeof(double) * (nrows * d + 3 * nrows + 2);
+}
+
+template <bool VEC>
+__device__ __forceinline__ void absr_tile(const double* __restrict__ X, const double* __restrict__ coef, int nrows, double* cm,
+                                          int d, int a0, int b0) {
+  int ai[4], bj[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { ai[k] = VEC ? a0 + k : min(a0 + k, d - 1); bj[k] = VEC ? b0 + k : min(b0 + k, d - 1); }
+  double v[4][4];  // v[i][j] = entry (a0 + i, b0 + j), read from its mirror image (b, a): contiguous in i
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i][j] = cm[(size_t)bj[j] * d + ai[i]];
+#pragma unroll 2
+  for (int r = 0; r < nrows; r++) {
+    const double f1 = coef[2 * r], f2 = coef[2 * r + 1];
+    if (f2 >= 0.0) {
+      const double* x = X + (size_t)r * d;
+      double da[4], db[4];
+      if (VEC) {  // d % 4 == 0: whole tiles, 16-byte aligned pairs
+        const double2 p0 = *reinterpret_cast<const double2*>(x + a0), p1 = *reinterpret_cast<const double2*>(x + a0 + 2);
+        const double2 q0 = *reinterpret_cast<const double2*>(x + b0), q1 = *reinterpret_cast<const double2*>(x + b0 + 2);
+        da[0] = p0.x; da[1] = p0.y; da[2] = p1.x; da[3] = p1.y;
+        db[0] = q0.x; db[1] = q0.y; db[2] = q1.x; db[3] = q1.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { da[k] = x[ai[k]]; db[k] = x[bj[k]]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[i][j] = v[i][j] + f1 * (f2 * (da[i] * db[j]) - v[i][j]);
+    } else if (f2 == -2.0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[i][j] = 0.0;
+    }
+  }
+  // entries below the diagonal of a diagonal tile and past the edge of a ragged one hold garbage: never stored
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (a0 + i <= b0 + j && b0 + j < d) cm[(size_t)(a0 + i) * d + b0 + j] = v[i][j];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (a0 + i <= b0 + j && b0 + j < d) cm[(size_t)(b0 + j) * d + a0 + i] = v[i][j];
+}
+
+// One CTA per chain: the plain adaptation branch (MCMC_adapt.F90:105-159 with adapthist <= 1) up to, not including,
+// the factorisation.  The host launches it only at such ticks (K2Launcher::tick_is_plain) and only when the rows fit.
+static __global__ void __launch_bounds__(K2_ABSR_THREADS) k2_absorb_resident_kernel(K2Params p) {
+  extern __shared__ __align__(16) double sm_absr[];
+  constexpr K2Layout Lo = k2_layout(1);
+  const long long c = blockIdx.x;
+  const int d = p.d, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  double* st = p.st + c;
+  int* ist = p.ist + c;
+  double* cm = p.cmat + (size_t)c * d * d;
+  double* gmean = p.mean + c * p.dp;
+  const double* theta = p.theta + c * p.dp;
+  const double* rb = p.rowbuf + (size_t)c * (p.rowcap + 1) * (d + 1);
+  const int nbuf = ist[Lo.i_nbuf * p.pitch], nrows = nbuf + 1;
+  double* X = sm_absr;
+  double* wt = X + (size_t)(p.rowcap + 1) * d;
+  double* coef = wt + (p.rowcap + 1) + ((p.rowcap + 1) & 1);  // 16-byte aligned
+  // ---- load: the logged rows (cp.async, 8 bytes each: row r starts at an odd multiple of 8 bytes when npar is even, so
+  // no bulk copy; nothing waits until every copy is in flight), then the open row with its pending weight
+  for (int r = warp; r < nbuf; r += nwarps) {
+    const double* x = rb + (size_t)r * (d + 1);
+    for (int k = lane; k <= d; k += 32) cp_async_8(k < d ? X + (size_t)r * d + k : wt + r, x + k);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int k = tid; k < d; k += nt) X[(size_t)nbuf * d + k] = theta[k];
+  if (tid == 0) wt[nbuf] = (double)ist[Lo.i_pend * p.pitch];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- phase 1a: the weight recursion.  One thread runs the additions in row order (wsum before row r -> coef[2r]);
+  // then thread r turns row r's pair (w, wsum) into the recursion's three quotients, all rows at once:
+  // coef[2r] = f1 = w / (wsum + w - 1), coef[2r+1] = f2 = wsum / (wsum + w) (-2: reset row, -1: no-op row), wt[r] = f3 =
+  // w / (wsum + w).  Same expressions as cta_absorb_rows, evaluated once per row instead of once per row and thread.
+  double ws = st[Lo.wsum * p.pitch];
+  if (tid == 0) {
+    for (int r = 0; r < nrows; r++) {
+      const double w = wt[r];
+      coef[2 * r] = ws;
+      if (ws > 0.0) ws = w + ws;
+      else if (w > 0.0) ws = w;
+    }
+    st[Lo.wsum * p.pitch] = ws;
+    ist[Lo.i_pend * p.pitch] = 0;
+    ist[Lo.i_nbuf * p.pitch] = 0;
+  }
+  __syncthreads();
+  for (int r = tid; r < nrows; r += nt) {
+    const double w = wt[r], w0 = coef[2 * r];
+    if (w0 > 0.0) {
+      coef[2 * r] = w / (w0 + w - 1.0);
+      coef[2 * r + 1] = w0 / (w0 + w);
+      wt[r] = w / (w0 + w);
+    } else {
+      coef[2 * r] = 0.0;
+      coef[2 * r + 1] = w > 0.0 ? -2.0 : -1.0;
+    }
+  }
+  __syncthreads();
+  // ---- phase 1b: rows in order, thread k owns component k (mean in a register); no barrier
+  for (int k = tid; k < d; k += nt) {
+    double m = gmean[k];
+    for (int r = 0; r < nrows; r++) {
+      const double f2 = coef[2 * r + 1];
+      double* x = X + (size_t)r * d + k;
+      if (f2 >= 0.0) {
+        const double f3 = wt[r];
+        const double dv = *x - m;
+        m = m + f3 * dv;
+        *x = dv;
+      } else if (f2 == -2.0) {
+        m = *x;
+      }
+    }
+    gmean[k] = m;
+  }
+  __syncthreads();
+  // ---- phase 2: 4 x 4 tiles of the upper triangle, tile t = jb (jb + 1) / 2 + ib, ib <= jb
+  const int nb = (d + 3) >> 2, ntiles = nb * (nb + 1) / 2;
+  const bool vec = (d & 3) == 0;
+  for (int t = tid; t < ntiles; t += nt) {
+    int jb = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (jb * (jb + 1) / 2 > t) jb--;
+    while ((jb + 1) * (jb + 2) / 2 <= t) jb++;
+    const int ib = t - jb * (jb + 1) / 2;
+    if (vec) absr_tile<true>(X, coef, nrows, cm, d, 4 * ib, 4 * jb);
+    else absr_tile<false>(X, coef, nrows, cm, d, 4 * ib, 4 * jb);
+  }
+}
+
 // MCMC_adapt.F90:12-174 at step index p.tick_i, one CTA per chain.
 static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
   extern __shared__ double sh[];  // absorb_smem_doubles(d)
@@ -565,14 +723,16 @@ static __global__ void k2_adapt_kernel(K2Params p, double* scratch) {
     if (!cf.pool && !cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
     // the open row joins the logged rows with its pending weight (slot nbuf always exists: rowcap + 1 rows)
-    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
-    if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
-    __syncthreads();
-    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, coef, sh);
-    if (threadIdx.x == 0) {
-      st[Lo.wsum * p.pitch] = wsum;
-      ist[Lo.i_pend * p.pitch] = 0;
-      ist[Lo.i_nbuf * p.pitch] = 0;
+    if (!p.absorbed) {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+      if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
+      __syncthreads();
+      cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, coef, sh);
+      if (threadIdx.x == 0) {
+        st[Lo.wsum * p.pitch] = wsum;
+        ist[Lo.i_pend * p.pitch] = 0;
+        ist[Lo.i_nbuf * p.pitch] = 0;
+      }
     }
     if (!cf.pool && !cta_calculate_R(cm, Rm, tmp, d, red) && threadIdx.x == 0) ist[Lo.i_status * p.pitch] |= MCMCB_ST_CHOLFAIL;
   }

@@ -229,14 +229,16 @@ static __global__ void k3_adapt_kernel(K2Params p, double* scratch, int mode) {
     cta_ap_window(rb, nbuf, theta, cm, mean, st, ist, p.pitch, d, cf.adapthist);
     if (!cf.pool) status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
   } else if (i >= cf.burnintime + cf.adaptint + cf.adapthist && cf.doadapt) {  // MCMC_adapt.F90:105-159
-    for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
-    if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
-    __syncthreads();
-    cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, p.coef + (size_t)blockIdx.x * 2 * (p.rowcap + 1), dvec);
-    if (threadIdx.x == 0) {
-      st[Lo.wsum * p.pitch] = wsum;
-      ist[Lo.i_pend * p.pitch] = 0;
-      ist[Lo.i_nbuf * p.pitch] = 0;
+    if (!p.absorbed) {
+      for (int k = threadIdx.x; k < d; k += blockDim.x) rb[(size_t)nbuf * (d + 1) + k] = theta[k];
+      if (threadIdx.x == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)ist[Lo.i_pend * p.pitch];
+      __syncthreads();
+      cta_absorb_rows(rb, nbuf + 1, cm, mean, wsum, d, p.coef + (size_t)blockIdx.x * 2 * (p.rowcap + 1), dvec);
+      if (threadIdx.x == 0) {
+        st[Lo.wsum * p.pitch] = wsum;
+        ist[Lo.i_pend * p.pitch] = 0;
+        ist[Lo.i_nbuf * p.pitch] = 0;
+      }
     }
     if (!cf.pool) status = cta_calculate_R_svd(cm, Rm, p.qstd + c * p.q_stride, tmpA, tmpU, d, mode, cf.condmax, sv, perm, red);
   }

@@ -17,6 +17,7 @@
 #include "k3_scam.cuh"
 #include "k4_ram.cuh"
 #include "k5_scam.cuh"
+#include "k5s_scam.cuh"
 #include "mcmcb200.h"
 #include "pool.cuh"
 #include "registry.h"
@@ -536,6 +537,7 @@ struct K2 {
     p.store_s2_p = h->d_store_s2;
     p.tile_counter = h->d_tile;
     p.tick_i = 0;
+    p.absorbed = 0;
     p.qstd = h->d_qstd;
     p.factor_mode = h->factor_mode;
     p.r_stride = h->r_stride;
@@ -741,6 +743,38 @@ struct K2 {
     return 0;
   }
 
+  // theta-in-shared-memory variant (k5s_scam.cuh): the model must evaluate views, and >= 64 chains' theta must fit beside
+  // the blob.  Returns the CTA size, 0 = not applicable.
+  static int k5s_threads(mcmcb_handle h) {
+    if constexpr (!has_ssfunction_view<M>::value) {
+      return 0;
+    } else {
+      if (const char* e = getenv("MCMCB_K5S")) { if (e[0] == '0') return 0; }  // tuning / tests
+      for (int t = K5S_THREADS; t >= 64; t -= 32)
+        if (k5s_smem_bytes(h->npar, t, h->blob_bytes) + 1024 <= h->max_smem) return t;
+      return 0;
+    }
+  }
+
+  static int launch_k5s(mcmcb_handle h, const K2Params& p, int threads) {
+    if constexpr (has_ssfunction_view<M>::value) {
+      int ilp = 8;
+      if (const char* e = getenv("MCMCB_K5S_ILP")) ilp = atoi(e);  // tuning experiments only
+      auto kern = ilp == 4 ? k5s_scam_step_kernel<M, 4> : k5s_scam_step_kernel<M, 8>;
+      const size_t smem = k5s_smem_bytes(h->npar, threads, h->blob_bytes);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned blocks = (unsigned)((h->cfg.nchains + threads - 1) / threads);
+      kern<<<blocks, threads, smem, h->stream>>>(p);
+      h->launches++;
+      h->blocks = (int)blocks;
+      h->smem = smem;
+      h->k2_warps = threads / 32;
+      h->k4 = true;  // one thread per chain (mcmcb_info)
+      CK(cudaGetLastError());
+    }
+    return 0;
+  }
+
   static bool is_tick(const mcmcb_config& c, long long i) {
     if (c.method == MCMCB_RAM) return false;
     if (!c.doadapt && !c.doburnin) return false;
@@ -794,6 +828,7 @@ struct K2 {
     if (group) { resident = false; W = GT * ngroups / 32; h->k2_group_threads = GT; }
     if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
     const bool k5 = use_k5(h);
+    const int k5s = k5 ? k5s_threads(h) : 0;
     int left = nsteps;
     bool first = true;
     while (left > 0 || first) {
@@ -803,7 +838,8 @@ struct K2 {
         if (is_tick(c, h->k2_i + k)) { seg = k; break; }
       K2Params p = params(h, seg);
       int rc;
-      if (k5) rc = (h->blob_bytes + 2048 <= h->max_smem) ? launch_k5<true>(h, p) : launch_k5<false>(h, p);
+      if (k5 && k5s) rc = launch_k5s(h, p, k5s);
+      else if (k5) rc = (h->blob_bytes + 2048 <= h->max_smem) ? launch_k5<true>(h, p) : launch_k5<false>(h, p);
       else rc = group ? (gblob ? launch_group<true>(h, p, GT, ngroups) : launch_group<false>(h, p, GT, ngroups))
                       : (smem_blob ? launch_step<true>(h, p) : launch_step<false>(h, p));
       if (rc) return rc;
@@ -811,18 +847,46 @@ struct K2 {
       left -= seg;
       if (seg > 0 && is_tick(c, h->k2_i)) {
         p.tick_i = (int)h->k2_i;
-        if (h->factor_mode == FACTOR_CHOL)
+        // plain AM ticks whose logged rows fit in shared memory: one CTA per SM folds them into the covariance at the
+        // FP64 rate (k2_absorb_resident_kernel); the factorisation, if the chains keep private factors, follows in
+        // the many-CTAs-per-SM kernel that hides its barrier latency
+        if (tick_is_plain(c, h->k2_i) && absorb_resident_ok(h)) {
+          const size_t sm = absorb_resident_smem_bytes(h->npar, p.rowcap);
+          const int ntiles = ((h->npar + 3) / 4) * ((h->npar + 3) / 4 + 1) / 2;
+          const int threads = std::min(K2_ABSR_THREADS, std::max(64, (ntiles + 31) / 32 * 32));
+          CK(cudaFuncSetAttribute(k2_absorb_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          k2_absorb_resident_kernel<<<(unsigned)c.nchains, threads, sm, h->stream>>>(p);
+          h->launches++;
+          CK(cudaGetLastError());
+          p.absorbed = 1;
+        }
+        if (p.absorbed && c.pool_adapt) {
+          // nothing else happens per chain: the pooled factor is built once for everybody (pool())
+        } else if (h->factor_mode == FACTOR_CHOL) {
           k2_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
                             sizeof(double) * absorb_smem_doubles(h->npar), h->stream>>>(p, h->d_scratch);
-        else
+          h->launches++;
+        } else {
           k3_adapt_kernel<<<(unsigned)c.nchains, K2_ADAPT_THREADS,
                             sizeof(double) * (2 * h->npar + absorb_smem_doubles(h->npar)), h->stream>>>(
               p, h->d_scratch, h->factor_mode);
-        h->launches++;
+          h->launches++;
+        }
         CK(cudaGetLastError());
       }
     }
     return 0;
+  }
+
+  // the tick at step i takes the plain branch of MCMC_adapt.F90:105-159 (not burn-in scaling, not the AP window)
+  static bool tick_is_plain(const mcmcb_config& c, long long i) {
+    return c.doadapt && c.adapthist <= 1 && i >= (long long)c.burnintime + c.adaptint + c.adapthist;
+  }
+
+  static bool absorb_resident_ok(mcmcb_handle h) {
+    if (const char* e = getenv("MCMCB_TICK_RESIDENT")) { if (e[0] == '0') return false; }  // tuning / tests
+    const K2Params p = params(h, 0);
+    return h->npar >= 16 && absorb_resident_smem_bytes(h->npar, p.rowcap) + 1024 <= h->max_smem;
   }
 
   // pooled adaptation, pool.cuh

@@ -362,8 +362,8 @@ struct HierN {
   // The same sum over a VIEW of the parameter vector (anything with operator[]): the thread-per-chain SCAM kernel
   // (k5_scam.cuh) hands in theta + delta U(:,j) -- and a few accepted moves it has not written back yet -- composed on the
   // fly, so a single-component move (MCMC_propose_sc, MCMC_run_scam.F90:94-117) never materialises its proposal.  One
-  // lane owns the chain; the same operations in the same order as ssfunction on the materialised vector.  Four groups'
-  // sums of squares run as independent chains; they join the total in group order.
+  // lane owns the chain; the same operations in the same order as ssfunction on the materialised vector.  W groups'
+  // sums of squares run as independent chains (W = mcmcb_view_ilp<V>); they join the total in group order.
   static constexpr bool MCMCB_VIEW_DEFAULTS = true;  // checkbounds is always true, priorfun is the default prior
   template <class V>
   __device__ __forceinline__ static void ssfunction_view(const V& theta, int, int, const mcmcb_ctx& c, double* ss) {
@@ -371,26 +371,34 @@ struct HierN {
     const double* __restrict__ y = c.data + 2;
     const double mu = theta[G], ltau = theta[G + 1];
     const double itau2 = exp(-2.0 * ltau);
+    constexpr int W = mcmcb_view_ilp<V>::value;  // groups in flight (4 unless the view asks otherwise)
     double acc = 0.0;
     int g = 0;
-    for (; g + 4 <= G; g += 4) {
-      double tg[4], a[4];
+    for (; g + W <= G; g += W) {
+      double tg[W], a[W];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { tg[q] = theta[g + q]; a[q] = 0.0; }
+      for (int q = 0; q < W; q++) { tg[q] = theta[g + q]; a[q] = 0.0; }
       for (int j = 0; j < J; j++) {
         const double* yj = y + (size_t)j * G + g;
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const double r = yj[q] - tg[q]; a[q] = fma(r, r, a[q]); }
+        for (int q = 0; q < W; q++) { const double r = yj[q] - tg[q]; a[q] = fma(r, r, a[q]); }
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
+      for (int q = 0; q < W; q++) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
     }
-    for (; g < G; g++) {
-      const double tg = theta[g];
-      double a = 0.0;
-      for (int j = 0; j < J; j++) { const double r = y[(size_t)j * G + g] - tg; a = fma(r, r, a); }
-      const double dm = tg - mu;
-      acc += a + dm * dm * itau2;
+    if (g < G) {  // the ragged last block: the same W chains, groups past the end clamped and left out of the total
+      double tg[W], a[W];
+      int gi[W];
+#pragma unroll
+      for (int q = 0; q < W; q++) { gi[q] = g + q < G ? g + q : G - 1; tg[q] = theta[gi[q]]; a[q] = 0.0; }
+      for (int j = 0; j < J; j++) {
+        const double* yj = y + (size_t)j * G;
+#pragma unroll
+        for (int q = 0; q < W; q++) { const double r = yj[gi[q]] - tg[q]; a[q] = fma(r, r, a[q]); }
+      }
+#pragma unroll
+      for (int q = 0; q < W; q++)
+        if (g + q < G) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
     }
     acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
     ss[0] = acc;

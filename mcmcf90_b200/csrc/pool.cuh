@@ -174,22 +174,39 @@ static __global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2
   }
   const int nv = d * d;
   const double W = buf[0];
+  constexpr int U = 8;  // chains in flight per thread: the sum over chains stays in chain order, the loads do not wait
+  const long long G = gridDim.x;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) {
     const int b = v / d, a = v - b * d;  // entry (a, b), column-major; symmetric result
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     double acc = 0.0;
-    for (long long c = blockIdx.x; c < p.nchains; c += gridDim.x) {
-      if (ram) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
+    if (ram) {
+      for (long long c = blockIdx.x; c < p.nchains; c += G) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
         const double* R = p.Rm + (size_t)c * p.r_stride;
         double s = 0.0;
         for (int i = 0; i <= lo; i++) s = fma(R[(size_t)i * d + lo], R[(size_t)i * d + hi], s);
         acc += s;
-      } else {
-        const double w = p.st[Lo.wsum * p.pitch + c];
-        if (!(w > 0.0)) continue;
-        const double da = p.mean[c * p.dp + a] - buf[1 + a] / W, db = p.mean[c * p.dp + b] - buf[1 + b] / W;
-        // cmat is kept symmetric by the recursion (cta_absorb updates every entry)
-        acc += (w - 1.0) * p.cmat[(size_t)c * d * d + (size_t)lo * d + hi] + w * (da * db);
+      }
+    } else {
+      // cmat is exactly symmetric after a tick (both images of an entry are written from one register by
+      // cta_absorb_rows / k2_absorb_resident_kernel / cta_ap_window), so entry v itself is read: consecutive threads,
+      // consecutive addresses.  The (lo, hi) image is a stride-d gather -- four times the sectors.
+      const double mua = buf[1 + a] / W, mub = buf[1 + b] / W;
+      for (long long c = blockIdx.x; c < p.nchains; c += U * G) {
+        double w[U], t[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const long long cc = c + u * G;
+          w[u] = cc < p.nchains ? p.st[Lo.wsum * p.pitch + cc] : 0.0;
+          t[u] = 0.0;
+          if (w[u] > 0.0) {
+            const double da = p.mean[cc * p.dp + a] - mua, db = p.mean[cc * p.dp + b] - mub;
+            t[u] = fma(w[u] - 1.0, p.cmat[(size_t)cc * nv + v], w[u] * (da * db));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (w[u] > 0.0) acc += t[u];
       }
     }
     partial[(size_t)blockIdx.x * nv + v] = acc;

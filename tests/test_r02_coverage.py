@@ -418,8 +418,9 @@ def test_thread_per_chain_ram_kernel_matches_the_oracle(case, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ thread-per-chain SCAM
-@pytest.mark.parametrize("G,J,N,steps", [(6, 4, 64, 59), (198, 10, 8, 3)])
-def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, monkeypatch):
+@pytest.mark.parametrize("k5s", ["1", "0"])
+@pytest.mark.parametrize("G,J,N,steps", [(6, 4, 64, 59), (198, 10, 8, 3), (13, 3, 150, 21)])
+def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, k5s, monkeypatch):
     """k5_scam_step_kernel (one thread per chain, shared rotation, proposal never materialised: HierN::ssfunction_axpy)
     is what large pooled SCAM populations run on (BASELINE C5); forced here on a small population.  Up to the first
     pooled tick every chain is the reference's own SCAM chain: exact counters against the oracle."""
@@ -431,12 +432,14 @@ def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, monkeyp
     par0 = 0.1 + 0.05 * rng.normal(size=(N, d))
     cmat0 = np.diag(0.02 * (1.0 + np.arange(d) / d))
     monkeypatch.setenv("MCMCB_K5", "1")
+    monkeypatch.setenv("MCMCB_K5S", k5s)   # theta in shared memory (k5s_scam.cuh) / in local memory (k5_scam.cuh)
     s = mb.Sampler(mb.default_config(nchains=N, seed=23, model="hier", pool_adapt=1, store_chains=2, **nml))
     s.set_data(blob)
     s.set_initial(par0, cmat0, [1.0], [G * J])
     s.run(steps // 2)
     s.run(steps - steps // 2)
     assert s.info()["lanes_per_chain"] == 1
+    assert (s.info()["smem_bytes"] > 8 * d * 64) == (k5s == "1")
     cnt, par, ss, s2 = s.counters(), s.fetch("par"), s.fetch("ss"), s.fetch("sigma2")
     assert (cnt["status"] == 0).all()
     for c in (0, 1, N - 1):
@@ -482,3 +485,91 @@ def test_thread_per_chain_scam_kernel_across_pooled_ticks(monkeypatch):
     assert a["pool"][0] == b["pool"][0]
     np.testing.assert_allclose(a["pool"][1], b["pool"][1], rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(a["q"][0], b["q"][0], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ resident tick
+def _tick_run(resident, monkeypatch, model, blob, d, N, nml, par0, cmat0, pool=0, kernel=2, runs=()):
+    monkeypatch.setenv("MCMCB_TICK_RESIDENT", "1" if resident else "0")
+    s = mb.Sampler(mb.default_config(nchains=N, seed=11, model=model, kernel=kernel, pool_adapt=pool, **nml))
+    s.set_data(blob)
+    s.set_initial(par0, cmat0, [1.0], [1])
+    for n in runs:
+        s.run(n)
+    out = dict(par=s.fetch("par"), cnt=s.counters(), launches=s.launches,
+               stats=[s.fetch_stats(c) for c in (0, N // 2, N - 1)])
+    if pool:
+        out["pool"] = s.pool_fetch()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("d,method,initcmatn,pool", [(100, "dram", 1, 0), (18, "dram", 0, 0), (33, "dram", 1, 0),
+                                                     (64, "scam", 1, 0), (24, "dram", 1, 1)])
+def test_resident_tick_is_bit_identical_to_the_streamed_tick(d, method, initcmatn, pool, monkeypatch):
+    """k2_absorb_resident_kernel (all logged rows in shared memory, 4 x 4 register tiles) against cta_absorb_rows (8-row
+    window, runs of 8 entries): the covariance recursion of matutils.F90:283-310 applied to every entry in the same
+    order, so means, covariances, factors, chains and counters must agree to the last bit -- ragged npar (18, 33),
+    the wsum = 0 reset row (initcmatn = 0), the SVD factor modes and the pooled tick included."""
+    N = 40
+    mu, lam = gauss_target(d)
+    blob = mb.models.blob_gauss(mu, lam)
+    a = 2 * d if not pool else 30
+    nml = dict(nsimu=3 * a + 10, adaptint=a, initcmatn=initcmatn, updatesigma=0, method=method,
+               drscale=2.0 if method == "dram" else 0.0)
+    par0 = 0.1 * np.random.default_rng(d).normal(size=(N, d))
+    runs = (a + 3, a, a + 2)   # three ticks, launches split off the tick boundaries
+    got = [_tick_run(r, monkeypatch, "gauss", blob, d, N, nml, par0, 0.02 * np.eye(d), pool=pool, runs=runs) for r in (0, 1)]
+    if not pool:                                            # the resident kernel did run: one more launch per private tick
+        assert got[1]["launches"] == got[0]["launches"] + 3
+    assert np.array_equal(got[0]["par"], got[1]["par"])
+    for k in CNT + ("status",):
+        assert np.array_equal(got[0]["cnt"][k], got[1]["cnt"][k]), k
+    for x, y in zip(got[0]["stats"], got[1]["stats"]):
+        assert x["wsum"] == y["wsum"] and x["wsum"] > 0
+        for k in ("mean", "cmat", "R"):
+            assert np.array_equal(x[k], y[k]), k
+        assert np.array_equal(x["cmat"], x["cmat"].T)
+    if pool:
+        for x, y in zip(got[0]["pool"], got[1]["pool"]):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
+# ------------------------------------------------------------------------------------------------ theta in shared memory
+@pytest.mark.parametrize("ilp", ["8", "4"])
+def test_scam_kernel_with_theta_in_shared_memory_is_bit_identical(ilp, monkeypatch):
+    """k5s_scam_step_kernel against k5_scam_step_kernel: the same draws and, element by element, the same fma sequence
+    (theta + delta U(:,j) composed on the fly, rewritten on acceptance) -- chains, sums of squares, counters, logged rows
+    (through the pooled covariance of two ticks) and the stored chain agree to the last bit.  150 chains: the last CTA
+    has shadow threads; 198 groups with 8 in flight: the ragged last block of the model's view."""
+    G, J, N = 198, 3, 150
+    rng = np.random.default_rng(31)
+    y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
+    blob = mb.models.blob_hier(y)
+    d = G + 2
+    nml = dict(method="scam", nsimu=14, adaptint=4, initcmatn=1, updatesigma=1, N0=2.0, S02=1.0)
+    par0 = 0.1 * rng.normal(size=(N, d))
+    monkeypatch.setenv("MCMCB_K5", "1")
+    monkeypatch.setenv("MCMCB_K5S_ILP", ilp)
+    out = {}
+    for k5s in ("1", "0"):
+        monkeypatch.setenv("MCMCB_K5S", k5s)
+        s = mb.Sampler(mb.default_config(nchains=N, seed=5, model="hier", pool_adapt=1, store_chains=3, **nml))
+        s.set_data(blob)
+        s.set_initial(par0, 0.05 * np.eye(d), [1.0], [G * J])
+        s.run(6)
+        s.run(7)
+        out[k5s] = dict(cnt=s.counters(), par=s.fetch("par"), ss=s.fetch("ss"), s2=s.fetch("sigma2"), pool=s.pool_fetch(),
+                        chain=s.fetch_chain(2), smem=s.info()["smem_bytes"])
+        assert (out[k5s]["cnt"]["status"] == 0).all()
+        s.close()
+    a, b = out["1"], out["0"]
+    assert a["smem"] > 8 * d * 64 > b["smem"]
+    for k in CNT:
+        assert np.array_equal(a["cnt"][k], b["cnt"][k]), k
+    for k in ("par", "ss", "s2"):
+        assert np.array_equal(a[k], b[k]), k
+    for x, y_ in zip(a["pool"], b["pool"]):
+        assert np.array_equal(np.asarray(x), np.asarray(y_))
+    for k in ("chain", "sschain", "s2chain"):
+        if k in a["chain"]:
+            assert np.array_equal(a["chain"][k], b["chain"][k]), k
