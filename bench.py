@@ -147,7 +147,7 @@ class Workload:
         self.cmat0, self.sigma2, self.nobs = 0.1 * np.eye(d), [1.0], [1]
         self.par0 = lambda nn, off: np.zeros((nn, d))
         self.pool, self.bound = 1, "fp64"
-        self.kernel = "k5_scam_step_kernel"
+        self.kernel = "k5s_scam_step_kernel"
 
     def blob(self, mod):
         return getattr(mod, self.blob_args[0])(*self.blob_args[1])

@@ -997,7 +997,7 @@ extern "C" int mcmcb_info(mcmcb_handle h, int* npar, int* nycol, int* lanes, int
   if (!h->kids.empty()) return mcmcb_info(h->kids[0], npar, nycol, lanes, kernel, tpb, blocks, smem);
   if (npar) *npar = h->npar;
   if (nycol) *nycol = h->nycol;
-  if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : (h->k4 ? 1 : h->L);
+  if (lanes) *lanes = (h->model && h->model->kernel == 2 && h->k2_group_threads > 0) ? h->k2_group_threads : (h->k5s_lanes > 0 ? h->k5s_lanes : (h->k4 ? 1 : h->L));
   if (kernel) *kernel = h->model ? h->model->kernel : 0;
   if (tpb) *tpb = (h->model && h->model->kernel == 2) ? h->k2_warps * 32 : h->k1_threads_used;
   if (blocks) *blocks = h->blocks;

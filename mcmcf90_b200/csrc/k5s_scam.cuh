@@ -25,42 +25,71 @@
 
 namespace mcmcb {
 
-constexpr int K5S_THREADS = 128;
+constexpr int K5S_CHAINS = 128;  // chains per CTA (fewer when npar is larger than ~200: k5s_chains)
+
+// Element k of the chain in slot s of the CTA's theta block.  Rows are NC slots long (NC a multiple of 16); odd rows
+// swap the two halves of every 16 slots, so the L lanes of a chain -- which read L consecutive rows at the same time --
+// spread over all banks (L = 4: the optimum of two wavefronts per 64-bit warp access instead of four).
+__device__ __forceinline__ int k5s_at(int k, int s, int NC) { return k * NC + (s ^ ((k & 1) << 3)); }
 
 template <int W>
 struct K5SView {
   static constexpr int ILP = W;
-  const double* th;  // shared: element k of this thread's chain at th[k * T]
-  const double* u;   // shared: the column of this warp's move
+  const double* th;  // shared: the CTA's theta block
+  const double* u;   // shared: the column of the CTA's current move
   double dl;
-  int T;
-  __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[(size_t)k * T]); }
+  int NC, s;
+  __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[k5s_at(k, s, NC)]); }
 };
 
-// bytes of dynamic shared memory: blob | per-warp column buffers | theta
-__host__ __device__ __forceinline__ size_t k5s_smem_bytes(int d, int threads, size_t blob_bytes) {
-  const size_t dpad = (size_t)(d + 1) & ~(size_t)1;
-  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * ((size_t)(threads / 32) * dpad + (size_t)d * threads);
+// bytes of dynamic shared memory: blob | two column buffers (npar + 1 doubles each: U(:,j) and qcovstd(j)) | theta
+__host__ __device__ __forceinline__ size_t k5s_smem_bytes(int d, int chains, size_t blob_bytes) {
+  const size_t dp2 = (size_t)(d + 2) & ~(size_t)1;
+  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * (2 * dp2 + (size_t)d * chains);
 }
 
-template <class M, int W>
-__global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
+template <int L>
+__device__ __forceinline__ double k5s_lanes_sum(double v) {
+#pragma unroll
+  for (int off = 1; off < L; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+
+// default prior (priorfun.f90:97-100) of a view, split over the chain's lanes
+template <class V>
+__device__ __forceinline__ double k5s_default_prior_view(const V& theta, int len, const mcmcb_ctx& c) {
+  if (c.prior == nullptr) return 0.0;
+  double p = 0.0;
+  for (int i = c.lane; i < len; i += c.nlanes) {
+    const double sg = c.prior[len + i];
+    if (sg > 0.0) {
+      const double t = (theta[i] - c.prior[i]) / sg;
+      p += t * t;
+    }
+  }
+  return p;
+}
+
+// W = accumulation chains the model keeps in flight, L = lanes per chain (1, 2 or 4; blockDim = L x chains per CTA)
+template <class M, int W, int L>
+__global__ void __launch_bounds__(K5S_CHAINS * L, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
-  constexpr int NPF = K4_DM / 32;  // column elements a lane prefetches
+  constexpr int NPF = (K4_DM + 64 * L - 1) / (64 * L);  // column elements a thread carries (blockDim >= 64 L)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);  // every thread of the CTA takes part (barrier inside)
   const double* data = reinterpret_cast<const double*>(smem_raw);
-  const int d = p.d, T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int dpad = (d + 1) & ~1;
-  double* ucol = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15)) + (size_t)warp * dpad;
-  double* th = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15)) + (size_t)(T >> 5) * dpad + tid;
+  const int d = p.d, T = blockDim.x, NC = T / L, tid = threadIdx.x, s = tid / L, sub = tid % L;
+  const int dp2 = (d + 2) & ~1;
+  double* ucol = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
+  double* th = ucol + 2 * (size_t)dp2;
 
-  // a thread past the last chain shadows the last chain (its warp's column staging needs every lane) and writes nothing
-  const long long c0 = (long long)blockIdx.x * T + tid;
+  // a slot past the last chain shadows the last chain (barriers and shuffles need every thread) and writes nothing
+  const long long c0 = (long long)blockIdx.x * NC + s;
   const bool live = c0 < p.nchains;
   const long long cc = live ? c0 : p.nchains - 1;
+  const bool lead = live && sub == 0;  // the lane that writes the chain's scalars
   const DevCfg& c = p.c;
   const size_t P = (size_t)p.pitch;
   double* st = p.st + cc;
@@ -70,7 +99,7 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
   double* gth = p.theta + cc * p.dp;
   double* rb = p.rowbuf + (size_t)cc * (p.rowcap + 1) * (d + 1);
 
-  for (int k = 0; k < d; k++) th[(size_t)k * T] = gth[k];
+  for (int k = sub; k < d; k += L) th[k5s_at(k, s, NC)] = gth[k];
   double ss1[NY], s2[NY];
 #pragma unroll
   for (int k = 0; k < NY; k++) { ss1[k] = st[(Lo.ss + k) * P]; s2[k] = st[(Lo.s2 + k) * P]; }
@@ -78,7 +107,7 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
   int stayed = ist[Lo.i_stayed * P], bnd = ist[Lo.i_bnd * P], chainind = ist[Lo.i_chainind * P];
   int simuind = ist[Lo.i_simuind * P], status = ist[Lo.i_status * P], cnt = ist[Lo.i_cnt * P], pend = ist[Lo.i_pend * P];
   int nbuf = ist[Lo.i_nbuf * P];
-  Rng g;
+  Rng g;  // the chain's L lanes run the same generator: same draws, same decisions
   g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * P] << 32) | (unsigned)ist[Lo.i_ndlo * P];
   g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
   g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
@@ -93,60 +122,57 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
   double* ss2st = p.store_s2_p + (size_t)cc * p.store_rows * NY;
 
   mcmcb_ctx ctx;
-  ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = 0; ctx.nlanes = 1;
+  ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = sub; ctx.nlanes = L;
   ctx.exp_tl = 0u; ctx.exp_c1 = MCMCB_EXP_C1L; ctx.exp_c2 = MCMCB_EXP_C2L; ctx.scratch = nullptr;
 
-  // the current point as a view: a zero move along a zeroed column (only the first launch evaluates it)
   K5SView<W> tv;
-  tv.th = th; tv.u = ucol; tv.dl = 0.0; tv.T = T;
+  tv.th = th; tv.u = ucol + dp2; tv.dl = 0.0; tv.NC = NC; tv.s = s;
 
-  for (int k = lane; k < d; k += 32) ucol[k] = 0.0;  // theta + 0 * 0: the current point itself
-  __syncwarp();
+  // buffer 0 <- column 0 and its scale; buffer 1 <- zeros (the current point as a view: a zero move along a zero column)
+  for (int k = tid; k < d; k += T) { ucol[k] = U[k]; ucol[dp2 + k] = 0.0; }
+  if (tid == 0) ucol[d] = gq[0];
+  __syncthreads();
   if (simuind == 0) {  // MCMC_run_scam.F90:26-36: initial point, saved as row 1
     double ssn[NY];
     M::ssfunction_view(tv, d, NY, ctx, ssn);
 #pragma unroll
-    for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
-    pri1 = k5_default_prior_view(tv, d, ctx);
+    for (int k = 0; k < NY; k++) ss1[k] = k5s_lanes_sum<L>(ssn[k]);
+    pri1 = k5s_lanes_sum<L>(k5s_default_prior_view(tv, d, ctx));
     chainind = 1; simuind = 1; cnt = 1; pend = 1;
     if (stored) {
-      for (int k = 0; k < d; k++) srow[k] = th[(size_t)k * T];
+      for (int k = sub; k < d; k += L) srow[k] = th[k5s_at(k, s, NC)];
+      if (sub == 0) {
 #pragma unroll
-      for (int k = 0; k < NY; k++) { srow[d + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
+        for (int k = 0; k < NY; k++) { srow[d + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
+      }
     }
   }
+  __syncthreads();  // nobody reads the zero column any more: it becomes the buffer of move 1
 
-  // column 0 and its scale, fetched ahead
-  double pf[NPF], qn = gq[0];
-#pragma unroll
-  for (int i = 0; i < NPF; i++) { const int k = lane + 32 * i; pf[i] = k < d ? U[k] : 0.0; }
-
+  int jb = 0;
   for (int done = 0; done < p.nsteps; done++) {
     bool rejall = true;
     bool logged = false;  // the row that is about to be replaced has been written to the row buffer
     for (int j = 0; j < d; j++) {
-      // ---- stage this move's column (everybody is done with the previous one), fetch the next
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < NPF; i++) { const int k = lane + 32 * i; if (k < d) ucol[k] = pf[i]; }
-      const double qj = qn;
-      __syncwarp();
+      const double* uc = ucol + (size_t)jb * dp2;
+      // ---- the next move's column and scale start their trip from L2 now and are published after this move
+      double pf[NPF], qn = 0.0;
       {
         const int jn = j + 1 < d ? j + 1 : 0;
         const double* ncol = U + (size_t)jn * d;
 #pragma unroll
-        for (int i = 0; i < NPF; i++) { const int k = lane + 32 * i; pf[i] = k < d ? ncol[k] : 0.0; }
-        qn = gq[jn];
+        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; pf[i] = k < d ? ncol[k] : 0.0; }
+        if (tid == 0) qn = gq[jn];
       }
       // MCMC_propose_sc (MCMC_run_scam.F90:94-117) in the O(d) form theta + delta U(:,j)
-      const double delta = g.normal() * qj;
-      tv.dl = delta;
+      const double delta = g.normal() * uc[d];
+      tv.u = uc; tv.dl = delta;
       double ssn[NY];
-      const double prn = k5_default_prior_view(tv, d, ctx);
+      const double prn = k5s_lanes_sum<L>(k5s_default_prior_view(tv, d, ctx));
       M::ssfunction_view(tv, d, NY, ctx, ssn);
       double sum = 0.0;
 #pragma unroll
-      for (int k = 0; k < NY; k++) sum += (ssn[k] - ss1[k]) / s2[k];
+      for (int k = 0; k < NY; k++) { ssn[k] = k5s_lanes_sum<L>(ssn[k]); sum += (ssn[k] - ss1[k]) / s2[k]; }
       const bool reject = mh_reject(alpha_from_tst(-0.5 * (sum + (prn - pri1))), g);
       if (!reject) {  // MCMC_run_scam.F90:63-68
         if (!logged) {
@@ -156,8 +182,8 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
           if (absorbing) {
             if (nbuf < p.rowcap) {
               if (live) {
-                for (int k = 0; k < d; k++) rb[(size_t)nbuf * (d + 1) + k] = th[(size_t)k * T];
-                rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
+                for (int k = sub; k < d; k += L) rb[(size_t)nbuf * (d + 1) + k] = th[k5s_at(k, s, NC)];
+                if (sub == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
               }
               nbuf++;
             } else {
@@ -166,12 +192,22 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
           }
           logged = true;
         }
-        for (int k = 0; k < d; k++) th[(size_t)k * T] = fma(ucol[k], delta, th[(size_t)k * T]);
+        for (int k = sub; k < d; k += L) { const int e = k5s_at(k, s, NC); th[e] = fma(uc[k], delta, th[e]); }
 #pragma unroll
         for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
         pri1 = prn;
         rejall = false;
       }
+      // ---- publish the next column (its buffer was last read during the previous move) and meet: theta elements
+      // written by one lane of a chain are read by the others in the next move
+      {
+        double* un = ucol + (size_t)(jb ^ 1) * dp2;
+#pragma unroll
+        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; if (k < d) un[k] = pf[i]; }
+        if (tid == 0) un[d] = qn;
+      }
+      __syncthreads();
+      jb ^= 1;
     }
     // ---------------- end of sweep, MCMC_run_scam.F90:74-86
     const int i = simuind + 1;
@@ -180,7 +216,7 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
       stayed++;
       cnt++; pend++;
     } else {
-      if (stored && chainind - 1 < p.store_rows) scnt[chainind - 1] = (double)cnt;
+      if (stored && sub == 0 && chainind - 1 < p.store_rows) scnt[chainind - 1] = (double)cnt;
       chainind++;
       cnt = 1; pend = 1;
     }
@@ -194,14 +230,16 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
     if (stored) {
       if (!rejall) {
         if (chainind - 1 < p.store_rows) {
-          for (int k = 0; k < d; k++) srow[(size_t)(chainind - 1) * (d + NY) + k] = th[(size_t)k * T];
+          for (int k = sub; k < d; k += L) srow[(size_t)(chainind - 1) * (d + NY) + k] = th[k5s_at(k, s, NC)];
+          if (sub == 0) {
 #pragma unroll
-          for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (d + NY) + d + k] = ss1[k];
+            for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (d + NY) + d + k] = ss1[k];
+          }
         } else {
           status |= MCMCB_ST_STORE_FULL;
         }
       }
-      if (c.updatesigma && i - 1 < p.store_rows) {
+      if (c.updatesigma && sub == 0 && i - 1 < p.store_rows) {
 #pragma unroll
         for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
       }
@@ -211,7 +249,8 @@ __global__ void __launch_bounds__(K5S_THREADS, 1) k5s_scam_step_kernel(const __g
 
   if (!live) return;
   // ---- write state back
-  for (int k = 0; k < d; k++) gth[k] = th[(size_t)k * T];
+  for (int k = sub; k < d; k += L) gth[k] = th[k5s_at(k, s, NC)];
+  if (!lead) return;
 #pragma unroll
   for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * P] = ss1[k]; st[(Lo.s2 + k) * P] = s2[k]; }
   st[Lo.pri * P] = pri1; st[Lo.spare * P] = g.spare;

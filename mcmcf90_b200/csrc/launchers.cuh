@@ -739,40 +739,49 @@ struct K2 {
     h->smem = smem;
     h->k2_warps = K5_THREADS / 32;
     h->k4 = true;  // one thread per chain (mcmcb_info)
+    h->k5s_lanes = 0;
     CK(cudaGetLastError());
     return 0;
   }
 
   // theta-in-shared-memory variant (k5s_scam.cuh): the model must evaluate views, and >= 64 chains' theta must fit beside
-  // the blob.  Returns the CTA size, 0 = not applicable.
-  static int k5s_threads(mcmcb_handle h) {
+  // the blob.  Returns the chains per CTA, 0 = not applicable.
+  static int k5s_chains(mcmcb_handle h) {
     if constexpr (!has_ssfunction_view<M>::value) {
       return 0;
     } else {
       if (const char* e = getenv("MCMCB_K5S")) { if (e[0] == '0') return 0; }  // tuning / tests
-      for (int t = K5S_THREADS; t >= 64; t -= 32)
-        if (k5s_smem_bytes(h->npar, t, h->blob_bytes) + 1024 <= h->max_smem) return t;
+      for (int nc = K5S_CHAINS; nc >= 64; nc -= 32)
+        if (k5s_smem_bytes(h->npar, nc, h->blob_bytes) + 1024 <= h->max_smem) return nc;
       return 0;
     }
   }
 
-  static int launch_k5s(mcmcb_handle h, const K2Params& p, int threads) {
+  template <int W, int L>
+  static int launch_k5s_as(mcmcb_handle h, const K2Params& p, int chains) {
     if constexpr (has_ssfunction_view<M>::value) {
-      int ilp = 8;
-      if (const char* e = getenv("MCMCB_K5S_ILP")) ilp = atoi(e);  // tuning experiments only
-      auto kern = ilp == 4 ? k5s_scam_step_kernel<M, 4> : k5s_scam_step_kernel<M, 8>;
-      const size_t smem = k5s_smem_bytes(h->npar, threads, h->blob_bytes);
+      auto kern = k5s_scam_step_kernel<M, W, L>;
+      const size_t smem = k5s_smem_bytes(h->npar, chains, h->blob_bytes);
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const unsigned blocks = (unsigned)((h->cfg.nchains + threads - 1) / threads);
-      kern<<<blocks, threads, smem, h->stream>>>(p);
+      const unsigned blocks = (unsigned)((h->cfg.nchains + chains - 1) / chains);
+      kern<<<blocks, chains * L, smem, h->stream>>>(p);
       h->launches++;
       h->blocks = (int)blocks;
       h->smem = smem;
-      h->k2_warps = threads / 32;
-      h->k4 = true;  // one thread per chain (mcmcb_info)
+      h->k2_warps = chains * L / 32;
+      h->k5s_lanes = L;
+      h->k4 = L == 1;  // one thread per chain (mcmcb_info)
       CK(cudaGetLastError());
     }
     return 0;
+  }
+
+  static int launch_k5s(mcmcb_handle h, const K2Params& p, int chains) {
+    int lanes = 4;
+    if (const char* e = getenv("MCMCB_K5S_LANES")) lanes = atoi(e);  // tuning / tests
+    if (lanes == 1) return launch_k5s_as<8, 1>(h, p, chains);
+    if (lanes == 2) return launch_k5s_as<4, 2>(h, p, chains);
+    return launch_k5s_as<4, 4>(h, p, chains);
   }
 
   static bool is_tick(const mcmcb_config& c, long long i) {
@@ -828,7 +837,7 @@ struct K2 {
     if (group) { resident = false; W = GT * ngroups / 32; h->k2_group_threads = GT; }
     if (resident != h->r_resident || W != h->k2_warps) { h->r_resident = resident; h->k2_warps = W; h->attr_set = false; }
     const bool k5 = use_k5(h);
-    const int k5s = k5 ? k5s_threads(h) : 0;
+    const int k5s = k5 ? k5s_chains(h) : 0;
     int left = nsteps;
     bool first = true;
     while (left > 0 || first) {
@@ -905,8 +914,14 @@ struct K2 {
     } else {
       const int nv = phase == 1 ? 1 + d : d * d;
       double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + d;
-      k2_pool_moments_kernel<<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
-      pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      if (phase == 2 && h->cfg.method != MCMCB_RAM) {  // (tile, slice) grid, four chains in flight per thread
+        const int S = pool_cov_slices(d), ntile = (d + POOL_COV_TB - 1) / POOL_COV_TB;
+        k2_pool_cov_kernel<<<ntile * S, POOL_THREADS, 0, h->stream>>>(p, h->d_pool, h->d_pool_partial);
+        pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, S, nv, out);
+      } else {
+        k2_pool_moments_kernel<<<POOL_BLOCKS, POOL_THREADS, 0, h->stream>>>(p, phase, h->d_pool, h->d_pool_partial);
+        pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, POOL_BLOCKS, nv, out);
+      }
       h->launches += 2;
     }
     CK(cudaGetLastError());

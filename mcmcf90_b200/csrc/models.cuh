@@ -372,25 +372,29 @@ struct HierN {
     const double mu = theta[G], ltau = theta[G + 1];
     const double itau2 = exp(-2.0 * ltau);
     constexpr int W = mcmcb_view_ilp<V>::value;  // groups in flight (4 unless the view asks otherwise)
+    // the chain's lanes take the groups round-robin (lane, lane + nlanes, ...): one lane = every group, in order
+    const int lane = c.lane, nl = c.nlanes;
+    const int mine = (G - lane + nl - 1) / nl;  // groups of this lane
     double acc = 0.0;
-    int g = 0;
-    for (; g + W <= G; g += W) {
+    int i = 0;
+    for (; i + W <= mine; i += W) {
+      const int g = lane + nl * i;
       double tg[W], a[W];
 #pragma unroll
-      for (int q = 0; q < W; q++) { tg[q] = theta[g + q]; a[q] = 0.0; }
+      for (int q = 0; q < W; q++) { tg[q] = theta[g + nl * q]; a[q] = 0.0; }
       for (int j = 0; j < J; j++) {
         const double* yj = y + (size_t)j * G + g;
 #pragma unroll
-        for (int q = 0; q < W; q++) { const double r = yj[q] - tg[q]; a[q] = fma(r, r, a[q]); }
+        for (int q = 0; q < W; q++) { const double r = yj[nl * q] - tg[q]; a[q] = fma(r, r, a[q]); }
       }
 #pragma unroll
       for (int q = 0; q < W; q++) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
     }
-    if (g < G) {  // the ragged last block: the same W chains, groups past the end clamped and left out of the total
+    if (i < mine) {  // the ragged last block: the same W chains, groups past the end clamped and left out of the total
       double tg[W], a[W];
       int gi[W];
 #pragma unroll
-      for (int q = 0; q < W; q++) { gi[q] = g + q < G ? g + q : G - 1; tg[q] = theta[gi[q]]; a[q] = 0.0; }
+      for (int q = 0; q < W; q++) { gi[q] = lane + nl * (i + q < mine ? i + q : mine - 1); tg[q] = theta[gi[q]]; a[q] = 0.0; }
       for (int j = 0; j < J; j++) {
         const double* yj = y + (size_t)j * G;
 #pragma unroll
@@ -398,9 +402,10 @@ struct HierN {
       }
 #pragma unroll
       for (int q = 0; q < W; q++)
-        if (g + q < G) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
+        if (i + q < mine) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
     }
-    acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
+    if (lane == 0)
+      acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
     ss[0] = acc;
   }
 };

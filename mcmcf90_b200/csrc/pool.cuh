@@ -172,44 +172,73 @@ static __global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2
     }
     return;
   }
+  // phase 2, RAM: sum of R'R (the covariance modes run k2_pool_cov_kernel)
   const int nv = d * d;
-  const double W = buf[0];
-  constexpr int U = 8;  // chains in flight per thread: the sum over chains stays in chain order, the loads do not wait
-  const long long G = gridDim.x;
   for (int v = threadIdx.x; v < nv; v += blockDim.x) {
     const int b = v / d, a = v - b * d;  // entry (a, b), column-major; symmetric result
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     double acc = 0.0;
-    if (ram) {
-      for (long long c = blockIdx.x; c < p.nchains; c += G) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
-        const double* R = p.Rm + (size_t)c * p.r_stride;
-        double s = 0.0;
-        for (int i = 0; i <= lo; i++) s = fma(R[(size_t)i * d + lo], R[(size_t)i * d + hi], s);
-        acc += s;
-      }
-    } else {
-      // cmat is exactly symmetric after a tick (both images of an entry are written from one register by
-      // cta_absorb_rows / k2_absorb_resident_kernel / cta_ap_window), so entry v itself is read: consecutive threads,
-      // consecutive addresses.  The (lo, hi) image is a stride-d gather -- four times the sectors.
-      const double mua = buf[1 + a] / W, mub = buf[1 + b] / W;
-      for (long long c = blockIdx.x; c < p.nchains; c += U * G) {
-        double w[U], t[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const long long cc = c + u * G;
-          w[u] = cc < p.nchains ? p.st[Lo.wsum * p.pitch + cc] : 0.0;
-          t[u] = 0.0;
-          if (w[u] > 0.0) {
-            const double da = p.mean[cc * p.dp + a] - mua, db = p.mean[cc * p.dp + b] - mub;
-            t[u] = fma(w[u] - 1.0, p.cmat[(size_t)cc * nv + v], w[u] * (da * db));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-          if (w[u] > 0.0) acc += t[u];
-      }
+    for (long long c = blockIdx.x; c < p.nchains; c += gridDim.x) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
+      const double* R = p.Rm + (size_t)c * p.r_stride;
+      double s = 0.0;
+      for (int i = 0; i <= lo; i++) s = fma(R[(size_t)i * d + lo], R[(size_t)i * d + hi], s);
+      acc += s;
     }
     partial[(size_t)blockIdx.x * nv + v] = acc;
+  }
+}
+
+// Phase 2 of the covariance modes at large populations: CTA (tile, slice) owns rows b0 .. b0+3 of the result and the
+// chains slice, slice + S, ...; thread a owns the four entries (a, b0 + q).  A chain costs a thread ONE mean element of its
+// own (the four mean(b) are uniform), four consecutive-address covariance reads and four independent accumulators; four
+// chains are in flight, so 16 covariance loads per thread are outstanding (84 GB at BASELINE C5: the layout of
+// k2_pool_moments_kernel, entries outer / chains inner with one dependent load chain per thread, ran at 0.6 TB/s).
+// cmat is exactly symmetric after a tick (both images of an entry are written from one register by cta_absorb_rows /
+// k2_absorb_resident_kernel / cta_ap_window), so image (b, a) -- consecutive a, consecutive addresses -- is read.
+// partial[slice][v]; pool_final_kernel adds the slices in index order: bit-reproducible for a given chain count per GPU.
+constexpr int POOL_COV_TB = 4;  // rows of the result per CTA
+__host__ __device__ __forceinline__ int pool_cov_slices(int d) { return max(1, POOL_BLOCKS / ((d + POOL_COV_TB - 1) / POOL_COV_TB)); }
+
+static __global__ void __launch_bounds__(POOL_THREADS) k2_pool_cov_kernel(K2Params p, const double* buf, double* partial) {
+  constexpr K2Layout Lo = k2_layout(1);
+  constexpr int U = 4, TB = POOL_COV_TB;
+  const int d = p.d, nv = d * d;
+  const int ntile = (d + TB - 1) / TB, S = pool_cov_slices(d);
+  const int tile = blockIdx.x % ntile, slice = blockIdx.x / ntile, b0 = TB * tile;
+  const double W = buf[0];
+  int bq[TB];
+  double mub[TB];
+#pragma unroll
+  for (int q = 0; q < TB; q++) { bq[q] = min(b0 + q, d - 1); mub[q] = buf[1 + bq[q]] / W; }
+  for (int a = threadIdx.x; a < d; a += blockDim.x) {
+    const double mua = buf[1 + a] / W;
+    double acc[TB];
+#pragma unroll
+    for (int q = 0; q < TB; q++) acc[q] = 0.0;
+    for (long long c = slice; c < p.nchains; c += (long long)U * S) {
+      double w[U], t[U][TB];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long cc = c + (long long)u * S;
+        w[u] = cc < p.nchains ? p.st[Lo.wsum * p.pitch + cc] : 0.0;
+        if (w[u] > 0.0) {
+          const double* m = p.mean + cc * p.dp;
+          const double* cm = p.cmat + (size_t)cc * nv + a;
+          const double da = m[a] - mua;
+#pragma unroll
+          for (int q = 0; q < TB; q++) t[u][q] = fma(w[u] - 1.0, cm[(size_t)bq[q] * d], w[u] * (da * (m[bq[q]] - mub[q])));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (w[u] > 0.0) {
+#pragma unroll
+          for (int q = 0; q < TB; q++) acc[q] += t[u][q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < TB; q++)
+      if (b0 + q < d) partial[(size_t)slice * nv + (size_t)(b0 + q) * d + a] = acc[q];
   }
 }
 

@@ -80,6 +80,7 @@ struct mcmcb_handle_s {
   long long r_stride = 0, q_stride = 0;
   bool r_resident = false;
   bool k4 = false;  // the thread-per-chain RAM kernel (k4_ram.cuh) ran the last launch
+  int k5s_lanes = 0;  // lanes per chain of the last launch when it was k5s_scam_step_kernel, else 0
   int k2_warps = 8;
   int k2_group_threads = 0;  // > 0: the group-of-warps-per-chain kernel (k2g_group.cuh) runs, this many threads per chain
   long long k2_i = 1;  // simuind shared by all chains of the handle

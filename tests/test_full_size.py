@@ -93,7 +93,7 @@ def test_c5_full_population_pooled_scam():
     par0[[0, 1000, N - 1]] = sub
     s.set_initial(par0, W.cmat0, W.sigma2, W.nobs)
     s.run(a - 1)          # sweeps before the first pooled tick: the reference's own SCAM chains
-    assert s.info()["lanes_per_chain"] == 1
+    assert s.info()["lanes_per_chain"] == 4 and s.info()["smem_bytes"] > 200 * 1024   # theta in shared memory, k5s_scam.cuh
     cnt = s.counters()
     invariants(cnt, a - 1, dr=False)
     for c in (0, 1000, N - 1):

@@ -418,9 +418,9 @@ def test_thread_per_chain_ram_kernel_matches_the_oracle(case, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ thread-per-chain SCAM
-@pytest.mark.parametrize("k5s", ["1", "0"])
+@pytest.mark.parametrize("lanes", [4, 2, 1, 0])
 @pytest.mark.parametrize("G,J,N,steps", [(6, 4, 64, 59), (198, 10, 8, 3), (13, 3, 150, 21)])
-def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, k5s, monkeypatch):
+def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, lanes, monkeypatch):
     """k5_scam_step_kernel (one thread per chain, shared rotation, proposal never materialised: HierN::ssfunction_axpy)
     is what large pooled SCAM populations run on (BASELINE C5); forced here on a small population.  Up to the first
     pooled tick every chain is the reference's own SCAM chain: exact counters against the oracle."""
@@ -432,14 +432,16 @@ def test_thread_per_chain_scam_kernel_matches_the_oracle(G, J, N, steps, k5s, mo
     par0 = 0.1 + 0.05 * rng.normal(size=(N, d))
     cmat0 = np.diag(0.02 * (1.0 + np.arange(d) / d))
     monkeypatch.setenv("MCMCB_K5", "1")
-    monkeypatch.setenv("MCMCB_K5S", k5s)   # theta in shared memory (k5s_scam.cuh) / in local memory (k5_scam.cuh)
+    # theta in shared memory, 4 / 2 / 1 lanes per chain (k5s_scam.cuh); 0: theta in local memory (k5_scam.cuh)
+    monkeypatch.setenv("MCMCB_K5S", "1" if lanes else "0")
+    monkeypatch.setenv("MCMCB_K5S_LANES", str(max(lanes, 1)))
     s = mb.Sampler(mb.default_config(nchains=N, seed=23, model="hier", pool_adapt=1, store_chains=2, **nml))
     s.set_data(blob)
     s.set_initial(par0, cmat0, [1.0], [G * J])
     s.run(steps // 2)
     s.run(steps - steps // 2)
-    assert s.info()["lanes_per_chain"] == 1
-    assert (s.info()["smem_bytes"] > 8 * d * 64) == (k5s == "1")
+    assert s.info()["lanes_per_chain"] == max(lanes, 1)
+    assert (s.info()["smem_bytes"] > 8 * d * 64) == (lanes > 0)
     cnt, par, ss, s2 = s.counters(), s.fetch("par"), s.fetch("ss"), s.fetch("sigma2")
     assert (cnt["status"] == 0).all()
     for c in (0, 1, N - 1):
@@ -475,7 +477,7 @@ def test_thread_per_chain_scam_kernel_across_pooled_ticks(monkeypatch):
         s.set_data(blob)
         s.set_initial(par0, 0.1 * np.eye(d), [1.0], [1])
         s.run(150)
-        assert s.info()["lanes_per_chain"] == (1 if k5 == "1" else 32)
+        assert s.info()["lanes_per_chain"] == (4 if k5 == "1" else 32)   # 4 lanes per chain: k5s_scam.cuh
         out[k5] = dict(cnt=s.counters(), par=s.fetch("par"), pool=s.pool_fetch(), q=s.fetch("qcovstd"))
         assert (out[k5]["cnt"]["status"] == 0).all()
         s.close()
@@ -535,12 +537,14 @@ def test_resident_tick_is_bit_identical_to_the_streamed_tick(d, method, initcmat
 
 
 # ------------------------------------------------------------------------------------------------ theta in shared memory
-@pytest.mark.parametrize("ilp", ["8", "4"])
-def test_scam_kernel_with_theta_in_shared_memory_is_bit_identical(ilp, monkeypatch):
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_scam_kernel_with_theta_in_shared_memory(lanes, monkeypatch):
     """k5s_scam_step_kernel against k5_scam_step_kernel: the same draws and, element by element, the same fma sequence
-    (theta + delta U(:,j) composed on the fly, rewritten on acceptance) -- chains, sums of squares, counters, logged rows
-    (through the pooled covariance of two ticks) and the stored chain agree to the last bit.  150 chains: the last CTA
-    has shadow threads; 198 groups with 8 in flight: the ragged last block of the model's view."""
+    (theta + delta U(:,j) composed on the fly, rewritten on acceptance).  With one lane per chain the model's sum runs in
+    the same order: chains, sums of squares, counters, logged rows (through the pooled covariance of three ticks) and
+    the stored chain agree to the last bit.  With 2 or 4 lanes the sum of squares is the sum of the lanes' partial sums
+    (rounding-level differences, as in the warp-per-chain kernel): same walks, values to 1e-9.  150 chains: the last
+    CTA has shadow slots; 198 groups: ragged last blocks of the model's view."""
     G, J, N = 198, 3, 150
     rng = np.random.default_rng(31)
     y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
@@ -549,7 +553,7 @@ def test_scam_kernel_with_theta_in_shared_memory_is_bit_identical(ilp, monkeypat
     nml = dict(method="scam", nsimu=14, adaptint=4, initcmatn=1, updatesigma=1, N0=2.0, S02=1.0)
     par0 = 0.1 * rng.normal(size=(N, d))
     monkeypatch.setenv("MCMCB_K5", "1")
-    monkeypatch.setenv("MCMCB_K5S_ILP", ilp)
+    monkeypatch.setenv("MCMCB_K5S_LANES", str(lanes))
     out = {}
     for k5s in ("1", "0"):
         monkeypatch.setenv("MCMCB_K5S", k5s)
@@ -559,17 +563,25 @@ def test_scam_kernel_with_theta_in_shared_memory_is_bit_identical(ilp, monkeypat
         s.run(6)
         s.run(7)
         out[k5s] = dict(cnt=s.counters(), par=s.fetch("par"), ss=s.fetch("ss"), s2=s.fetch("sigma2"), pool=s.pool_fetch(),
-                        chain=s.fetch_chain(2), smem=s.info()["smem_bytes"])
+                        chain=s.fetch_chain(2), smem=s.info()["smem_bytes"], lanes=s.info()["lanes_per_chain"])
         assert (out[k5s]["cnt"]["status"] == 0).all()
         s.close()
     a, b = out["1"], out["0"]
-    assert a["smem"] > 8 * d * 64 > b["smem"]
-    for k in CNT:
-        assert np.array_equal(a["cnt"][k], b["cnt"][k]), k
-    for k in ("par", "ss", "s2"):
-        assert np.array_equal(a[k], b[k]), k
-    for x, y_ in zip(a["pool"], b["pool"]):
-        assert np.array_equal(np.asarray(x), np.asarray(y_))
-    for k in ("chain", "sschain", "s2chain"):
-        if k in a["chain"]:
+    assert a["smem"] > 8 * d * 64 > b["smem"] and a["lanes"] == lanes and b["lanes"] == 1
+    if lanes == 1:
+        for k in CNT:
+            assert np.array_equal(a["cnt"][k], b["cnt"][k]), k
+        for k in ("par", "ss", "s2"):
+            assert np.array_equal(a[k], b[k]), k
+        for x, y_ in zip(a["pool"], b["pool"]):
+            assert np.array_equal(np.asarray(x), np.asarray(y_))
+        for k in ("chain", "sschain", "s2chain"):
             assert np.array_equal(a["chain"][k], b["chain"][k]), k
+    else:
+        same = [c for c in range(N) if all(a["cnt"][k][c] == b["cnt"][k][c] for k in CNT)]
+        assert len(same) >= N - 3, len(same)
+        np.testing.assert_allclose(a["par"][same], b["par"][same], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(a["ss"][same], b["ss"][same], rtol=1e-11)
+        assert a["pool"][0] == b["pool"][0]
+        if len(same) == N:
+            np.testing.assert_allclose(a["pool"][2], b["pool"][2], rtol=1e-7, atol=1e-10)
