@@ -34,6 +34,10 @@
  *       operator[]): the thread-per-chain SCAM kernel hands in theta + delta*U(:,j) composed on the fly, so a
  *       single-component move (MCMC_run_scam.F90:94-117) never materialises its proposal; needs
  *       `static constexpr bool MCMCB_VIEW_DEFAULTS = true` (checkbounds always true, priorfun = the default prior).
+ *       The lanes ctx.lane of ctx.nlanes that share the chain each return a partial sum; the kernel adds them.
+ *   template<int C, class V> ssfunction_view_batch(const V theta[C],npar,ny,ctx,double ss[C*ny])  the same for C
+ *       chains of one thread in ONE sweep over the data: a datum read from shared memory is used C times (the SCAM
+ *       kernel with theta in shared memory is bound by shared-memory wavefronts, not by FP64, without it).
  */
 #ifndef MCMCB200_MODEL_CUH
 #define MCMCB200_MODEL_CUH

@@ -27,19 +27,31 @@ namespace mcmcb {
 
 constexpr int K5S_CHAINS = 128;  // chains per CTA (fewer when npar is larger than ~200: k5s_chains)
 
-// Element k of the chain in slot s of the CTA's theta block.  Rows are NC slots long (NC a multiple of 16); odd rows
-// swap the two halves of every 16 slots, so the L lanes of a chain -- which read L consecutive rows at the same time --
-// spread over all banks (L = 4: the optimum of two wavefronts per 64-bit warp access instead of four).
-__device__ __forceinline__ int k5s_at(int k, int s, int NC) { return k * NC + (s ^ ((k & 1) << 3)); }
+// Element k of the chain in slot s of the CTA's theta block.  Rows are NC slots long (NC a multiple of 16).  The L lanes
+// of a chain read L consecutive rows at the same time and a half-warp holds 16 / L neighbouring slots, so row k is
+// rotated by (k mod L) * (16 / L) slots inside every group of 16: the half-warp's 16 addresses fall into 16 different
+// 8-byte bank pairs (measured before: 2.3 wavefronts per shared load, 4 per store).
+template <int L>
+__device__ __forceinline__ int k5s_at(int k, int s, int NC) {
+  return k * NC + (s ^ ((k & (L - 1)) * (16 / L)));
+}
 
-template <int W>
+template <int W, int L>
 struct K5SView {
   static constexpr int ILP = W;
   const double* th;  // shared: the CTA's theta block
   const double* u;   // shared: the column of the CTA's current move
   double dl;
   int NC, s;
-  __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[k5s_at(k, s, NC)]); }
+  __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[k5s_at<L>(k, s, NC)]); }
+};
+
+// does the model evaluate C views in one sweep over its data (ssfunction_view_batch<C, V>)?
+template <class M, class = void>
+struct has_ssfunction_view_batch { static constexpr bool value = false; };
+template <class M>
+struct has_ssfunction_view_batch<M, decltype((void)&M::template ssfunction_view_batch<2, mcmcb_view_probe>)> {
+  static constexpr bool value = true;
 };
 
 // bytes of dynamic shared memory: blob | two column buffers (npar + 1 doubles each: U(:,j) and qcovstd(j)) | theta
@@ -70,80 +82,114 @@ __device__ __forceinline__ double k5s_default_prior_view(const V& theta, int len
   return p;
 }
 
-// W = accumulation chains the model keeps in flight, L = lanes per chain (1, 2 or 4; blockDim = L x chains per CTA)
-template <class M, int W, int L>
-__global__ void __launch_bounds__(K5S_CHAINS * L, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
+// the scalars of one chain a thread carries through the launch
+template <int NY>
+struct K5SChain {
+  double ss1[NY], s2[NY], pri1;
+  int stayed, bnd, chainind, simuind, status, cnt, pend, nbuf;
+  Rng g;
+  long long cc;
+  bool live, rejall, logged;
+};
+
+// W = accumulation chains per chain the model keeps in flight, L = lanes per chain, C = chains per thread;
+// blockDim = L x (chains per CTA) / C
+template <class M, int W, int L, int C>
+__global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
-  constexpr int NPF = (K4_DM + 64 * L - 1) / (64 * L);  // column elements a thread carries (blockDim >= 64 L)
+  constexpr int NPF = (K4_DM * C + 64 * L - 1) / (64 * L);  // column elements a thread carries (blockDim >= 64 L / C)
+  using View = K5SView<W, L>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);  // every thread of the CTA takes part (barrier inside)
   const double* data = reinterpret_cast<const double*>(smem_raw);
-  const int d = p.d, T = blockDim.x, NC = T / L, tid = threadIdx.x, s = tid / L, sub = tid % L;
+  const int d = p.d, T = blockDim.x, NT = T / L, NC = NT * C, tid = threadIdx.x, grp = tid / L, sub = tid % L;
   const int dp2 = (d + 2) & ~1;
   double* ucol = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
   double* th = ucol + 2 * (size_t)dp2;
-
-  // a slot past the last chain shadows the last chain (barriers and shuffles need every thread) and writes nothing
-  const long long c0 = (long long)blockIdx.x * NC + s;
-  const bool live = c0 < p.nchains;
-  const long long cc = live ? c0 : p.nchains - 1;
-  const bool lead = live && sub == 0;  // the lane that writes the chain's scalars
   const DevCfg& c = p.c;
   const size_t P = (size_t)p.pitch;
-  double* st = p.st + cc;
-  int* ist = p.ist + cc;
   const double* U = p.Rm;    // shared rotation, column-major: column j at U + j d
   const double* gq = p.qstd; // shared qcovstd
-  double* gth = p.theta + cc * p.dp;
-  double* rb = p.rowbuf + (size_t)cc * (p.rowcap + 1) * (d + 1);
-
-  for (int k = sub; k < d; k += L) th[k5s_at(k, s, NC)] = gth[k];
-  double ss1[NY], s2[NY];
-#pragma unroll
-  for (int k = 0; k < NY; k++) { ss1[k] = st[(Lo.ss + k) * P]; s2[k] = st[(Lo.s2 + k) * P]; }
-  double pri1 = st[Lo.pri * P];
-  int stayed = ist[Lo.i_stayed * P], bnd = ist[Lo.i_bnd * P], chainind = ist[Lo.i_chainind * P];
-  int simuind = ist[Lo.i_simuind * P], status = ist[Lo.i_status * P], cnt = ist[Lo.i_cnt * P], pend = ist[Lo.i_pend * P];
-  int nbuf = ist[Lo.i_nbuf * P];
-  Rng g;  // the chain's L lanes run the same generator: same draws, same decisions
-  g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * P] << 32) | (unsigned)ist[Lo.i_ndlo * P];
-  g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + cc);
-  g.inj = p.inj ? p.inj + (unsigned long long)cc * p.inj_per_chain : nullptr;
-  g.inj_n = p.inj_per_chain;
-  g.cache_valid = false; g.cache_lo = g.cache_hi = 0; g.cache_blk = 0;
-  g.has_spare = ist[Lo.i_hasspare * P] != 0;
-  g.spare = st[Lo.spare * P];
-  g.exhausted = 0;
-  const bool stored = live && cc < p.store_chains;
-  double* srow = p.store_rows_p + (size_t)cc * p.store_rows * (d + NY);
-  double* scnt = p.store_cnt_p + (size_t)cc * p.store_rows;
-  double* ss2st = p.store_s2_p + (size_t)cc * p.store_rows * NY;
 
   mcmcb_ctx ctx;
   ctx.data = data; ctx.ndata = p.blob_n; ctx.prior = p.prior; ctx.lane = sub; ctx.nlanes = L;
   ctx.exp_tl = 0u; ctx.exp_c1 = MCMCB_EXP_C1L; ctx.exp_c2 = MCMCB_EXP_C2L; ctx.scratch = nullptr;
 
-  K5SView<W> tv;
-  tv.th = th; tv.u = ucol + dp2; tv.dl = 0.0; tv.NC = NC; tv.s = s;
+  // chain i of this thread sits in slot i * NT + grp.  A slot past the last chain shadows the last chain (barriers and
+  // shuffles need every thread) and writes nothing.
+  K5SChain<NY> ch[C];
+  View tv[C];
+#pragma unroll
+  for (int i = 0; i < C; i++) {
+    K5SChain<NY>& q = ch[i];
+    const int s = i * NT + grp;
+    const long long c0 = (long long)blockIdx.x * NC + s;
+    q.live = c0 < p.nchains;
+    q.cc = q.live ? c0 : p.nchains - 1;
+    const double* st = p.st + q.cc;
+    const int* ist = p.ist + q.cc;
+    const double* gth = p.theta + q.cc * p.dp;
+    for (int k = sub; k < d; k += L) th[k5s_at<L>(k, s, NC)] = gth[k];
+#pragma unroll
+    for (int k = 0; k < NY; k++) { q.ss1[k] = st[(Lo.ss + k) * P]; q.s2[k] = st[(Lo.s2 + k) * P]; }
+    q.pri1 = st[Lo.pri * P];
+    q.stayed = ist[Lo.i_stayed * P]; q.bnd = ist[Lo.i_bnd * P]; q.chainind = ist[Lo.i_chainind * P];
+    q.simuind = ist[Lo.i_simuind * P]; q.status = ist[Lo.i_status * P]; q.cnt = ist[Lo.i_cnt * P];
+    q.pend = ist[Lo.i_pend * P]; q.nbuf = ist[Lo.i_nbuf * P];
+    Rng& g = q.g;  // the chain's L lanes run the same generator: same draws, same decisions
+    g.nd = ((unsigned long long)(unsigned)ist[Lo.i_ndhi * P] << 32) | (unsigned)ist[Lo.i_ndlo * P];
+    g.seed = p.seed; g.chain = (unsigned long long)(p.chain_offset + q.cc);
+    g.inj = p.inj ? p.inj + (unsigned long long)q.cc * p.inj_per_chain : nullptr;
+    g.inj_n = p.inj_per_chain;
+    g.cache_valid = false; g.cache_lo = g.cache_hi = 0; g.cache_blk = 0;
+    g.has_spare = ist[Lo.i_hasspare * P] != 0;
+    g.spare = st[Lo.spare * P];
+    g.exhausted = 0;
+    tv[i].th = th; tv[i].u = ucol + dp2; tv[i].dl = 0.0; tv[i].NC = NC; tv[i].s = s;
+  }
+
+  // C views -> C sums of squares (summed over the chain's lanes) and C priors
+  auto evaluate = [&](double (&ssn)[C][NY], double (&prn)[C]) {
+#pragma unroll
+    for (int i = 0; i < C; i++) prn[i] = k5s_lanes_sum<L>(k5s_default_prior_view(tv[i], d, ctx));
+    if constexpr (C > 1 && has_ssfunction_view_batch<M>::value) {
+      M::template ssfunction_view_batch<C>(tv, d, NY, ctx, &ssn[0][0]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < C; i++) M::ssfunction_view(tv[i], d, NY, ctx, ssn[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < C; i++)
+#pragma unroll
+      for (int k = 0; k < NY; k++) ssn[i][k] = k5s_lanes_sum<L>(ssn[i][k]);
+  };
 
   // buffer 0 <- column 0 and its scale; buffer 1 <- zeros (the current point as a view: a zero move along a zero column)
   for (int k = tid; k < d; k += T) { ucol[k] = U[k]; ucol[dp2 + k] = 0.0; }
   if (tid == 0) ucol[d] = gq[0];
   __syncthreads();
-  if (simuind == 0) {  // MCMC_run_scam.F90:26-36: initial point, saved as row 1
-    double ssn[NY];
-    M::ssfunction_view(tv, d, NY, ctx, ssn);
+  if (ch[0].simuind == 0) {  // MCMC_run_scam.F90:26-36: initial point, saved as row 1 (every chain of a launch starts together)
+    double ssn[C][NY], prn[C];
+    evaluate(ssn, prn);
 #pragma unroll
-    for (int k = 0; k < NY; k++) ss1[k] = k5s_lanes_sum<L>(ssn[k]);
-    pri1 = k5s_lanes_sum<L>(k5s_default_prior_view(tv, d, ctx));
-    chainind = 1; simuind = 1; cnt = 1; pend = 1;
-    if (stored) {
-      for (int k = sub; k < d; k += L) srow[k] = th[k5s_at(k, s, NC)];
-      if (sub == 0) {
+    for (int i = 0; i < C; i++) {
+      K5SChain<NY>& q = ch[i];
 #pragma unroll
-        for (int k = 0; k < NY; k++) { srow[d + k] = ss1[k]; if (c.updatesigma) ss2st[k] = s2[k]; }
+      for (int k = 0; k < NY; k++) q.ss1[k] = ssn[i][k];
+      q.pri1 = prn[i];
+      q.chainind = 1; q.simuind = 1; q.cnt = 1; q.pend = 1;
+      if (q.live && q.cc < p.store_chains) {
+        double* srow = p.store_rows_p + (size_t)q.cc * p.store_rows * (d + NY);
+        for (int k = sub; k < d; k += L) srow[k] = th[k5s_at<L>(k, tv[i].s, NC)];
+        if (sub == 0) {
+#pragma unroll
+          for (int k = 0; k < NY; k++) {
+            srow[d + k] = q.ss1[k];
+            if (c.updatesigma) p.store_s2_p[(size_t)q.cc * p.store_rows * NY + k] = q.s2[k];
+          }
+        }
       }
     }
   }
@@ -151,8 +197,8 @@ __global__ void __launch_bounds__(K5S_CHAINS * L, 1) k5s_scam_step_kernel(const 
 
   int jb = 0;
   for (int done = 0; done < p.nsteps; done++) {
-    bool rejall = true;
-    bool logged = false;  // the row that is about to be replaced has been written to the row buffer
+#pragma unroll
+    for (int i = 0; i < C; i++) { ch[i].rejall = true; ch[i].logged = false; }
     for (int j = 0; j < d; j++) {
       const double* uc = ucol + (size_t)jb * dp2;
       // ---- the next move's column and scale start their trip from L2 now and are published after this move
@@ -165,38 +211,45 @@ __global__ void __launch_bounds__(K5S_CHAINS * L, 1) k5s_scam_step_kernel(const 
         if (tid == 0) qn = gq[jn];
       }
       // MCMC_propose_sc (MCMC_run_scam.F90:94-117) in the O(d) form theta + delta U(:,j)
-      const double delta = g.normal() * uc[d];
-      tv.u = uc; tv.dl = delta;
-      double ssn[NY];
-      const double prn = k5s_lanes_sum<L>(k5s_default_prior_view(tv, d, ctx));
-      M::ssfunction_view(tv, d, NY, ctx, ssn);
-      double sum = 0.0;
+      const double qj = uc[d];
 #pragma unroll
-      for (int k = 0; k < NY; k++) { ssn[k] = k5s_lanes_sum<L>(ssn[k]); sum += (ssn[k] - ss1[k]) / s2[k]; }
-      const bool reject = mh_reject(alpha_from_tst(-0.5 * (sum + (prn - pri1))), g);
-      if (!reject) {  // MCMC_run_scam.F90:63-68
-        if (!logged) {
-          // first acceptance of this sweep: the current row is complete -- log it for the adaptation
-          // kernel before theta changes (the reference reads it back from the stored chain)
-          const bool absorbing = c.doadapt && !(c.adaptend > 0 && simuind + 1 > c.adaptend);
-          if (absorbing) {
-            if (nbuf < p.rowcap) {
-              if (live) {
-                for (int k = sub; k < d; k += L) rb[(size_t)nbuf * (d + 1) + k] = th[k5s_at(k, s, NC)];
-                if (sub == 0) rb[(size_t)nbuf * (d + 1) + d] = (double)((c.doadapt && c.adapthist > 1) ? cnt : pend);
+      for (int i = 0; i < C; i++) { tv[i].u = uc; tv[i].dl = ch[i].g.normal() * qj; }
+      double ssn[C][NY], prn[C];
+      evaluate(ssn, prn);
+#pragma unroll
+      for (int i = 0; i < C; i++) {
+        K5SChain<NY>& q = ch[i];
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NY; k++) sum += (ssn[i][k] - q.ss1[k]) / q.s2[k];
+        const bool reject = mh_reject(alpha_from_tst(-0.5 * (sum + (prn[i] - q.pri1))), q.g);
+        if (!reject) {  // MCMC_run_scam.F90:63-68
+          const int s = tv[i].s;
+          if (!q.logged) {
+            // first acceptance of this sweep: the current row is complete -- log it for the adaptation
+            // kernel before theta changes (the reference reads it back from the stored chain)
+            const bool absorbing = c.doadapt && !(c.adaptend > 0 && q.simuind + 1 > c.adaptend);
+            if (absorbing) {
+              if (q.nbuf < p.rowcap) {
+                if (q.live) {
+                  double* rb = p.rowbuf + ((size_t)q.cc * (p.rowcap + 1) + q.nbuf) * (d + 1);
+                  for (int k = sub; k < d; k += L) rb[k] = th[k5s_at<L>(k, s, NC)];
+                  if (sub == 0) rb[d] = (double)((c.doadapt && c.adapthist > 1) ? q.cnt : q.pend);
+                }
+                q.nbuf++;
+              } else {
+                q.status |= MCMCB_ST_STORE_FULL;
               }
-              nbuf++;
-            } else {
-              status |= MCMCB_ST_STORE_FULL;
             }
+            q.logged = true;
           }
-          logged = true;
-        }
-        for (int k = sub; k < d; k += L) { const int e = k5s_at(k, s, NC); th[e] = fma(uc[k], delta, th[e]); }
+          const double delta = tv[i].dl;
+          for (int k = sub; k < d; k += L) { const int e = k5s_at<L>(k, s, NC); th[e] = fma(uc[k], delta, th[e]); }
 #pragma unroll
-        for (int k = 0; k < NY; k++) ss1[k] = ssn[k];
-        pri1 = prn;
-        rejall = false;
+          for (int k = 0; k < NY; k++) q.ss1[k] = ssn[i][k];
+          q.pri1 = prn[i];
+          q.rejall = false;
+        }
       }
       // ---- publish the next column (its buffer was last read during the previous move) and meet: theta elements
       // written by one lane of a chain are read by the others in the next move
@@ -210,56 +263,71 @@ __global__ void __launch_bounds__(K5S_CHAINS * L, 1) k5s_scam_step_kernel(const 
       jb ^= 1;
     }
     // ---------------- end of sweep, MCMC_run_scam.F90:74-86
-    const int i = simuind + 1;
-    simuind = i;
-    if (rejall) {
-      stayed++;
-      cnt++; pend++;
-    } else {
-      if (stored && sub == 0 && chainind - 1 < p.store_rows) scnt[chainind - 1] = (double)cnt;
-      chainind++;
-      cnt = 1; pend = 1;
-    }
-    if (c.updatesigma) {
 #pragma unroll
-      for (int k = 0; k < NY; k++) {
-        const double gg = g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + ss1[k]));
-        s2[k] = 1.0 / gg;
+    for (int i = 0; i < C; i++) {
+      K5SChain<NY>& q = ch[i];
+      const bool stored = q.live && q.cc < p.store_chains;
+      double* srow = p.store_rows_p + (size_t)q.cc * p.store_rows * (d + NY);
+      double* scnt = p.store_cnt_p + (size_t)q.cc * p.store_rows;
+      double* ss2st = p.store_s2_p + (size_t)q.cc * p.store_rows * NY;
+      const int it = q.simuind + 1;
+      q.simuind = it;
+      if (q.rejall) {
+        q.stayed++;
+        q.cnt++; q.pend++;
+      } else {
+        if (stored && sub == 0 && q.chainind - 1 < p.store_rows) scnt[q.chainind - 1] = (double)q.cnt;
+        q.chainind++;
+        q.cnt = 1; q.pend = 1;
       }
-    }
-    if (stored) {
-      if (!rejall) {
-        if (chainind - 1 < p.store_rows) {
-          for (int k = sub; k < d; k += L) srow[(size_t)(chainind - 1) * (d + NY) + k] = th[k5s_at(k, s, NC)];
-          if (sub == 0) {
+      if (c.updatesigma) {
 #pragma unroll
-            for (int k = 0; k < NY; k++) srow[(size_t)(chainind - 1) * (d + NY) + d + k] = ss1[k];
-          }
-        } else {
-          status |= MCMCB_ST_STORE_FULL;
+        for (int k = 0; k < NY; k++) {
+          const double gg = q.g.gamma(c.N0 / 2.0 + (double)p.nobs[k] / 2.0, 2.0 / (c.N0 * c.S02 + q.ss1[k]));
+          q.s2[k] = 1.0 / gg;
         }
       }
-      if (c.updatesigma && sub == 0 && i - 1 < p.store_rows) {
+      if (stored) {
+        if (!q.rejall) {
+          if (q.chainind - 1 < p.store_rows) {
+            for (int k = sub; k < d; k += L) srow[(size_t)(q.chainind - 1) * (d + NY) + k] = th[k5s_at<L>(k, tv[i].s, NC)];
+            if (sub == 0) {
 #pragma unroll
-        for (int k = 0; k < NY; k++) ss2st[(size_t)(i - 1) * NY + k] = s2[k];
+              for (int k = 0; k < NY; k++) srow[(size_t)(q.chainind - 1) * (d + NY) + d + k] = q.ss1[k];
+            }
+          } else {
+            q.status |= MCMCB_ST_STORE_FULL;
+          }
+        }
+        if (c.updatesigma && sub == 0 && it - 1 < p.store_rows) {
+#pragma unroll
+          for (int k = 0; k < NY; k++) ss2st[(size_t)(it - 1) * NY + k] = q.s2[k];
+        }
       }
+      if (q.g.exhausted) q.status |= MCMCB_ST_RNG_EXHAUSTED;
     }
-    if (g.exhausted) status |= MCMCB_ST_RNG_EXHAUSTED;
   }
 
-  if (!live) return;
   // ---- write state back
-  for (int k = sub; k < d; k += L) gth[k] = th[k5s_at(k, s, NC)];
-  if (!lead) return;
 #pragma unroll
-  for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * P] = ss1[k]; st[(Lo.s2 + k) * P] = s2[k]; }
-  st[Lo.pri * P] = pri1; st[Lo.spare * P] = g.spare;
-  ist[Lo.i_stayed * P] = stayed; ist[Lo.i_bnd * P] = bnd;
-  ist[Lo.i_chainind * P] = chainind; ist[Lo.i_simuind * P] = simuind; ist[Lo.i_status * P] = status;
-  ist[Lo.i_hasspare * P] = g.has_spare ? 1 : 0;
-  ist[Lo.i_cnt * P] = cnt; ist[Lo.i_pend * P] = pend; ist[Lo.i_nbuf * P] = nbuf;
-  ist[Lo.i_ndlo * P] = (int)(unsigned)(g.nd & 0xffffffffull);
-  ist[Lo.i_ndhi * P] = (int)(unsigned)(g.nd >> 32);
+  for (int i = 0; i < C; i++) {
+    K5SChain<NY>& q = ch[i];
+    if (!q.live) continue;
+    double* gth = p.theta + q.cc * p.dp;
+    for (int k = sub; k < d; k += L) gth[k] = th[k5s_at<L>(k, tv[i].s, NC)];
+    if (sub != 0) continue;
+    double* st = p.st + q.cc;
+    int* ist = p.ist + q.cc;
+#pragma unroll
+    for (int k = 0; k < NY; k++) { st[(Lo.ss + k) * P] = q.ss1[k]; st[(Lo.s2 + k) * P] = q.s2[k]; }
+    st[Lo.pri * P] = q.pri1; st[Lo.spare * P] = q.g.spare;
+    ist[Lo.i_stayed * P] = q.stayed; ist[Lo.i_bnd * P] = q.bnd;
+    ist[Lo.i_chainind * P] = q.chainind; ist[Lo.i_simuind * P] = q.simuind; ist[Lo.i_status * P] = q.status;
+    ist[Lo.i_hasspare * P] = q.g.has_spare ? 1 : 0;
+    ist[Lo.i_cnt * P] = q.cnt; ist[Lo.i_pend * P] = q.pend; ist[Lo.i_nbuf * P] = q.nbuf;
+    ist[Lo.i_ndlo * P] = (int)(unsigned)(q.g.nd & 0xffffffffull);
+    ist[Lo.i_ndhi * P] = (int)(unsigned)(q.g.nd >> 32);
+  }
 }
 
 }  // namespace mcmcb

@@ -757,18 +757,18 @@ struct K2 {
     }
   }
 
-  template <int W, int L>
+  template <int W, int L, int C>
   static int launch_k5s_as(mcmcb_handle h, const K2Params& p, int chains) {
     if constexpr (has_ssfunction_view<M>::value) {
-      auto kern = k5s_scam_step_kernel<M, W, L>;
+      auto kern = k5s_scam_step_kernel<M, W, L, C>;
       const size_t smem = k5s_smem_bytes(h->npar, chains, h->blob_bytes);
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const unsigned blocks = (unsigned)((h->cfg.nchains + chains - 1) / chains);
-      kern<<<blocks, chains * L, smem, h->stream>>>(p);
+      kern<<<blocks, chains * L / C, smem, h->stream>>>(p);
       h->launches++;
       h->blocks = (int)blocks;
       h->smem = smem;
-      h->k2_warps = chains * L / 32;
+      h->k2_warps = chains * L / C / 32;
       h->k5s_lanes = L;
       h->k4 = L == 1;  // one thread per chain (mcmcb_info)
       CK(cudaGetLastError());
@@ -776,12 +776,16 @@ struct K2 {
     return 0;
   }
 
+  // lanes per chain x chains per thread: 4 x 2 by default (profiles/r02_summary.md); the others for tuning / tests
   static int launch_k5s(mcmcb_handle h, const K2Params& p, int chains) {
-    int lanes = 4;
-    if (const char* e = getenv("MCMCB_K5S_LANES")) lanes = atoi(e);  // tuning / tests
-    if (lanes == 1) return launch_k5s_as<8, 1>(h, p, chains);
-    if (lanes == 2) return launch_k5s_as<4, 2>(h, p, chains);
-    return launch_k5s_as<4, 4>(h, p, chains);
+    int lanes = 4, cpt = 2;
+    if (const char* e = getenv("MCMCB_K5S_LANES")) lanes = atoi(e);
+    if (const char* e = getenv("MCMCB_K5S_CPT")) cpt = atoi(e);
+    if (lanes == 1) return launch_k5s_as<8, 1, 1>(h, p, chains);
+    if (lanes == 2) return launch_k5s_as<4, 2, 1>(h, p, chains);
+    if (lanes == 8) return cpt == 4 ? launch_k5s_as<2, 8, 4>(h, p, chains) : launch_k5s_as<4, 8, 2>(h, p, chains);
+    if (cpt == 1) return launch_k5s_as<4, 4, 1>(h, p, chains);
+    return launch_k5s_as<4, 4, 2>(h, p, chains);
   }
 
   static bool is_tick(const mcmcb_config& c, long long i) {

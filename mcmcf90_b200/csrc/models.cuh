@@ -359,54 +359,65 @@ struct HierN {
     if (c.lane == 0) acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
     ss[0] = acc;
   }
-  // The same sum over a VIEW of the parameter vector (anything with operator[]): the thread-per-chain SCAM kernel
-  // (k5_scam.cuh) hands in theta + delta U(:,j) -- and a few accepted moves it has not written back yet -- composed on the
-  // fly, so a single-component move (MCMC_propose_sc, MCMC_run_scam.F90:94-117) never materialises its proposal.  One
-  // lane owns the chain; the same operations in the same order as ssfunction on the materialised vector.  W groups'
-  // sums of squares run as independent chains (W = mcmcb_view_ilp<V>); they join the total in group order.
+  // The same sum over a VIEW of the parameter vector (anything with operator[]): the thread-per-chain SCAM kernels
+  // (k5_scam.cuh, k5s_scam.cuh) hand in theta + delta U(:,j) composed on the fly, so a single-component move
+  // (MCMC_propose_sc, MCMC_run_scam.F90:94-117) never materialises its proposal.  The chain's lanes take the groups
+  // round-robin (lane, lane + nlanes, ...) and return partial sums; one lane = every group, in ssfunction's order.  W
+  // groups' sums of squares run as independent accumulation chains (W = mcmcb_view_ilp<V>) and join the total in group
+  // order; the batched form does that for C chains of one thread at once, every datum read once for all of them.
   static constexpr bool MCMCB_VIEW_DEFAULTS = true;  // checkbounds is always true, priorfun is the default prior
-  template <class V>
-  __device__ __forceinline__ static void ssfunction_view(const V& theta, int, int, const mcmcb_ctx& c, double* ss) {
+
+  // WB groups g0, g0 + nl, ... of C chains
+  template <int C, int WB, class V>
+  __device__ __forceinline__ static void view_block(const V* theta, const double* __restrict__ y, int G, int J, int g0, int nl,
+                                                    const double* mu, const double* itau2, double* acc) {
+    double tg[C][WB], a[C][WB];
+#pragma unroll
+    for (int c = 0; c < C; c++)
+#pragma unroll
+      for (int q = 0; q < WB; q++) { tg[c][q] = theta[c][g0 + nl * q]; a[c][q] = 0.0; }
+    for (int j = 0; j < J; j++) {
+      const double* yj = y + (size_t)j * G + g0;
+#pragma unroll
+      for (int q = 0; q < WB; q++) {
+        const double yv = yj[nl * q];
+#pragma unroll
+        for (int c = 0; c < C; c++) { const double r = yv - tg[c][q]; a[c][q] = fma(r, r, a[c][q]); }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++)
+#pragma unroll
+      for (int q = 0; q < WB; q++) { const double dm = tg[c][q] - mu[c]; acc[c] += a[c][q] + dm * dm * itau2[c]; }
+  }
+
+  template <int C, class V>
+  __device__ __forceinline__ static void ssfunction_view_batch(const V* theta, int, int, const mcmcb_ctx& c, double* ss) {
     const int G = (int)c.data[0], J = (int)c.data[1];
     const double* __restrict__ y = c.data + 2;
-    const double mu = theta[G], ltau = theta[G + 1];
-    const double itau2 = exp(-2.0 * ltau);
-    constexpr int W = mcmcb_view_ilp<V>::value;  // groups in flight (4 unless the view asks otherwise)
-    // the chain's lanes take the groups round-robin (lane, lane + nlanes, ...): one lane = every group, in order
+    constexpr int W = mcmcb_view_ilp<V>::value;  // groups in flight per chain (4 unless the view asks otherwise)
+    static_assert(W == 1 || W == 2 || W == 4 || W == 8, "groups in flight: a power of two up to 8");
+    double mu[C], ltau[C], itau2[C], acc[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) { mu[k] = theta[k][G]; ltau[k] = theta[k][G + 1]; itau2[k] = exp(-2.0 * ltau[k]); acc[k] = 0.0; }
     const int lane = c.lane, nl = c.nlanes;
     const int mine = (G - lane + nl - 1) / nl;  // groups of this lane
-    double acc = 0.0;
     int i = 0;
-    for (; i + W <= mine; i += W) {
-      const int g = lane + nl * i;
-      double tg[W], a[W];
+    for (; i + W <= mine; i += W) view_block<C, W>(theta, y, G, J, lane + nl * i, nl, mu, itau2, acc);
+    // the ragged rest in blocks of W/2, W/4, ...: no group is evaluated twice, the join order stays the group order
+    if constexpr (W >= 8) { if (mine - i >= 4) { view_block<C, 4>(theta, y, G, J, lane + nl * i, nl, mu, itau2, acc); i += 4; } }
+    if constexpr (W >= 4) { if (mine - i >= 2) { view_block<C, 2>(theta, y, G, J, lane + nl * i, nl, mu, itau2, acc); i += 2; } }
+    if constexpr (W >= 2) { if (mine - i >= 1) { view_block<C, 1>(theta, y, G, J, lane + nl * i, nl, mu, itau2, acc); i += 1; } }
 #pragma unroll
-      for (int q = 0; q < W; q++) { tg[q] = theta[g + nl * q]; a[q] = 0.0; }
-      for (int j = 0; j < J; j++) {
-        const double* yj = y + (size_t)j * G + g;
-#pragma unroll
-        for (int q = 0; q < W; q++) { const double r = yj[nl * q] - tg[q]; a[q] = fma(r, r, a[q]); }
-      }
-#pragma unroll
-      for (int q = 0; q < W; q++) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
+    for (int k = 0; k < C; k++) {
+      if (lane == 0) acc[k] += 2.0 * G * ltau[k] + mu[k] * mu[k] / 100.0 + ltau[k] * ltau[k] / 4.0;
+      ss[k] = acc[k];  // NY = 1
     }
-    if (i < mine) {  // the ragged last block: the same W chains, groups past the end clamped and left out of the total
-      double tg[W], a[W];
-      int gi[W];
-#pragma unroll
-      for (int q = 0; q < W; q++) { gi[q] = lane + nl * (i + q < mine ? i + q : mine - 1); tg[q] = theta[gi[q]]; a[q] = 0.0; }
-      for (int j = 0; j < J; j++) {
-        const double* yj = y + (size_t)j * G;
-#pragma unroll
-        for (int q = 0; q < W; q++) { const double r = yj[gi[q]] - tg[q]; a[q] = fma(r, r, a[q]); }
-      }
-#pragma unroll
-      for (int q = 0; q < W; q++)
-        if (i + q < mine) { const double dm = tg[q] - mu; acc += a[q] + dm * dm * itau2; }
-    }
-    if (lane == 0)
-      acc += 2.0 * G * ltau + mu * mu / 100.0 + ltau * ltau / 4.0;
-    ss[0] = acc;
+  }
+
+  template <class V>
+  __device__ __forceinline__ static void ssfunction_view(const V& theta, int len, int ny, const mcmcb_ctx& c, double* ss) {
+    ssfunction_view_batch<1>(&theta, len, ny, c, ss);
   }
 };
 

@@ -537,14 +537,15 @@ def test_resident_tick_is_bit_identical_to_the_streamed_tick(d, method, initcmat
 
 
 # ------------------------------------------------------------------------------------------------ theta in shared memory
-@pytest.mark.parametrize("lanes", [1, 2, 4])
-def test_scam_kernel_with_theta_in_shared_memory(lanes, monkeypatch):
+@pytest.mark.parametrize("lanes,cpt", [(1, 1), (2, 1), (4, 1), (4, 2), (8, 2), (8, 4)])
+def test_scam_kernel_with_theta_in_shared_memory(lanes, cpt, monkeypatch):
     """k5s_scam_step_kernel against k5_scam_step_kernel: the same draws and, element by element, the same fma sequence
     (theta + delta U(:,j) composed on the fly, rewritten on acceptance).  With one lane per chain the model's sum runs in
     the same order: chains, sums of squares, counters, logged rows (through the pooled covariance of three ticks) and
     the stored chain agree to the last bit.  With 2 or 4 lanes the sum of squares is the sum of the lanes' partial sums
     (rounding-level differences, as in the warp-per-chain kernel): same walks, values to 1e-9.  150 chains: the last
-    CTA has shadow slots; 198 groups: ragged last blocks of the model's view."""
+    CTA has shadow slots; 198 groups: ragged last blocks of the model's view.  cpt = chains per thread (the model's
+    batched view: one sweep over the data for all of them) does not change a single bit."""
     G, J, N = 198, 3, 150
     rng = np.random.default_rng(31)
     y = rng.normal(size=(G, 1)) + rng.normal(size=(G, J))
@@ -555,8 +556,11 @@ def test_scam_kernel_with_theta_in_shared_memory(lanes, monkeypatch):
     monkeypatch.setenv("MCMCB_K5", "1")
     monkeypatch.setenv("MCMCB_K5S_LANES", str(lanes))
     out = {}
-    for k5s in ("1", "0"):
-        monkeypatch.setenv("MCMCB_K5S", k5s)
+    for k5s in ("1", "0", "1x"):
+        if k5s == "1x" and cpt == 1:
+            continue
+        monkeypatch.setenv("MCMCB_K5S", k5s[0])
+        monkeypatch.setenv("MCMCB_K5S_CPT", "1" if k5s == "1x" else str(cpt))
         s = mb.Sampler(mb.default_config(nchains=N, seed=5, model="hier", pool_adapt=1, store_chains=3, **nml))
         s.set_data(blob)
         s.set_initial(par0, 0.05 * np.eye(d), [1.0], [G * J])
@@ -568,6 +572,12 @@ def test_scam_kernel_with_theta_in_shared_memory(lanes, monkeypatch):
         s.close()
     a, b = out["1"], out["0"]
     assert a["smem"] > 8 * d * 64 > b["smem"] and a["lanes"] == lanes and b["lanes"] == 1
+    if "1x" in out and lanes == 4:   # (lanes 8 has no one-chain-per-thread instantiation: MCMCB_K5S_CPT=1 is ignored there)
+        x = out["1x"]
+        for k in CNT:
+            assert np.array_equal(a["cnt"][k], x["cnt"][k]), k
+        for k in ("par", "ss", "s2"):
+            assert np.array_equal(a[k], x[k]), k
     if lanes == 1:
         for k in CNT:
             assert np.array_equal(a["cnt"][k], b["cnt"][k]), k
