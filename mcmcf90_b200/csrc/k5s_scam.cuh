@@ -40,7 +40,7 @@ template <int W, int L>
 struct K5SView {
   static constexpr int ILP = W;
   const double* th;  // shared: the CTA's theta block
-  const double* u;   // shared: the column of the CTA's current move
+  const double* u;   // global (L1): the rotation's column of the current move, the same for every chain
   double dl;
   int NC, s;
   __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[k5s_at<L>(k, s, NC)]); }
@@ -54,10 +54,9 @@ struct has_ssfunction_view_batch<M, decltype((void)&M::template ssfunction_view_
   static constexpr bool value = true;
 };
 
-// bytes of dynamic shared memory: blob | two column buffers (npar + 1 doubles each: U(:,j) and qcovstd(j)) | theta
+// bytes of dynamic shared memory: blob | theta
 __host__ __device__ __forceinline__ size_t k5s_smem_bytes(int d, int chains, size_t blob_bytes) {
-  const size_t dp2 = (size_t)(d + 2) & ~(size_t)1;
-  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * (2 * dp2 + (size_t)d * chains);
+  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * ((size_t)d * chains);
 }
 
 template <int L>
@@ -98,16 +97,14 @@ template <class M, int W, int L, int C>
 __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
-  constexpr int NPF = (K4_DM * C + 64 * L - 1) / (64 * L);  // column elements a thread carries (blockDim >= 64 L / C)
   using View = K5SView<W, L>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);  // every thread of the CTA takes part (barrier inside)
   const double* data = reinterpret_cast<const double*>(smem_raw);
   const int d = p.d, T = blockDim.x, NT = T / L, NC = NT * C, tid = threadIdx.x, grp = tid / L, sub = tid % L;
-  const int dp2 = (d + 2) & ~1;
-  double* ucol = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
-  double* th = ucol + 2 * (size_t)dp2;
+  const int lane = tid & 31;
+  double* th = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
   const DevCfg& c = p.c;
   const size_t P = (size_t)p.pitch;
   const double* U = p.Rm;    // shared rotation, column-major: column j at U + j d
@@ -147,7 +144,7 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
     g.has_spare = ist[Lo.i_hasspare * P] != 0;
     g.spare = st[Lo.spare * P];
     g.exhausted = 0;
-    tv[i].th = th; tv[i].u = ucol + dp2; tv[i].dl = 0.0; tv[i].NC = NC; tv[i].s = s;
+    tv[i].th = th; tv[i].u = U; tv[i].dl = 0.0; tv[i].NC = NC; tv[i].s = s;
   }
 
   // C views -> C sums of squares (summed over the chain's lanes) and C priors
@@ -166,10 +163,8 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
       for (int k = 0; k < NY; k++) ssn[i][k] = k5s_lanes_sum<L>(ssn[i][k]);
   };
 
-  // buffer 0 <- column 0 and its scale; buffer 1 <- zeros (the current point as a view: a zero move along a zero column)
-  for (int k = tid; k < d; k += T) { ucol[k] = U[k]; ucol[dp2 + k] = 0.0; }
-  if (tid == 0) ucol[d] = gq[0];
-  __syncthreads();
+  __syncwarp();  // the chain's lanes have written its theta (a chain never spans two warps: no CTA barrier anywhere below)
+  // the current point as a view: a zero move along column 0 (theta + 0 U = theta)
   if (ch[0].simuind == 0) {  // MCMC_run_scam.F90:26-36: initial point, saved as row 1 (every chain of a launch starts together)
     double ssn[C][NY], prn[C];
     evaluate(ssn, prn);
@@ -193,25 +188,20 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
       }
     }
   }
-  __syncthreads();  // nobody reads the zero column any more: it becomes the buffer of move 1
 
-  int jb = 0;
   for (int done = 0; done < p.nsteps; done++) {
 #pragma unroll
     for (int i = 0; i < C; i++) { ch[i].rejall = true; ch[i].logged = false; }
     for (int j = 0; j < d; j++) {
-      const double* uc = ucol + (size_t)jb * dp2;
-      // ---- the next move's column and scale start their trip from L2 now and are published after this move
-      double pf[NPF], qn = 0.0;
+      // U(:,j) comes through L1 (every warp of the CTA is within a few moves of the same j: 1.6 KB per column); the
+      // next column's lines are requested now so that no warp waits for L2 at the start of its next move
+      const double* uc = U + (size_t)j * d;
       {
-        const int jn = j + 1 < d ? j + 1 : 0;
-        const double* ncol = U + (size_t)jn * d;
-#pragma unroll
-        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; pf[i] = k < d ? ncol[k] : 0.0; }
-        if (tid == 0) qn = gq[jn];
+        const double* ncol = U + (size_t)(j + 1 < d ? j + 1 : 0) * d;
+        if (lane * 16 < d) asm volatile("prefetch.global.L1 [%0];" ::"l"(ncol + lane * 16));
       }
       // MCMC_propose_sc (MCMC_run_scam.F90:94-117) in the O(d) form theta + delta U(:,j)
-      const double qj = uc[d];
+      const double qj = gq[j];
 #pragma unroll
       for (int i = 0; i < C; i++) { tv[i].u = uc; tv[i].dl = ch[i].g.normal() * qj; }
       double ssn[C][NY], prn[C];
@@ -251,16 +241,7 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
           q.rejall = false;
         }
       }
-      // ---- publish the next column (its buffer was last read during the previous move) and meet: theta elements
-      // written by one lane of a chain are read by the others in the next move
-      {
-        double* un = ucol + (size_t)(jb ^ 1) * dp2;
-#pragma unroll
-        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; if (k < d) un[k] = pf[i]; }
-        if (tid == 0) un[d] = qn;
-      }
-      __syncthreads();
-      jb ^= 1;
+      __syncwarp();  // theta elements written by one lane of a chain are read by the others in the next move
     }
     // ---------------- end of sweep, MCMC_run_scam.F90:74-86
 #pragma unroll

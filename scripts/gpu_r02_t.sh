@@ -11,7 +11,7 @@ for l in sys.stdin:
     elif 'rror' in l: print(l.rstrip()[-300:])
 "
 }
-for v in "4 2" "8 2" "8 4" "4 1"; do
+for v in "4 2" "4 1" "8 2" "2 1"; do
   set -- $v
   MCMCB_K5S_LANES=$1 MCMCB_K5S_CPT=$2 timeout 300 python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e 2>&1 | one "c5 k5s lanes=$1 cpt=$2"
 done
