@@ -1,25 +1,33 @@
-// K5S: the thread-per-chain SCAM sweep of k5_scam.cuh with every chain's theta RESIDENT IN SHARED MEMORY.
+// K5S: the SCAM sweep of k5_scam.cuh for large populations that share one rotation, with every chain's theta RESIDENT IN
+// SHARED MEMORY, L lanes per chain and C chains per thread.
 //
-// k5_scam_step_kernel keeps theta in local memory: a component move reads the npar elements once for the model and, when
-// the move is accepted, rewrites them -- 3.2 KB per move at npar = 200 against ~4400 FP64 instructions of model.  At the
-// FP64 rate that is ~9 TB/s of theta traffic, more than HBM delivers, and the chains resident on the GPU (4 CTAs x 128
-// threads x 148 SMs x 1.6 KB = 121 MB) do not stay in L2: the ncu capture of round 2 shows 3.05 TB/s of DRAM traffic, L2
-// hit 63 %, FP64 pipe 37 % (profiles/r02_summary.md).  Here one CTA per SM holds its chains' theta in shared memory for
-// the whole launch (blockDim x npar doubles, element k of thread t at th[k * blockDim + t]: conflict-free), so a move
-// touches no global memory except the rotation's column:
+// k5_scam_step_kernel (one thread per chain) keeps theta in local memory: a component move reads the npar elements once
+// for the model and, when the move is accepted, rewrites them -- 3.2 KB per move at npar = 200 against ~5800 FP64
+// instructions.  At the FP64 rate that is ~9 TB/s of theta traffic, and the chains resident on the GPU (4 CTAs x 128
+// threads x 148 SMs x 1.6 KB = 121 MB) do not stay in L2: 3.05 TB/s of DRAM traffic, L2 hit 63 %, FP64 pipe 37 %, the
+// board at its power cap (profiles/r02_summary.md).  Here one CTA per SM holds 128 chains' theta in shared memory for the
+// whole launch (element k of slot s at th[k * 128 + s'], s' = s rotated inside its group of 16 slots by (k mod L) * 16 / L:
+// the 16 addresses of a half-warp -- L consecutive rows x 16 / L neighbouring slots -- fall into 16 different bank pairs),
+// and a move touches no global memory except the rotation's column:
 //
-//   * U(:,j) is the same for every chain of the population (pooled rotation, stride 0).  Each warp stages the column
-//     of its current move in its own shared buffer; the column of the NEXT move is fetched into registers while the model
-//     runs, so its L2 latency is never exposed (a warp is alone on its scheduler here: nothing else would hide it);
-//   * the model evaluates the view theta + delta U(:,j) (ssfunction_view<V>, mcmcb200_model.cuh) with V::ILP = 8
-//     accumulation chains in flight: with four warps per SM the instruction-level parallelism has to come from the
-//     thread itself (255 registers are available to it);
-//   * an accepted move rewrites theta in shared memory.
+//   * U(:,j) and qcovstd(j) are the same for every chain (pooled rotation, stride 0).  The CTA keeps two column buffers:
+//     every thread fetches its share of the NEXT move's column into a register at the start of a move (the L2 latency
+//     runs under the model), publishes it after the accept step, and one __syncthreads per move flips the buffers.
+//     Dropping the barrier and reading the column through L1 was measured slower (5.10 s against 4.50 s per 100 sweeps);
+//   * L lanes share a chain (default 4): they take the model's groups round-robin (mcmcb_ctx::lane / nlanes), their
+//     partial sums are added with a shuffle butterfly (every lane gets the same bits), each lane rewrites its own elements
+//     of theta on acceptance; the chain's generator runs on all of its lanes (same draws, same decisions, no extra issue
+//     slots: the lanes sit in one warp).  128 threads per CTA (L = 1) leave one warp per scheduler: latency-bound;
+//   * C chains per thread (default 2) go through the model in ONE sweep over its data (optional model member
+//     ssfunction_view_batch<C, V>): with one chain per thread the kernel is bound by shared-memory wavefronts (a 64-bit
+//     shared load costs two wavefronts whatever its addresses: ncu, L1 data stage 90 % busy, 2.3e9 wavefronts per
+//     wave), the datum loads being 2/3 of them.
 //
 // Draw order, acceptance rule, row logging and the state layout are k5_scam_step_kernel's (MCMC_run_scam.F90:26-88): both
-// kernels apply, element by element, the fma sequence of an eager update, so they agree to the last bit
-// (tests/test_r02_coverage.py).  Models without ssfunction_view, private rotations and populations whose theta does not
-// fit stay on the other kernels.
+// kernels apply, element by element, the fma sequence of an eager update.  With L = 1 they agree to the last bit; with
+// L > 1 the sum of squares is the sum of the lanes' partial sums (rounding-level differences, as in the warp-per-chain
+// kernel); C does not change a bit (tests/test_r02_coverage.py).  Models without ssfunction_view, private rotations and
+// populations whose theta does not fit stay on the other kernels.
 #pragma once
 #include "k5_scam.cuh"
 
@@ -40,7 +48,7 @@ template <int W, int L>
 struct K5SView {
   static constexpr int ILP = W;
   const double* th;  // shared: the CTA's theta block
-  const double* u;   // global (L1): the rotation's column of the current move, the same for every chain
+  const double* u;   // shared: the column of the CTA's current move
   double dl;
   int NC, s;
   __device__ __forceinline__ double operator[](int k) const { return fma(u[k], dl, th[k5s_at<L>(k, s, NC)]); }
@@ -54,9 +62,10 @@ struct has_ssfunction_view_batch<M, decltype((void)&M::template ssfunction_view_
   static constexpr bool value = true;
 };
 
-// bytes of dynamic shared memory: blob | theta
+// bytes of dynamic shared memory: blob | two column buffers (npar + 1 doubles each: U(:,j) and qcovstd(j)) | theta
 __host__ __device__ __forceinline__ size_t k5s_smem_bytes(int d, int chains, size_t blob_bytes) {
-  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * ((size_t)d * chains);
+  const size_t dp2 = (size_t)(d + 2) & ~(size_t)1;
+  return ((blob_bytes + 15) & ~(size_t)15) + sizeof(double) * (2 * dp2 + (size_t)d * chains);
 }
 
 template <int L>
@@ -97,14 +106,16 @@ template <class M, int W, int L, int C>
 __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(const __grid_constant__ K2Params p) {
   constexpr int NY = M::NY;
   constexpr K2Layout Lo = k2_layout(NY);
+  constexpr int NPF = (K4_DM * C + 64 * L - 1) / (64 * L);  // column elements a thread carries (blockDim >= 64 L / C)
   using View = K5SView<W, L>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   tma_stage_blob(smem_raw, p.blob, p.blob_bytes, &mbar);  // every thread of the CTA takes part (barrier inside)
   const double* data = reinterpret_cast<const double*>(smem_raw);
   const int d = p.d, T = blockDim.x, NT = T / L, NC = NT * C, tid = threadIdx.x, grp = tid / L, sub = tid % L;
-  const int lane = tid & 31;
-  double* th = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
+  const int dp2 = (d + 2) & ~1;
+  double* ucol = reinterpret_cast<double*>(smem_raw + (((size_t)p.blob_bytes + 15) & ~(size_t)15));
+  double* th = ucol + 2 * (size_t)dp2;
   const DevCfg& c = p.c;
   const size_t P = (size_t)p.pitch;
   const double* U = p.Rm;    // shared rotation, column-major: column j at U + j d
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
     g.has_spare = ist[Lo.i_hasspare * P] != 0;
     g.spare = st[Lo.spare * P];
     g.exhausted = 0;
-    tv[i].th = th; tv[i].u = U; tv[i].dl = 0.0; tv[i].NC = NC; tv[i].s = s;
+    tv[i].th = th; tv[i].u = ucol + dp2; tv[i].dl = 0.0; tv[i].NC = NC; tv[i].s = s;
   }
 
   // C views -> C sums of squares (summed over the chain's lanes) and C priors
@@ -163,8 +174,10 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
       for (int k = 0; k < NY; k++) ssn[i][k] = k5s_lanes_sum<L>(ssn[i][k]);
   };
 
-  __syncwarp();  // the chain's lanes have written its theta (a chain never spans two warps: no CTA barrier anywhere below)
-  // the current point as a view: a zero move along column 0 (theta + 0 U = theta)
+  // buffer 0 <- column 0 and its scale; buffer 1 <- zeros (the current point as a view: a zero move along a zero column)
+  for (int k = tid; k < d; k += T) { ucol[k] = U[k]; ucol[dp2 + k] = 0.0; }
+  if (tid == 0) ucol[d] = gq[0];
+  __syncthreads();
   if (ch[0].simuind == 0) {  // MCMC_run_scam.F90:26-36: initial point, saved as row 1 (every chain of a launch starts together)
     double ssn[C][NY], prn[C];
     evaluate(ssn, prn);
@@ -188,20 +201,25 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
       }
     }
   }
+  __syncthreads();  // nobody reads the zero column any more: it becomes the buffer of move 1
 
+  int jb = 0;
   for (int done = 0; done < p.nsteps; done++) {
 #pragma unroll
     for (int i = 0; i < C; i++) { ch[i].rejall = true; ch[i].logged = false; }
     for (int j = 0; j < d; j++) {
-      // U(:,j) comes through L1 (every warp of the CTA is within a few moves of the same j: 1.6 KB per column); the
-      // next column's lines are requested now so that no warp waits for L2 at the start of its next move
-      const double* uc = U + (size_t)j * d;
+      const double* uc = ucol + (size_t)jb * dp2;
+      // ---- the next move's column and scale start their trip from L2 now and are published after this move
+      double pf[NPF], qn = 0.0;
       {
-        const double* ncol = U + (size_t)(j + 1 < d ? j + 1 : 0) * d;
-        if (lane * 16 < d) asm volatile("prefetch.global.L1 [%0];" ::"l"(ncol + lane * 16));
+        const int jn = j + 1 < d ? j + 1 : 0;
+        const double* ncol = U + (size_t)jn * d;
+#pragma unroll
+        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; pf[i] = k < d ? ncol[k] : 0.0; }
+        if (tid == 0) qn = gq[jn];
       }
       // MCMC_propose_sc (MCMC_run_scam.F90:94-117) in the O(d) form theta + delta U(:,j)
-      const double qj = gq[j];
+      const double qj = uc[d];
 #pragma unroll
       for (int i = 0; i < C; i++) { tv[i].u = uc; tv[i].dl = ch[i].g.normal() * qj; }
       double ssn[C][NY], prn[C];
@@ -241,7 +259,16 @@ __global__ void __launch_bounds__(K5S_CHAINS * L / C, 1) k5s_scam_step_kernel(co
           q.rejall = false;
         }
       }
-      __syncwarp();  // theta elements written by one lane of a chain are read by the others in the next move
+      // ---- publish the next column (its buffer was last read during the previous move) and meet: theta elements
+      // written by one lane of a chain are read by the others in the next move
+      {
+        double* un = ucol + (size_t)(jb ^ 1) * dp2;
+#pragma unroll
+        for (int i = 0; i < NPF; i++) { const int k = tid + T * i; if (k < d) un[k] = pf[i]; }
+        if (tid == 0) un[d] = qn;
+      }
+      __syncthreads();
+      jb ^= 1;
     }
     // ---------------- end of sweep, MCMC_run_scam.F90:74-86
 #pragma unroll
