@@ -918,7 +918,7 @@ struct K2 {
     } else {
       const int nv = phase == 1 ? 1 + d : d * d;
       double* out = phase == 1 ? h->d_pool : h->d_pool + 1 + d;
-      if (phase == 2 && h->cfg.method != MCMCB_RAM) {  // (tile, slice) grid, four chains in flight per thread
+      if (phase == 2 && h->cfg.method != MCMCB_RAM && d >= 64) {  // (tile, slice) grid, four chains in flight per thread
         const int S = pool_cov_slices(d), ntile = (d + POOL_COV_TB - 1) / POOL_COV_TB;
         k2_pool_cov_kernel<<<ntile * S, POOL_THREADS, 0, h->stream>>>(p, h->d_pool, h->d_pool_partial);
         pool_final_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_pool_partial, S, nv, out);

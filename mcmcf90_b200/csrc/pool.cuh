@@ -172,23 +172,32 @@ static __global__ void __launch_bounds__(POOL_THREADS) k2_pool_moments_kernel(K2
     }
     return;
   }
-  // phase 2, RAM: sum of R'R (the covariance modes run k2_pool_cov_kernel)
+  // phase 2: RAM (sum of R'R), and the covariance modes at small npar (from npar = 64 up they run k2_pool_cov_kernel)
   const int nv = d * d;
+  const double W = buf[0];
   for (int v = threadIdx.x; v < nv; v += blockDim.x) {
     const int b = v / d, a = v - b * d;  // entry (a, b), column-major; symmetric result
     const int lo = a < b ? a : b, hi = a < b ? b : a;
     double acc = 0.0;
-    for (long long c = blockIdx.x; c < p.nchains; c += gridDim.x) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
-      const double* R = p.Rm + (size_t)c * p.r_stride;
-      double s = 0.0;
-      for (int i = 0; i <= lo; i++) s = fma(R[(size_t)i * d + lo], R[(size_t)i * d + hi], s);
-      acc += s;
+    for (long long c = blockIdx.x; c < p.nchains; c += gridDim.x) {
+      if (ram) {  // (R'R)(a,b) = sum_{i <= min(a,b)} R(i,a) R(i,b); R row-major upper
+        const double* R = p.Rm + (size_t)c * p.r_stride;
+        double s = 0.0;
+        for (int i = 0; i <= lo; i++) s = fma(R[(size_t)i * d + lo], R[(size_t)i * d + hi], s);
+        acc += s;
+      } else {
+        const double w = p.st[Lo.wsum * p.pitch + c];
+        if (!(w > 0.0)) continue;
+        const double da = p.mean[c * p.dp + a] - buf[1 + a] / W, db = p.mean[c * p.dp + b] - buf[1 + b] / W;
+        // cmat is kept symmetric by the recursion (cta_absorb updates every entry)
+        acc += (w - 1.0) * p.cmat[(size_t)c * d * d + (size_t)lo * d + hi] + w * (da * db);
+      }
     }
     partial[(size_t)blockIdx.x * nv + v] = acc;
   }
 }
 
-// Phase 2 of the covariance modes at large populations: CTA (tile, slice) owns rows b0 .. b0+3 of the result and the
+// Phase 2 of the covariance modes from npar = 64 up: CTA (tile, slice) owns rows b0 .. b0+3 of the result and the
 // chains slice, slice + S, ...; thread a owns the four entries (a, b0 + q).  A chain costs a thread ONE mean element of its
 // own (the four mean(b) are uniform), four consecutive-address covariance reads and four independent accumulators; four
 // chains are in flight, so 16 covariance loads per thread are outstanding (84 GB at BASELINE C5: the layout of

@@ -73,9 +73,11 @@ def test_pooled_dram_register_kernel_matches_lockstep_oracle():
     s.close()
 
 
-@pytest.mark.parametrize("variant", ["dram", "am", "svd"])
-def test_pooled_large_npar_kernel_matches_lockstep_oracle(variant):
-    d, N = 12, 40
+@pytest.mark.parametrize("variant,d", [("dram", 12), ("am", 12), ("svd", 12), ("am", 66)])
+def test_pooled_large_npar_kernel_matches_lockstep_oracle(variant, d):
+    # d = 66: the (tile, slice) second-moment kernel (k2_pool_cov_kernel, from npar = 64 up; 66 leaves a ragged tile) and
+    # the shared-memory-resident covariance tick (k2_absorb_resident_kernel) in pooled mode
+    N = 40
     mu, lam = gauss_target(d)
     blob = mb.models.blob_gauss(mu, lam)
     nml = dict(nsimu=301, adaptint=60, initcmatn=1, updatesigma=0, drscale=2.0 if variant == "dram" else 0.0,
