@@ -134,6 +134,22 @@ def test_dram_large_dim_two_ticks():
     compare(a, b, rtol=1e-8)
 
 
+@pytest.mark.parametrize("nml", [
+    dict(nsimu=301, adaptint=50, drscale=0.0, condmax=1e12, initcmatn=1, updatesigma=0),                 # AM, usesvd
+    dict(nsimu=301, adaptint=40, adapthist=60, drscale=0.0, condmax=1e10, initcmatn=1, updatesigma=0),   # AP window -> SVD
+    dict(method="scam", nsimu=201, adaptint=40, adapthist=60, initcmatn=1, updatesigma=0),               # SCAM + AP window
+], ids=["am_usesvd", "ap_usesvd", "scam_ap"])
+def test_svd_factor_modes_on_a_correlated_gaussian(nml):
+    """covtor_svd / scam_svd (matutils.F90:378-453, 583-653) behind AM with condmax > 0 and behind SCAM, fed by the plain
+    recursion and by the AP window (MCMC_adapt.F90:116-136): the C oracle's restated Jacobi against LAPACK's dgesvd."""
+    d = 6
+    mu, lam = G.gauss_target(d)
+    u = np.random.default_rng(7).random(20 * 301 * d * 2)
+    a, b = run_both(nml, O.MODEL_GAUSS, O.blob_gauss(mu, lam), R2.Gauss(mu, lam), 0.1 * np.ones(d), 0.05 * np.eye(d), [1.0], [1], u)
+    assert b.usesvd and a["chainind"] > 100
+    compare(a, b, svd=True)
+
+
 def test_mat4_writer_reproduces_reference_fixture(tmp_path):
     """testcases/data.mat is the reference's own MAT-v4 image of testcases/data.dat (header 0,11,2,0,5,"data\\0",
     column-major float64; matfiles.F90:41-48,66-126): the writer must reproduce it byte for byte."""
